@@ -1,0 +1,118 @@
+/* lqmpc_b200.h — C ABI of the B200-native batch engine for the lq_mpc hot path.
+ *
+ * The reference (lcrekko/lq_mpc) has no FFI/plugin boundary: its boundary is its Python surface
+ * (utils_class.py / utils.py).  Each entry point below is the *batched* replacement of the per-sample reference
+ * call it cites; `lq_mpc_b200/utils_class.py` and `lq_mpc_b200/utils.py` keep the reference's class and function
+ * signatures and bind these symbols through ctypes (see INTEGRATION.md for the stub a maintainer would add).
+ *
+ * Conventions
+ *   - plain C, no torch types; every pointer is a DEVICE pointer to FP64 data unless the name ends in `_host`.
+ *   - batched operands are struct-of-arrays: element e of sample s lives at  ptr[e * S + s]  (row-major element
+ *     order inside a matrix, e = i*cols + j), so a warp reads 32 consecutive samples of one element: coalesced.
+ *   - all work is enqueued on the context's CUDA stream; nothing synchronises unless stated.
+ *   - return value: 0 on success, negative LQMPC_E* on error (never throws); lqmpc_last_error() gives the text.
+ *   - there is NO CPU path: every function fails with LQMPC_ENODEVICE when no CUDA device is usable.
+ *   - a context is not thread-safe; distinct contexts are independent.
+ */
+#ifndef LQMPC_B200_H
+#define LQMPC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LQMPC_OK 0
+#define LQMPC_EINVAL (-1)     /* bad argument / unsupported size        */
+#define LQMPC_ENODEVICE (-2)  /* no usable CUDA device                  */
+#define LQMPC_ECUDA (-3)      /* a CUDA runtime call failed             */
+#define LQMPC_ESTATE (-4)     /* problem not set                        */
+
+/* per-eval status bits written to the int32 `flags` outputs */
+#define LQMPC_FLAG_UNSTABLE 1
+#define LQMPC_FLAG_QP_ACTIVE 2
+#define LQMPC_FLAG_QP_MAXITER 4
+#define LQMPC_FLAG_DARE_NOCONV 8
+#define LQMPC_FLAG_NONFINITE 16
+#define LQMPC_FLAG_BOUND_INVALID 32
+#define LQMPC_FLAG_LYAP_NOCONV 64
+#define LQMPC_FLAG_EIG_NOCONV 128
+#define LQMPC_FLAG_CHOL_FAIL 256
+
+typedef struct lqmpc_ctx lqmpc_ctx;
+
+/* ABI version (bumped on any signature change) and the list of compiled (n, m) pairs, e.g. "2x1,4x2". */
+int lqmpc_abi_version(void);
+const char* lqmpc_supported_dims(void);
+
+/* One context per (device, stream). `cuda_stream` is a cudaStream_t (NULL = the legacy default stream). */
+int lqmpc_create(lqmpc_ctx** out, int device, void* cuda_stream);
+void lqmpc_destroy(lqmpc_ctx* ctx);
+const char* lqmpc_last_error(const lqmpc_ctx* ctx);
+int lqmpc_sync(lqmpc_ctx* ctx);
+
+/* Problem data shared by every sample (HOST pointers, row-major FP64): the TRUE plant (A n x n, B n x m), the
+ * stage weights Q, R, the terminal weight P (every reference caller passes P = Q), the input box u_lo <= u <= u_hi
+ * (both NULL: unconstrained) and N_opc, the horizon of the expert open-loop cost V_expert (<=0: DARE limit).
+ * Replaces the constructor arguments of LQ_MPC_Controller / LQ_MPC_Simulator / LQ_RDP_Calculator /
+ * LQ_RDP_Behavior_Multiple (utils_class.py:23, 218, 293, 691-764). The derived constants (Q^-1, eigenvalue
+ * extremes, V_expert's matrix) are computed ON THE DEVICE by a one-thread preparation kernel. */
+int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A_true_host, const double* B_true_host,
+                      const double* Q_host, const double* R_host, const double* P_term_host,
+                      const double* u_lo_host, const double* u_hi_host, int N_opc);
+
+/* Copy the device-prepared constants back: Pexp (n*n), then Qinv (n*n), then maxQ,minQ,maxR,minR. Synchronises. */
+int lqmpc_get_prepared(lqmpc_ctx* ctx, double* out_host, int64_t capacity);
+
+/* K1 — unconstrained certainty-equivalent MPC evaluation, nested horizons N_min..N_max (H = N_max-N_min+1 columns).
+ * Per (sample s, horizon N): Riccati gain K_0 on (A+dA_s, B+dB_s); closed loop A_cl = A + B K_0 on the true plant;
+ * rho(A_cl); J_inf = x0' S x0 (Lyapunov squared doubling; +inf and LQMPC_FLAG_UNSTABLE if rho >= 1);
+ * ratio = J_inf / V_expert(x0); optionally J_T (T > 0; the finite sum of utils_class.py:261,282-283), the open-loop
+ * value V_N = x0' P_0 x0 (utils_class.py:91) and the gain itself.
+ * Replaces, for the unconstrained law, LQ_MPC_Controller.solve (utils_class.py:48-91) +
+ * LQ_MPC_Simulator.simulate (utils_class.py:245-285) inside the sweep loops (utils_class.py:802-833, 886-916).
+ *   dA [n*n][S], dB [n*m][S], x0 [n][S]            inputs
+ *   J, rho, ratio, V_N, J_T : [H][S] (any may be NULL; J_T requires T > 0), flags [H][S] int32 (may be NULL),
+ *   K0 [H][m*n][S] (may be NULL) */
+int lqmpc_eval_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, const double* x0, int N_min,
+                     int N_max, int T, double* J, double* rho, double* ratio, double* V_N, double* J_T,
+                     int32_t* flags, double* K0);
+
+/* Same computation driven from HOST buffers (pinned or pageable): the batch is cut into chunks that are copied
+ * H2D, evaluated and copied back D2H on alternating streams so copies overlap compute. All pointers are HOST
+ * pointers with the same SoA layout over the full S. Synchronises before returning. This is the call `bench.py`
+ * times for the end-to-end figure. */
+int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host, const double* dB_host,
+                          const double* x0_host, int N_min, int N_max, int T, double* J_host, double* rho_host,
+                          double* ratio_host, int32_t* flags_host, int64_t chunk);
+
+/* K2a — batched LQ_MPC_Controller.solve (utils_class.py:48-91) with the input box of lqmpc_set_problem, zero
+ * references, terminal weight P: for every sample the controller model is (A+dA_s, B+dB_s) (dA/dB NULL = the true
+ * model, e.g. for V_expert, utils_class.py:786). The QP is solved EXACTLY (Riccati-structured primal active set).
+ * Initial states: either `pts` — npts states shared by all samples, device [npts][n] (the ring of
+ * OL_energy_bound, utils_class.py:439-466) — or `x0`, one state per sample, device [n][S] (then P = 1).
+ *   V [P][S] open-loop value V_N (incl. x0'Qx0), u0 [P][m][S] first input, M_V [S] = max_p V (utils_class.py:464),
+ *   flags [P][S]; any output may be NULL. Needs N*m <= 64 whenever a bound is active. */
+int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int npts,
+                          const double* pts, const double* x0, double* V, double* u0, double* M_V, int32_t* flags);
+
+/* K2b — batched LQ_MPC_Simulator.simulate (utils_class.py:245-285): T receding-horizon steps, the controller plans
+ * with (A+dA_s, B+dB_s) and horizon N, the plant is the TRUE model; J_T as accumulated at utils_class.py:261,282-283.
+ * Initial state: `x0_shared` device [n] (one state for all samples) or `x0` device [n][S].
+ *   J_T [S], X [T+1][n][S], U [T][m][S], flags [S], n_active [S] (steps whose QP had an active bound); NULL = skip. */
+int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int T,
+                         const double* x0_shared, const double* x0, double* J_T, double* X, double* U,
+                         int32_t* flags, int32_t* n_active);
+
+/* DFMA-chain micro-benchmark: achieved FP64 FMA throughput of this device in TFLOP/s (2 flop per FMA), used as the
+ * measured denominator of the FP64 roofline (MEASURED_PEAKS.json has none). Synchronises. */
+int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out);
+
+/* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
+int64_t lqmpc_launch_count(const lqmpc_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LQMPC_B200_H */

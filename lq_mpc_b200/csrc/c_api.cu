@@ -1,0 +1,318 @@
+// c_api.cu — the extern "C" boundary declared in include/lqmpc_b200.h.
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+
+#include "../../include/lqmpc_b200.h"
+#include "engine.h"
+
+int lq_set_error(lqmpc_ctx* ctx, int code, const char* what) {
+  if (ctx) ctx->err = what ? what : "";
+  return code;
+}
+
+int lq_check_cuda(lqmpc_ctx* ctx, cudaError_t e, const char* what) {
+  if (e == cudaSuccess) return LQMPC_OK;
+  if (ctx) {
+    ctx->err = std::string(what ? what : "cuda") + ": " + cudaGetErrorString(e);
+  }
+  return LQMPC_ECUDA;
+}
+
+int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes) {
+  if (bytes <= ctx->ws_bytes) return LQMPC_OK;
+  if (ctx->ws) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->ws);
+    ctx->ws = nullptr;
+    ctx->ws_bytes = 0;
+  }
+  size_t want = bytes + bytes / 4;
+  int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->ws, want), "cudaMalloc workspace");
+  if (rc) return rc;
+  ctx->ws_bytes = want;
+  return LQMPC_OK;
+}
+
+namespace {
+
+// Packs the host problem description into the byte image of lq::Problem<n,m> (field order of riccati.cuh).
+template <int n, int m>
+void pack_problem(lqmpc_ctx* ctx, const double* A, const double* B, const double* Q, const double* R,
+                  const double* P, const double* lo, const double* hi) {
+  lq::Problem<n, m> pb;
+  memset(&pb, 0, sizeof(pb));
+  memcpy(pb.A, A, sizeof(pb.A));
+  memcpy(pb.B, B, sizeof(pb.B));
+  memcpy(pb.Q, Q, sizeof(pb.Q));
+  memcpy(pb.R, R, sizeof(pb.R));
+  memcpy(pb.Pt, P, sizeof(pb.Pt));
+  pb.has_bounds = (lo != nullptr || hi != nullptr) ? 1 : 0;
+  for (int j = 0; j < m; ++j) {
+    pb.ulo[j] = lo ? lo[j] : -HUGE_VAL;
+    pb.uhi[j] = hi ? hi[j] : HUGE_VAL;
+  }
+  memcpy(ctx->pb, &pb, sizeof(pb));
+}
+
+int ensure_pipe(lqmpc_ctx* ctx, size_t bytes_per_slot) {
+  for (int i = 0; i < 2; ++i) {
+    if (!ctx->pipe_stream[i]) {
+      int rc = lq_check_cuda(ctx, cudaStreamCreateWithFlags(&ctx->pipe_stream[i], cudaStreamNonBlocking),
+                             "pipe stream");
+      if (rc) return rc;
+      rc = lq_check_cuda(ctx, cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming), "pipe event");
+      if (rc) return rc;
+    }
+  }
+  if (bytes_per_slot > ctx->pipe_bytes) {
+    for (int i = 0; i < 2; ++i) {
+      if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
+      ctx->pipe_buf[i] = nullptr;
+    }
+    ctx->pipe_bytes = 0;
+    for (int i = 0; i < 2; ++i) {
+      int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->pipe_buf[i], bytes_per_slot), "cudaMalloc pipeline slot");
+      if (rc) return rc;
+    }
+    ctx->pipe_bytes = bytes_per_slot;
+  }
+  return LQMPC_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int lqmpc_abi_version(void) { return 1; }
+
+const char* lqmpc_supported_dims(void) { return LQ_DIMS_STRING; }
+
+int lqmpc_create(lqmpc_ctx** out, int device, void* cuda_stream) {
+  if (!out) return LQMPC_EINVAL;
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count <= 0 || device < 0 || device >= count) return LQMPC_ENODEVICE;
+  if (cudaSetDevice(device) != cudaSuccess) return LQMPC_ENODEVICE;
+  lqmpc_ctx* ctx = new (std::nothrow) lqmpc_ctx();
+  if (!ctx) return LQMPC_EINVAL;
+  ctx->device = device;
+  // NULL is the legacy default stream (what torch.cuda.current_stream() is unless the caller changed it)
+  ctx->stream = reinterpret_cast<cudaStream_t>(cuda_stream);
+  ctx->own_stream = false;
+  *out = ctx;
+  return LQMPC_OK;
+}
+
+void lqmpc_destroy(lqmpc_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->pb_dev) cudaFree(ctx->pb_dev);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
+    if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+    if (ctx->pipe_stream[i]) cudaStreamDestroy(ctx->pipe_stream[i]);
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+const char* lqmpc_last_error(const lqmpc_ctx* ctx) { return ctx ? ctx->err.c_str() : "null context"; }
+
+int lqmpc_sync(lqmpc_ctx* ctx) {
+  if (!ctx) return LQMPC_EINVAL;
+  return lq_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "stream sync");
+}
+
+int64_t lqmpc_launch_count(const lqmpc_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const double* B, const double* Q,
+                      const double* R, const double* P, const double* lo, const double* hi, int N_opc) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!A || !B || !Q || !R || !P) return lq_set_error(ctx, LQMPC_EINVAL, "null problem matrix");
+  cudaSetDevice(ctx->device);
+  bool found = false;
+#define X(N_, M_)                                   \
+  if (n == N_ && m == M_) {                         \
+    pack_problem<N_, M_>(ctx, A, B, Q, R, P, lo, hi); \
+    found = true;                                   \
+  }
+  LQ_FOR_EACH_DIM(X)
+#undef X
+  if (!found) return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
+  ctx->n = n;
+  ctx->m = m;
+  ctx->N_opc = N_opc;
+  ctx->has_problem = false;
+  int rc = lq_launch_prepare(ctx);
+  if (rc) return rc;
+  ctx->has_problem = true;
+  return LQMPC_OK;
+}
+
+int lqmpc_get_prepared(lqmpc_ctx* ctx, double* out, int64_t capacity) {
+  if (!ctx || !out) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  const int n = ctx->n;
+  if (capacity < 2 * n * n + 4) return lq_set_error(ctx, LQMPC_EINVAL, "capacity too small");
+  bool done = false;
+#define X(N_, M_)                                                                       \
+  if (!done && ctx->n == N_ && ctx->m == M_) {                                          \
+    const lq::Problem<N_, M_>& pb = *reinterpret_cast<const lq::Problem<N_, M_>*>(ctx->pb); \
+    memcpy(out, pb.Pexp, sizeof(pb.Pexp));                                              \
+    memcpy(out + N_ * N_, pb.Qinv, sizeof(pb.Qinv));                                    \
+    out[2 * N_ * N_ + 0] = pb.maxQ;                                                     \
+    out[2 * N_ * N_ + 1] = pb.minQ;                                                     \
+    out[2 * N_ * N_ + 2] = pb.maxR;                                                     \
+    out[2 * N_ * N_ + 3] = pb.minR;                                                     \
+    done = true;                                                                        \
+  }
+  LQ_FOR_EACH_DIM(X)
+#undef X
+  return done ? LQMPC_OK : LQMPC_EINVAL;
+}
+
+int lqmpc_eval_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, const double* x0, int N_min,
+                     int N_max, int T, double* J, double* rho, double* ratio, double* V_N, double* J_T,
+                     int32_t* flags, double* K0) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || N_min < 1 || N_max < N_min || T < 0) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N_min/N_max/T");
+  if (S == 0) return LQMPC_OK;
+  if (!dA || !dB || !x0) return lq_set_error(ctx, LQMPC_EINVAL, "null input");
+  if (J_T && T <= 0) return lq_set_error(ctx, LQMPC_EINVAL, "J_T requested with T <= 0");
+  cudaSetDevice(ctx->device);
+  EvalArgs a;
+  a.S = S; a.ld = S; a.dA = dA; a.dB = dB; a.x0 = x0;
+  a.N_min = N_min; a.N_max = N_max; a.T = J_T ? T : 0;
+  a.J = J; a.rho = rho; a.ratio = ratio; a.Vn = V_N; a.JT = J_T; a.flags = flags; a.K0 = K0;
+  return lq_launch_eval(ctx, a, ctx->stream);
+}
+
+int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const double* dB_h, const double* x0_h,
+                          int N_min, int N_max, int T, double* J_h, double* rho_h, double* ratio_h,
+                          int32_t* flags_h, int64_t chunk) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || N_min < 1 || N_max < N_min) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N_min/N_max");
+  if (S == 0) return LQMPC_OK;
+  if (!dA_h || !dB_h || !x0_h) return lq_set_error(ctx, LQMPC_EINVAL, "null input");
+  (void)T;
+  cudaSetDevice(ctx->device);
+  const int n = ctx->n, m = ctx->m;
+  const int H = N_max - N_min + 1;
+  if (chunk <= 0) chunk = 1 << 20;
+  if (chunk > S) chunk = S;
+  chunk = (chunk + 31) / 32 * 32;
+  const int64_t in_rows = (int64_t)n * n + (int64_t)n * m + n;
+  const int64_t out_rows = 3 * (int64_t)H;  // J, rho, ratio
+  const size_t slot = (size_t)chunk * 8 * (size_t)(in_rows + out_rows) + (size_t)chunk * 4 * (size_t)H;
+  int rc = ensure_pipe(ctx, slot);
+  if (rc) return rc;
+  // the caller's stream must be idle w.r.t. these buffers: order the pipeline after it
+  rc = lq_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "pre-pipeline sync");
+  if (rc) return rc;
+  int64_t nchunks = (S + chunk - 1) / chunk;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    cudaStream_t st = ctx->pipe_stream[b];
+    const int64_t s0 = c * chunk;
+    const int64_t cs = (s0 + chunk <= S) ? chunk : (S - s0);
+    double* base = reinterpret_cast<double*>(ctx->pipe_buf[b]);
+    double* d_dA = base;
+    double* d_dB = d_dA + (int64_t)n * n * chunk;
+    double* d_x0 = d_dB + (int64_t)n * m * chunk;
+    double* d_J = d_x0 + (int64_t)n * chunk;
+    double* d_rho = d_J + (int64_t)H * chunk;
+    double* d_ratio = d_rho + (int64_t)H * chunk;
+    int32_t* d_flags = reinterpret_cast<int32_t*>(d_ratio + (int64_t)H * chunk);
+    const size_t w = (size_t)cs * 8, dp = (size_t)chunk * 8, sp = (size_t)S * 8;
+    // stream order makes slot reuse safe: chunk c+2 is enqueued on the same stream after chunk c's D2H
+    rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_dA, dp, dA_h + s0, sp, w, (size_t)n * n, cudaMemcpyHostToDevice, st),
+                       "H2D dA");
+    if (rc) return rc;
+    rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_dB, dp, dB_h + s0, sp, w, (size_t)n * m, cudaMemcpyHostToDevice, st),
+                       "H2D dB");
+    if (rc) return rc;
+    rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_x0, dp, x0_h + s0, sp, w, (size_t)n, cudaMemcpyHostToDevice, st),
+                       "H2D x0");
+    if (rc) return rc;
+    EvalArgs a;
+    a.S = cs; a.ld = chunk; a.dA = d_dA; a.dB = d_dB; a.x0 = d_x0;
+    a.N_min = N_min; a.N_max = N_max; a.T = 0;
+    a.J = J_h ? d_J : nullptr; a.rho = rho_h ? d_rho : nullptr; a.ratio = ratio_h ? d_ratio : nullptr;
+    a.Vn = nullptr; a.JT = nullptr; a.flags = flags_h ? d_flags : nullptr; a.K0 = nullptr;
+    rc = lq_launch_eval(ctx, a, st);
+    if (rc) return rc;
+    if (J_h) {
+      rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(J_h + s0, sp, d_J, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st),
+                         "D2H J");
+      if (rc) return rc;
+    }
+    if (rho_h) {
+      rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(rho_h + s0, sp, d_rho, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st),
+                         "D2H rho");
+      if (rc) return rc;
+    }
+    if (ratio_h) {
+      rc = lq_check_cuda(
+          ctx, cudaMemcpy2DAsync(ratio_h + s0, sp, d_ratio, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st), "D2H ratio");
+      if (rc) return rc;
+    }
+    if (flags_h) {
+      rc = lq_check_cuda(ctx,
+                         cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)chunk * 4, (size_t)cs * 4,
+                                           (size_t)H, cudaMemcpyDeviceToHost, st),
+                         "D2H flags");
+      if (rc) return rc;
+    }
+  }
+  for (int b = 0; b < 2; ++b) {
+    rc = lq_check_cuda(ctx, cudaStreamSynchronize(ctx->pipe_stream[b]), "pipeline sync");
+    if (rc) return rc;
+  }
+  return LQMPC_OK;
+}
+
+int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int npts,
+                          const double* pts, const double* x0, double* V, double* u0, double* M_V, int32_t* flags) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || N < 1) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N");
+  if (S == 0) return LQMPC_OK;
+  if ((pts == nullptr) == (x0 == nullptr)) return lq_set_error(ctx, LQMPC_EINVAL, "give exactly one of pts / x0");
+  if (pts && npts < 1) return lq_set_error(ctx, LQMPC_EINVAL, "npts < 1");
+  cudaSetDevice(ctx->device);
+  MpcArgs a{};
+  a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.T = 0; a.npts = npts; a.pts = pts; a.x0 = x0;
+  a.V = V; a.u0 = u0; a.M_V = M_V; a.flags = flags;
+  return lq_launch_mpc(ctx, a, false);
+}
+
+int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int T,
+                         const double* x0_shared, const double* x0, double* J_T, double* X, double* U,
+                         int32_t* flags, int32_t* n_active) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || N < 1 || T < 0) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N/T");
+  if (S == 0) return LQMPC_OK;
+  if ((x0_shared == nullptr) == (x0 == nullptr))
+    return lq_set_error(ctx, LQMPC_EINVAL, "give exactly one of x0_shared / x0");
+  cudaSetDevice(ctx->device);
+  MpcArgs a{};
+  a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.T = T; a.npts = 1; a.pts = x0_shared; a.x0 = x0;
+  a.J_T = J_T; a.X = X; a.U = U; a.flags = flags; a.n_active = n_active;
+  return lq_launch_mpc(ctx, a, true);
+}
+
+int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return LQMPC_EINVAL;
+  cudaSetDevice(ctx->device);
+  return lq_launch_fp64_peak(ctx, tflops_out);
+}
+
+}  // extern "C"

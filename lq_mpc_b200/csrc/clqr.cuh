@@ -1,0 +1,354 @@
+// clqr.cuh — exact solution of the input-box-constrained finite-horizon LQ problem, one sample per thread.
+//
+// Reference semantics: LQ_MPC_Controller.solve (utils_class.py:48-91) with zero references builds
+//     min_{u_0..u_{N-1}}  sum_{k<N} ( x_{k+1}' W_{k+1} x_{k+1} + u_k' R u_k ),  W_k = Q (k<N), W_N = P,
+//     x_{k+1} = A^ x_k + B^ u_k,   lo <= u_k <= hi          (F_u u <= 1 with F_u = [diag(1/hi); diag(1/lo)], :81)
+// and returns u_0 and V_N = optimum + x0' Q x0 (:91).  The reference hands this to cvxpy; the minimiser of a
+// strictly convex QP is unique, so any exact method gives the same u_0 / V_N.
+//
+// Method (designed for the GPU, not a translation of a dense QP solver): a primal active-set iteration whose
+// equality-constrained sub-problems are solved by an *affine Riccati sweep* — clamped inputs are constants, free
+// inputs are optimised stage by stage — so one iteration costs O(N n^3) flops on register-resident n x n blocks
+// instead of a dense (N m)^3 factorisation, and the KKT multipliers come from a costate sweep over the stored
+// trajectory. If the unconstrained plan is feasible it is returned at once (it is the QP minimiser).
+//
+// Per-thread scratch lives in a strided workspace view (element e at p[e*stride]): coalesced across the warp on
+// the device, contiguous on the host test harness.
+#pragma once
+#include "riccati.cuh"
+
+namespace lq {
+
+struct WsView {
+  double* p;
+  int64_t stride;
+  LQ_HD double& operator[](int64_t e) const { return p[e * stride]; }
+};
+
+template <int n, int m>
+struct ClqrLayout {
+  int N;
+  int64_t oKu, oKc, okc, oz, ozs, oxs, total;
+  LQ_HD explicit ClqrLayout(int N_) : N(N_) {
+    oKu = 0;
+    oKc = oKu + (int64_t)N * m * n;
+    okc = oKc + (int64_t)N * m * n;
+    oz = okc + (int64_t)N * m;
+    ozs = oz + (int64_t)N * m;
+    oxs = ozs + (int64_t)N * m;
+    total = oxs + (int64_t)(N + 1) * n;
+  }
+};
+
+template <int n, int m>
+LQ_HD int64_t clqr_ws_doubles(int N) {
+  return ClqrLayout<n, m>(N).total;
+}
+
+// Per-sample model of the controller (estimated system) + weights, in registers.
+template <int n, int m>
+struct Plan {
+  double Ah[n * n], Bh[n * m];
+  double P0[n * n];  // unconstrained horizon-N cost-to-go: V_N = x0' P0 x0 when no bound is active
+};
+
+// Unconstrained Riccati sweep; stores the gains K_k (u_k = K_k x_k) for k = 0..N-1 in the workspace.
+template <int n, int m>
+LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsView& ws) {
+  const ClqrLayout<n, m> L(N);
+  double P[n * n];
+  LQ_UNROLL for (int i = 0; i < n * n; ++i) P[i] = pb.Pt[i];
+  RicStage<n, m> st;
+  int flags = 0;
+  for (int k = N - 1; k >= 0; --k) {
+    riccati_factor<n, m>(P, pl.Bh, pb.R, st);
+    if (!st.ok) flags |= FLAG_CHOL_FAIL;
+    double K[m * n];
+    riccati_gain<n, m>(st, pl.Ah, K);
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oKu + (int64_t)k * (m * n) + e] = K[e];
+    riccati_update<n, m>(st, pl.Ah, pb.Q, P);
+  }
+  LQ_UNROLL for (int i = 0; i < n * n; ++i) pl.P0[i] = P[i];
+  return flags;
+}
+
+template <int n, int m>
+LQ_HD void step_model(const double* A, const double* B, const double* x, const double* u, double* xn) {
+  LQ_UNROLL for (int i = 0; i < n; ++i) {
+    double acc = 0.0;
+    LQ_UNROLL for (int j = 0; j < n; ++j) acc = fma(A[i * n + j], x[j], acc);
+    LQ_UNROLL for (int j = 0; j < m; ++j) acc = fma(B[i * m + j], u[j], acc);
+    xn[i] = acc;
+  }
+}
+
+// Backward affine Riccati sweep for the working set (fixed, athi): stores K_k (m x n) and k_k (m).
+template <int n, int m>
+LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, uint64_t fixed, uint64_t athi,
+                         const WsView& ws) {
+  const ClqrLayout<n, m> L(N);
+  double S[n * n], s[n];
+  LQ_UNROLL for (int i = 0; i < n * n; ++i) S[i] = pb.Pt[i];
+  LQ_UNROLL for (int i = 0; i < n; ++i) s[i] = 0.0;
+  bool ok = true;
+  for (int k = N - 1; k >= 0; --k) {
+    double SB[n * m], G[m * m], Hx[m * (n + 1)];
+    mm<n, n, m>(S, pl.Bh, SB);
+    LQ_UNROLL for (int i = 0; i < m; ++i)
+      LQ_UNROLL for (int j = 0; j <= i; ++j) {
+        double acc = pb.R[i * m + j];
+        LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Bh[r * m + i], SB[r * m + j], acc);
+        G[i * m + j] = acc; G[j * m + i] = acc;
+      }
+    // Hx = [ B^' S A^ | B^' s ]   (m x (n+1))
+    LQ_UNROLL for (int i = 0; i < m; ++i) {
+      LQ_UNROLL for (int j = 0; j < n; ++j) {
+        double acc = 0.0;
+        LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(SB[r * m + i], pl.Ah[r * n + j], acc);
+        Hx[i * (n + 1) + j] = acc;
+      }
+      double acc = 0.0;
+      LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Bh[r * m + i], s[r], acc);
+      Hx[i * (n + 1) + n] = acc;
+    }
+    // clamp: substitute constants for the fixed components
+    double uc[m];
+    bool fx[m];
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      const uint64_t bit = (uint64_t)1 << (k * m + j);
+      fx[j] = (fixed & bit) != 0;
+      uc[j] = (athi & bit) ? pb.uhi[j] : pb.ulo[j];
+    }
+    LQ_UNROLL for (int i = 0; i < m; ++i) {
+      if (!fx[i]) {
+        LQ_UNROLL for (int j = 0; j < m; ++j)
+          if (fx[j]) Hx[i * (n + 1) + n] = fma(G[i * m + j], uc[j], Hx[i * (n + 1) + n]);
+      }
+    }
+    LQ_UNROLL for (int i = 0; i < m; ++i)
+      LQ_UNROLL for (int j = 0; j < m; ++j)
+        if (fx[i] || fx[j]) G[i * m + j] = (i == j) ? 1.0 : 0.0;
+    LQ_UNROLL for (int i = 0; i < m; ++i)
+      if (fx[i]) {
+        LQ_UNROLL for (int j = 0; j < n; ++j) Hx[i * (n + 1) + j] = 0.0;
+        Hx[i * (n + 1) + n] = -uc[i];
+      }
+    ok = chol<m>(G) && ok;
+    solve_l<m, n + 1>(G, Hx);
+    solve_lt<m, n + 1>(G, Hx);
+    double K[m * n], kv[m];
+    LQ_UNROLL for (int i = 0; i < m; ++i) {
+      LQ_UNROLL for (int j = 0; j < n; ++j) K[i * n + j] = -Hx[i * (n + 1) + j];
+      kv[i] = fx[i] ? uc[i] : -Hx[i * (n + 1) + n];
+    }
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oKc + (int64_t)k * (m * n) + e] = K[e];
+    LQ_UNROLL for (int e = 0; e < m; ++e) ws[L.okc + (int64_t)k * m + e] = kv[e];
+    if (k > 0) {
+      // S_k = Q + K'RK + Acl' S Acl ;  s_k = K'R kv + Acl'(S B kv + s)
+      double Acl[n * n], SA[n * n], RK[m * n], bk[n], t[n], Rk[m];
+      LQ_UNROLL for (int i = 0; i < n; ++i)
+        LQ_UNROLL for (int j = 0; j < n; ++j) {
+          double acc = pl.Ah[i * n + j];
+          LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(pl.Bh[i * m + r], K[r * n + j], acc);
+          Acl[i * n + j] = acc;
+        }
+      mv<n, m>(pl.Bh, kv, bk);
+      LQ_UNROLL for (int i = 0; i < n; ++i) {
+        double acc = s[i];
+        LQ_UNROLL for (int j = 0; j < n; ++j) acc = fma(S[i * n + j], bk[j], acc);
+        t[i] = acc;
+      }
+      mm<m, m, n>(pb.R, K, RK);
+      mv<m, m>(pb.R, kv, Rk);
+      LQ_UNROLL for (int i = 0; i < n; ++i) {
+        double acc = 0.0;
+        LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(K[r * n + i], Rk[r], acc);
+        LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(Acl[r * n + i], t[r], acc);
+        s[i] = acc;
+      }
+      mm<n, n, n>(S, Acl, SA);
+      double Sn[n * n];
+      sym_add_mtm<m, n>(pb.Q, K, RK, Sn);
+      sym_add_mtm<n, n>(Sn, Acl, SA, S);
+    }
+  }
+  return ok;
+}
+
+// Exact constrained solve from state x0. Returns flags; writes u0[m] and V (= optimum + x0'Qx0).
+template <int n, int m>
+LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const double* x0, const WsView& ws,
+                     double* u0, double* V) {
+  const ClqrLayout<n, m> L(N);
+  double x[n], xn[n], u[m];
+  // ---- 1. unconstrained plan; feasible => optimal
+  bool feas = true;
+  LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
+  for (int k = 0; k < N; ++k) {
+    double K[m * n];
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+    mv<m, n>(K, x, u);
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) feas = false;
+      if (k == 0) u0[j] = u[j];
+    }
+    if (!feas) break;
+    step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
+    LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  if (feas) {
+    *V = quad<n>(x0, pl.P0, x0);
+    return 0;
+  }
+  int flags = FLAG_QP_ACTIVE;
+  if (N * m > 64) return flags | FLAG_QP_MAXITER;   // working set is a 64-bit mask
+  // ---- 2. feasible start: saturated rollout of the unconstrained gains; clipped components enter the working set
+  uint64_t fixed = 0, athi = 0;
+  LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
+  for (int k = 0; k < N; ++k) {
+    double K[m * n];
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+    mv<m, n>(K, x, u);
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      const uint64_t bit = (uint64_t)1 << (k * m + j);
+      if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed |= bit; athi |= bit; }
+      else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed |= bit; }
+      ws[L.oz + (int64_t)k * m + j] = u[j];
+    }
+    step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
+    LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  // ---- 3. primal active-set iterations
+  const int maxit = 8 * N * m + 32;
+  bool done = false;
+  for (int it = 0; it < maxit && !done; ++it) {
+    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws)) flags |= FLAG_CHOL_FAIL;
+    // forward sweep: candidate z* (stored in zs), trajectory in xs, largest feasible step along z* - z
+    double alpha = 1.0;
+    int block = -1;
+    bool block_hi = false;
+    LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = x0[i]; ws[L.oxs + i] = x0[i]; }
+    for (int k = 0; k < N; ++k) {
+      double K[m * n];
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKc + (int64_t)k * (m * n) + e];
+      mv<m, n>(K, x, u);
+      LQ_UNROLL for (int j = 0; j < m; ++j) {
+        u[j] += ws[L.okc + (int64_t)k * m + j];
+        const uint64_t bit = (uint64_t)1 << (k * m + j);
+        if (fixed & bit) u[j] = (athi & bit) ? pb.uhi[j] : pb.ulo[j];
+        ws[L.ozs + (int64_t)k * m + j] = u[j];
+        if (!(fixed & bit)) {
+          const double zc = ws[L.oz + (int64_t)k * m + j];
+          if (u[j] > pb.uhi[j]) {
+            const double a = (pb.uhi[j] - zc) / (u[j] - zc);
+            if (a < alpha) { alpha = a; block = k * m + j; block_hi = true; }
+          } else if (u[j] < pb.ulo[j]) {
+            const double a = (pb.ulo[j] - zc) / (u[j] - zc);
+            if (a < alpha) { alpha = a; block = k * m + j; block_hi = false; }
+          }
+        }
+      }
+      step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
+      LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = xn[i]; ws[L.oxs + (int64_t)(k + 1) * n + i] = xn[i]; }
+    }
+    if (block >= 0) {
+      // partial step to the blocking bound, which joins the working set
+      if (alpha < 0.0) alpha = 0.0;
+      for (int e = 0; e < N * m; ++e) {
+        const double zc = ws[L.oz + e];
+        ws[L.oz + e] = fma(alpha, ws[L.ozs + e] - zc, zc);
+      }
+      const int j = block % m;
+      ws[L.oz + block] = block_hi ? pb.uhi[j] : pb.ulo[j];
+      fixed |= (uint64_t)1 << block;
+      if (block_hi) athi |= (uint64_t)1 << block; else athi &= ~((uint64_t)1 << block);
+      continue;
+    }
+    // full step: z = z*; multipliers from the costate sweep over the stored trajectory
+    for (int e = 0; e < N * m; ++e) ws[L.oz + e] = ws[L.ozs + e];
+    double lam[n];
+    {
+      double xe[n];
+      LQ_UNROLL for (int i = 0; i < n; ++i) xe[i] = ws[L.oxs + (int64_t)N * n + i];
+      mv<n, n>(pb.Pt, xe, lam);
+      LQ_UNROLL for (int i = 0; i < n; ++i) lam[i] *= 2.0;
+    }
+    double worst = 0.0;
+    int rel = -1;
+    for (int k = N - 1; k >= 0; --k) {
+      double uk[m], g1[m], g2[m];
+      LQ_UNROLL for (int j = 0; j < m; ++j) uk[j] = ws[L.oz + (int64_t)k * m + j];
+      mv<m, m>(pb.R, uk, g1);
+      LQ_UNROLL for (int j = 0; j < m; ++j) {
+        double acc = 0.0;
+        LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Bh[r * m + j], lam[r], acc);
+        g2[j] = acc;
+        const uint64_t bit = (uint64_t)1 << (k * m + j);
+        if (fixed & bit) {
+          const double g = 2.0 * g1[j] + g2[j];            // dJ/du_{k,j}
+          const double tol = 1e-11 * (fabs(2.0 * g1[j]) + fabs(g2[j])) + 1e-300;
+          const double viol = (athi & bit) ? g : -g;       // at hi need g <= 0 ; at lo need g >= 0
+          if (viol > tol && viol > worst) { worst = viol; rel = k * m + j; }
+        }
+      }
+      if (k > 0) {
+        double xk[n], qx[n], atl[n];
+        LQ_UNROLL for (int i = 0; i < n; ++i) xk[i] = ws[L.oxs + (int64_t)k * n + i];
+        mv<n, n>(pb.Q, xk, qx);
+        LQ_UNROLL for (int i = 0; i < n; ++i) {
+          double acc = 2.0 * qx[i];
+          LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Ah[r * n + i], lam[r], acc);
+          atl[i] = acc;
+        }
+        LQ_UNROLL for (int i = 0; i < n; ++i) lam[i] = atl[i];
+      }
+    }
+    if (rel < 0) done = true;
+    else fixed &= ~((uint64_t)1 << rel);
+  }
+  if (!done) flags |= FLAG_QP_MAXITER;
+  // ---- 4. objective along z
+  LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
+  double cost = quad<n>(x0, pb.Q, x0);
+  for (int k = 0; k < N; ++k) {
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      u[j] = ws[L.oz + (int64_t)k * m + j];
+      if (k == 0) u0[j] = u[j];
+    }
+    step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
+    cost += quad<m>(u, pb.R, u);
+    cost += (k == N - 1) ? quad<n>(xn, pb.Pt, xn) : quad<n>(xn, pb.Q, xn);
+    LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  *V = cost;
+  return flags;
+}
+
+// Closed-loop simulation (utils_class.py:245-285): the controller re-solves from the measured state every step,
+// the plant is the TRUE model. Optional trajectories X [(T+1)*n], U [T*m] through strided views.
+template <int n, int m, class Traj>
+LQ_HD int simulate_sample(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, int T, const double* x0,
+                          const WsView& ws, double* J_T, int* n_active, Traj& traj) {
+  double x[n], xn[n], u[m];
+  LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
+  traj.state(0, x);
+  double cost = quad<n>(x, pb.Q, x);
+  int flags = 0, act = 0;
+  for (int t = 0; t < T; ++t) {
+    double V;
+    const int f = clqr_solve<n, m>(pb, pl, N, x, ws, u, &V);
+    flags |= f;
+    act += (f & FLAG_QP_ACTIVE) ? 1 : 0;
+    step_model<n, m>(pb.A, pb.B, x, u, xn);
+    cost += quad<n>(xn, pb.Q, xn);
+    cost += quad<m>(u, pb.R, u);
+    traj.input(t, u);
+    traj.state(t + 1, xn);
+    LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
+  }
+  *J_T = cost;
+  *n_active = act;
+  return flags;
+}
+
+}  // namespace lq

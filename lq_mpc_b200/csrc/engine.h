@@ -1,0 +1,82 @@
+// engine.h — internal (non-ABI) declarations shared by the kernel translation units and c_api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "riccati.cuh"
+
+// (n, m) pairs every templated kernel is instantiated for. The thread-per-sample register design targets n <= 4;
+// n = 6, 8 compile from the same templates (spilling to local memory) and are provided for completeness.
+#define LQ_FOR_EACH_DIM(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 4) X(6, 2) X(8, 2)
+#define LQ_DIMS_STRING "1x1,2x1,2x2,3x1,3x2,3x3,4x1,4x2,4x4,6x2,8x2"
+#define LQ_MAX_N 8
+#define LQ_MAX_M 4
+
+struct lqmpc_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int n = 0, m = 0;
+  bool has_problem = false;
+  int N_opc = 0;
+  // packed lq::Problem<n,m> (host copy of the device-prepared struct), passed by value to kernels
+  alignas(16) unsigned char pb[sizeof(lq::Problem<LQ_MAX_N, LQ_MAX_M>)];
+  void* pb_dev = nullptr;
+  std::string err;
+  int64_t launches = 0;
+  // scratch (grown on demand)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // host-pipeline resources
+  cudaStream_t pipe_stream[2] = {nullptr, nullptr};
+  cudaEvent_t pipe_done[2] = {nullptr, nullptr};
+  void* pipe_buf[2] = {nullptr, nullptr};
+  size_t pipe_bytes = 0;
+};
+
+struct EvalArgs {
+  int64_t S;         // samples in this launch
+  int64_t ld;        // leading dimension (stride between consecutive elements) of every SoA operand
+  const double* dA;
+  const double* dB;
+  const double* x0;
+  int N_min, N_max, T;
+  double* J;
+  double* rho;
+  double* ratio;
+  double* Vn;
+  double* JT;
+  int32_t* flags;
+  double* K0;
+};
+
+struct MpcArgs {
+  int64_t S;
+  const double* dA;   // [n*n][S] or NULL (zero perturbation)
+  const double* dB;   // [n*m][S] or NULL
+  int N, T;
+  int npts;
+  const double* pts;  // shared initial states [npts][n] (device) or NULL
+  const double* x0;   // per-sample initial states [n][S] (device), used when pts == NULL
+  double* V;          // [P][S]
+  double* u0;         // [P][m][S]
+  double* M_V;        // [S]
+  double* J_T;        // [S]
+  double* X;          // [T+1][n][S]
+  double* U;          // [T][m][S]
+  int32_t* flags;     // solve: [P][S]; simulate: [S]
+  int32_t* n_active;  // [S]
+  double* ws;         // filled by the launcher
+};
+
+int lq_set_error(lqmpc_ctx* ctx, int code, const char* what);
+int lq_check_cuda(lqmpc_ctx* ctx, cudaError_t e, const char* what);
+int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes);
+
+// launchers (one per kernel family; each switches on ctx->n, ctx->m)
+int lq_launch_prepare(lqmpc_ctx* ctx);
+int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
+int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
+int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);

@@ -1,0 +1,282 @@
+"""ctypes binding of the C ABI in include/lqmpc_b200.h + a thin tensor-level wrapper.
+
+PyTorch is used here only for device memory, streams and (elsewhere) torch.distributed; every computation is done
+by the hand-written sm_100a kernels in `_lib/liblqmpc_b200.so`.  There is NO CPU path: if the library or a CUDA
+device is missing, every entry point raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_PKG, "_lib", "liblqmpc_b200.so")
+
+FLAG_UNSTABLE = 1
+FLAG_QP_ACTIVE = 2
+FLAG_QP_MAXITER = 4
+FLAG_DARE_NOCONV = 8
+FLAG_NONFINITE = 16
+FLAG_BOUND_INVALID = 32
+FLAG_LYAP_NOCONV = 64
+FLAG_EIG_NOCONV = 128
+FLAG_CHOL_FAIL = 256
+
+_c_double_p = ctypes.POINTER(ctypes.c_double)
+_c_int32_p = ctypes.POINTER(ctypes.c_int32)
+_vp = ctypes.c_void_p
+_i64 = ctypes.c_int64
+_int = ctypes.c_int
+
+# name -> (restype, argtypes); the single source of truth for the symbols include/lqmpc_b200.h declares
+ABI = {
+    "lqmpc_abi_version": (_int, []),
+    "lqmpc_supported_dims": (ctypes.c_char_p, []),
+    "lqmpc_create": (_int, [ctypes.POINTER(_vp), _int, _vp]),
+    "lqmpc_destroy": (None, [_vp]),
+    "lqmpc_last_error": (ctypes.c_char_p, [_vp]),
+    "lqmpc_sync": (_int, [_vp]),
+    "lqmpc_set_problem": (_int, [_vp, _int, _int] + [_vp] * 7 + [_int]),
+    "lqmpc_get_prepared": (_int, [_vp, _vp, _i64]),
+    "lqmpc_eval_batch": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int] + [_vp] * 7),
+    "lqmpc_eval_batch_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64]),
+    "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
+    "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
+    "lqmpc_fp64_peak": (_int, [_vp, _c_double_p]),
+    "lqmpc_launch_count": (_i64, [_vp]),
+}
+
+_lib = None
+
+
+class EngineError(RuntimeError):
+    pass
+
+
+def load_library(path: Optional[str] = None):
+    """dlopen the engine and bind every ABI symbol. Raises (never falls back) when the library is missing."""
+    global _lib
+    if _lib is not None and path is None:
+        return _lib
+    p = path or LIB_PATH
+    if not os.path.exists(p):
+        raise EngineError(
+            "lq_mpc_b200: CUDA engine %s not built (run `python -c 'import __graft_entry__ as g; g.build()'`). "
+            "There is no CPU fallback." % p)
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in ABI.items():
+        fn = getattr(lib, name)          # AttributeError if the symbol is missing: loud by design
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _lib = lib
+    return lib
+
+
+def _np_f64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None:
+        a = a.reshape(shape)
+    return a
+
+
+def _ptr(t):
+    """Device/host pointer of a torch tensor or numpy array (None -> NULL)."""
+    if t is None:
+        return None
+    if isinstance(t, np.ndarray):
+        return t.ctypes.data
+    return t.data_ptr()
+
+
+class Engine:
+    """One engine context per (device, stream). Not thread-safe."""
+
+    def __init__(self, device: int = 0, stream=None):
+        import torch
+        if not torch.cuda.is_available():
+            raise EngineError("lq_mpc_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+        self.torch = torch
+        self.lib = load_library()
+        self.device = torch.device("cuda", device)
+        torch.cuda.set_device(self.device)
+        torch.zeros(1, device=self.device)  # make sure the primary context exists
+        self._stream = stream if stream is not None else torch.cuda.current_stream(self.device)
+        h = _vp()
+        rc = self.lib.lqmpc_create(ctypes.byref(h), device, _vp(self._stream.cuda_stream))
+        if rc != 0:
+            raise EngineError("lqmpc_create failed with code %d" % rc)
+        self._h = h
+        self.n = self.m = 0
+
+    # ------------------------------------------------------------------------------------------------ plumbing
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.lqmpc_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc, what):
+        if rc != 0:
+            msg = self.lib.lqmpc_last_error(self._h)
+            raise EngineError("%s failed (%d): %s" % (what, rc, msg.decode() if msg else ""))
+
+    def sync(self):
+        self._check(self.lib.lqmpc_sync(self._h), "lqmpc_sync")
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.lqmpc_launch_count(self._h))
+
+    def supported_dims(self):
+        return [tuple(int(v) for v in s.split("x")) for s in self.lib.lqmpc_supported_dims().decode().split(",")]
+
+    def _dev(self, a):
+        """numpy / tensor -> contiguous float64 CUDA tensor on this engine's device."""
+        torch = self.torch
+        if isinstance(a, torch.Tensor):
+            t = a.to(device=self.device, dtype=torch.float64)
+        else:
+            t = torch.from_numpy(_np_f64(a)).to(self.device)
+        return t.contiguous()
+
+    # ------------------------------------------------------------------------------------------------ problem
+    def set_problem(self, A, B, Q, R, P=None, u_lo=None, u_hi=None, N_opc: int = 30):
+        A = _np_f64(A)
+        n = A.shape[0]
+        B = _np_f64(B, (n, -1))
+        m = B.shape[1]
+        Q = _np_f64(Q, (n, n))
+        R = _np_f64(R, (m, m))
+        P = Q if P is None else _np_f64(P, (n, n))
+        lo = None if u_lo is None else _np_f64(u_lo, (m,))
+        hi = None if u_hi is None else _np_f64(u_hi, (m,))
+        rc = self.lib.lqmpc_set_problem(self._h, n, m, _ptr(A), _ptr(B), _ptr(Q), _ptr(R), _ptr(P), _ptr(lo),
+                                        _ptr(hi), int(N_opc))
+        self._check(rc, "lqmpc_set_problem")
+        self.n, self.m = n, m
+        self.A, self.B, self.Q, self.R, self.P = A, B, Q, R, P
+        self.u_lo, self.u_hi = lo, hi
+        return self
+
+    def prepared(self):
+        n = self.n
+        out = np.zeros(2 * n * n + 4)
+        self._check(self.lib.lqmpc_get_prepared(self._h, _ptr(out), out.size), "lqmpc_get_prepared")
+        return {"Pexp": out[:n * n].reshape(n, n).copy(), "Qinv": out[n * n:2 * n * n].reshape(n, n).copy(),
+                "maxQ": out[2 * n * n], "minQ": out[2 * n * n + 1], "maxR": out[2 * n * n + 2],
+                "minR": out[2 * n * n + 3]}
+
+    # ------------------------------------------------------------------------------------------------ K1
+    def eval_batch(self, dA, dB, x0, N_min: int, N_max: int, T: int = 0, want=("J", "rho", "ratio", "flags")):
+        """dA [n*n][S], dB [n*m][S], x0 [n][S] (SoA, device). Returns dict of [H][S] device tensors."""
+        torch = self.torch
+        n, m = self.n, self.m
+        dA, dB, x0 = self._dev(dA), self._dev(dB), self._dev(x0)
+        S = dA.shape[-1]
+        if dA.numel() != n * n * S or dB.numel() != n * m * S or x0.numel() != n * S:
+            raise ValueError("operand shapes do not match (n, m, S)")
+        H = N_max - N_min + 1
+        out = {}
+        for k in ("J", "rho", "ratio", "V_N", "J_T"):
+            if k in want:
+                out[k] = torch.empty((H, S), dtype=torch.float64, device=self.device)
+        if "flags" in want:
+            out["flags"] = torch.empty((H, S), dtype=torch.int32, device=self.device)
+        if "K0" in want:
+            out["K0"] = torch.empty((H, m * n, S), dtype=torch.float64, device=self.device)
+        rc = self.lib.lqmpc_eval_batch(self._h, S, _ptr(dA), _ptr(dB), _ptr(x0), N_min, N_max, T,
+                                       _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
+                                       _ptr(out.get("V_N")), _ptr(out.get("J_T")), _ptr(out.get("flags")),
+                                       _ptr(out.get("K0")))
+        self._check(rc, "lqmpc_eval_batch")
+        return out
+
+    def eval_batch_host(self, dA, dB, x0, N_min: int, N_max: int, out=None, chunk: int = 1 << 20):
+        """Same as eval_batch but from/to HOST buffers (numpy arrays or CPU tensors, ideally pinned), pipelined in
+        chunks with copies overlapping compute. `out` may hold preallocated host arrays J/rho/ratio/flags [H][S]."""
+        torch = self.torch
+        n, m = self.n, self.m
+        S = dA.shape[-1]
+        H = N_max - N_min + 1
+        if out is None:
+            out = {"J": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "rho": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "ratio": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "flags": torch.empty((H, S), dtype=torch.int32).pin_memory()}
+        rc = self.lib.lqmpc_eval_batch_host(self._h, S, _ptr(dA), _ptr(dB), _ptr(x0), N_min, N_max, 0,
+                                            _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
+                                            _ptr(out.get("flags")), chunk)
+        self._check(rc, "lqmpc_eval_batch_host")
+        return out
+
+    # ------------------------------------------------------------------------------------------------ K2
+    def _opt_dev(self, a):
+        return None if a is None else self._dev(a)
+
+    def mpc_solve_batch(self, dA, dB, N: int, pts=None, x0=None, S: Optional[int] = None,
+                        want=("V", "u0", "M_V", "flags")):
+        """Batched LQ_MPC_Controller.solve. dA/dB: [n*n][S]/[n*m][S] or None (true model; give S).
+        pts: (npts, n) states shared by all samples, or x0: [n][S] one state per sample."""
+        torch = self.torch
+        n, m = self.n, self.m
+        dA, dB = self._opt_dev(dA), self._opt_dev(dB)
+        if S is None:
+            S = dA.shape[-1] if dA is not None else (x0.shape[-1] if x0 is not None else 1)
+        pts_d = None if pts is None else self._dev(np.asarray(pts, dtype=np.float64).reshape(-1, n))
+        x0_d = self._opt_dev(x0)
+        P = pts_d.shape[0] if pts_d is not None else 1
+        out = {}
+        if "V" in want:
+            out["V"] = torch.empty((P, S), dtype=torch.float64, device=self.device)
+        if "u0" in want:
+            out["u0"] = torch.empty((P, m, S), dtype=torch.float64, device=self.device)
+        if "M_V" in want:
+            out["M_V"] = torch.empty((S,), dtype=torch.float64, device=self.device)
+        if "flags" in want:
+            out["flags"] = torch.empty((P, S), dtype=torch.int32, device=self.device)
+        rc = self.lib.lqmpc_mpc_solve_batch(self._h, S, _ptr(dA), _ptr(dB), int(N), P if pts_d is not None else 0,
+                                            _ptr(pts_d), _ptr(x0_d), _ptr(out.get("V")), _ptr(out.get("u0")),
+                                            _ptr(out.get("M_V")), _ptr(out.get("flags")))
+        self._check(rc, "lqmpc_mpc_solve_batch")
+        return out
+
+    def simulate_batch(self, dA, dB, N: int, T: int, x0_shared=None, x0=None, S: Optional[int] = None,
+                       want=("J_T", "flags", "n_active")):
+        """Batched LQ_MPC_Simulator.simulate. x0_shared: (n,) one state for all samples, or x0: [n][S]."""
+        torch = self.torch
+        n, m = self.n, self.m
+        dA, dB = self._opt_dev(dA), self._opt_dev(dB)
+        if S is None:
+            S = dA.shape[-1] if dA is not None else (x0.shape[-1] if x0 is not None else 1)
+        xs = None if x0_shared is None else self._dev(np.asarray(x0_shared, dtype=np.float64).reshape(n))
+        x0_d = self._opt_dev(x0)
+        out = {}
+        if "J_T" in want:
+            out["J_T"] = torch.empty((S,), dtype=torch.float64, device=self.device)
+        if "X" in want:
+            out["X"] = torch.empty((T + 1, n, S), dtype=torch.float64, device=self.device)
+        if "U" in want:
+            out["U"] = torch.empty((T, m, S), dtype=torch.float64, device=self.device)
+        if "flags" in want:
+            out["flags"] = torch.empty((S,), dtype=torch.int32, device=self.device)
+        if "n_active" in want:
+            out["n_active"] = torch.empty((S,), dtype=torch.int32, device=self.device)
+        rc = self.lib.lqmpc_simulate_batch(self._h, S, _ptr(dA), _ptr(dB), int(N), int(T), _ptr(xs), _ptr(x0_d),
+                                           _ptr(out.get("J_T")), _ptr(out.get("X")), _ptr(out.get("U")),
+                                           _ptr(out.get("flags")), _ptr(out.get("n_active")))
+        self._check(rc, "lqmpc_simulate_batch")
+        return out
+
+    def fp64_peak(self) -> float:
+        v = ctypes.c_double(0.0)
+        self._check(self.lib.lqmpc_fp64_peak(self._h, ctypes.byref(v)), "lqmpc_fp64_peak")
+        return float(v.value)

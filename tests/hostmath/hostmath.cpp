@@ -1,0 +1,197 @@
+// TEST FIXTURE ONLY — compiles the engine's __host__ __device__ math templates with g++ so that the per-sample
+// numerics can be compared with the oracle inside the GPU-less build container.  It is built and loaded by
+// tests/ only; nothing in lq_mpc_b200/ links or loads it (the product has no CPU path).
+#include <stdint.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../lq_mpc_b200/csrc/clqr.cuh"
+
+#define HM_FOR_EACH_DIM(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 4) X(6, 2) X(8, 2)
+
+namespace {
+
+template <int n, int m>
+void fill_problem(lq::Problem<n, m>& pb, const double* A, const double* B, const double* Q, const double* R,
+                  const double* P, const double* lo, const double* hi, int N_opc) {
+  memset(&pb, 0, sizeof(pb));
+  memcpy(pb.A, A, sizeof(pb.A));
+  memcpy(pb.B, B, sizeof(pb.B));
+  memcpy(pb.Q, Q, sizeof(pb.Q));
+  memcpy(pb.R, R, sizeof(pb.R));
+  memcpy(pb.Pt, P, sizeof(pb.Pt));
+  pb.has_bounds = (lo || hi) ? 1 : 0;
+  for (int j = 0; j < m; ++j) {
+    pb.ulo[j] = lo ? lo[j] : -HUGE_VAL;
+    pb.uhi[j] = hi ? hi[j] : HUGE_VAL;
+  }
+  lq::prepare_problem<n, m>(pb, N_opc);
+}
+
+struct HostSink {
+  int64_t S, s;
+  int mn;
+  double *J, *rho, *ratio, *Vn, *JT, *K0;
+  int32_t* flags;
+  void operator()(int h, double j, double r, double ra, double vn, double jt, int fl, const double* K) const {
+    const int64_t o = (int64_t)h * S + s;
+    if (J) J[o] = j;
+    if (rho) rho[o] = r;
+    if (ratio) ratio[o] = ra;
+    if (Vn) Vn[o] = vn;
+    if (JT) JT[o] = jt;
+    if (flags) flags[o] = fl;
+    if (K0)
+      for (int e = 0; e < mn; ++e) K0[((int64_t)h * mn + e) * S + s] = K[e];
+  }
+};
+
+template <int n, int m>
+int eval_t(const double* A, const double* B, const double* Q, const double* R, const double* P, int N_opc,
+           int64_t S, const double* dA, const double* dB, const double* x0, int Nmin, int Nmax, int T, double* J,
+           double* rho, double* ratio, double* Vn, double* JT, int32_t* flags, double* K0, double* prepared) {
+  lq::Problem<n, m> pb;
+  fill_problem<n, m>(pb, A, B, Q, R, P, nullptr, nullptr, N_opc);
+  if (prepared) {
+    memcpy(prepared, pb.Pexp, sizeof(pb.Pexp));
+    memcpy(prepared + n * n, pb.Qinv, sizeof(pb.Qinv));
+    prepared[2 * n * n + 0] = pb.maxQ; prepared[2 * n * n + 1] = pb.minQ;
+    prepared[2 * n * n + 2] = pb.maxR; prepared[2 * n * n + 3] = pb.minR;
+  }
+  for (int64_t s = 0; s < S; ++s) {
+    double a[n * n], b[n * m], x[n];
+    for (int e = 0; e < n * n; ++e) a[e] = dA[e * S + s];
+    for (int e = 0; e < n * m; ++e) b[e] = dB[e * S + s];
+    for (int e = 0; e < n; ++e) x[e] = x0[e * S + s];
+    HostSink sink{S, s, m * n, J, rho, ratio, Vn, T > 0 ? JT : nullptr, K0, flags};
+    lq::eval_sample<n, m>(pb, a, b, x, Nmin, Nmax, T, Vn != nullptr, sink);
+  }
+  return 0;
+}
+
+struct HostTraj {
+  int n, m;
+  int64_t S, s;
+  double *X, *U;
+  void state(int t, const double* x) const {
+    if (X) for (int i = 0; i < n; ++i) X[((int64_t)t * n + i) * S + s] = x[i];
+  }
+  void input(int t, const double* u) const {
+    if (U) for (int j = 0; j < m; ++j) U[((int64_t)t * m + j) * S + s] = u[j];
+  }
+};
+
+// mode 0: open-loop solves over `npts` shared points (pts != NULL) or the per-sample x0; mode 1: closed-loop simulate
+template <int n, int m>
+int mpc_t(int mode, const double* A, const double* B, const double* Q, const double* R, const double* P,
+          const double* lo, const double* hi, int64_t S, const double* dA, const double* dB, int N, int T, int npts,
+          const double* pts, const double* x0, double* V, double* u0, double* M_V, double* J_T, double* X, double* U,
+          int32_t* flags, int32_t* n_active) {
+  lq::Problem<n, m> pb;
+  fill_problem<n, m>(pb, A, B, Q, R, P, lo, hi, 1);
+  std::vector<double> wsbuf((size_t)lq::clqr_ws_doubles<n, m>(N));
+  const lq::WsView ws{wsbuf.data(), 1};
+  for (int64_t s = 0; s < S; ++s) {
+    lq::Plan<n, m> pl;
+    for (int e = 0; e < n * n; ++e) pl.Ah[e] = pb.A[e] + (dA ? dA[e * S + s] : 0.0);
+    for (int e = 0; e < n * m; ++e) pl.Bh[e] = pb.B[e] + (dB ? dB[e * S + s] : 0.0);
+    const int pf = lq::plan_prepare<n, m>(pb, pl, N, ws);
+    if (mode == 0) {
+      const int Pn = pts ? npts : 1;
+      double mvv = -HUGE_VAL;
+      for (int p = 0; p < Pn; ++p) {
+        double xx[n], uu[m], v;
+        for (int i = 0; i < n; ++i) xx[i] = pts ? pts[p * n + i] : x0[i * S + s];
+        const int f = pf | lq::clqr_solve<n, m>(pb, pl, N, xx, ws, uu, &v);
+        if (v > mvv) mvv = v;
+        if (V) V[(int64_t)p * S + s] = v;
+        if (u0) for (int j = 0; j < m; ++j) u0[((int64_t)p * m + j) * S + s] = uu[j];
+        if (flags) flags[(int64_t)p * S + s] = f;
+      }
+      if (M_V) M_V[s] = mvv;
+    } else {
+      double xx[n], jt;
+      int act;
+      for (int i = 0; i < n; ++i) xx[i] = pts ? pts[i] : x0[i * S + s];
+      HostTraj traj{n, m, S, s, X, U};
+      const int f = pf | lq::simulate_sample<n, m>(pb, pl, N, T, xx, ws, &jt, &act, traj);
+      if (J_T) J_T[s] = jt;
+      if (flags) flags[s] = f;
+      if (n_active) n_active[s] = act;
+    }
+  }
+  return 0;
+}
+
+template <int n>
+int rho_t(int64_t S, const double* M, double* rho, int32_t* okf) {
+  for (int64_t s = 0; s < S; ++s) {
+    bool ok;
+    rho[s] = lq::spectral_radius<n>(M + s * n * n, &ok);
+    okf[s] = ok ? 1 : 0;
+  }
+  return 0;
+}
+
+template <int n>
+int symeig_t(int64_t S, const double* M, double* lo, double* hi) {
+  for (int64_t s = 0; s < S; ++s) lq::sym_eig_minmax<n>(M + s * n * n, lo + s, hi + s);
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int hm_eval(int n, int m, const double* A, const double* B, const double* Q, const double* R, const double* P,
+            int N_opc, int64_t S, const double* dA, const double* dB, const double* x0, int Nmin, int Nmax, int T,
+            double* J, double* rho, double* ratio, double* Vn, double* JT, int32_t* flags, double* K0,
+            double* prepared) {
+#define X(N_, M_) \
+  if (n == N_ && m == M_) \
+    return eval_t<N_, M_>(A, B, Q, R, P, N_opc, S, dA, dB, x0, Nmin, Nmax, T, J, rho, ratio, Vn, JT, flags, K0, prepared);
+  HM_FOR_EACH_DIM(X)
+#undef X
+  return -1;
+}
+
+int hm_mpc(int mode, int n, int m, const double* A, const double* B, const double* Q, const double* R, const double* P,
+           const double* lo, const double* hi, int64_t S, const double* dA, const double* dB, int N, int T, int npts,
+           const double* pts, const double* x0, double* V, double* u0, double* M_V, double* J_T, double* X, double* U,
+           int32_t* flags, int32_t* n_active) {
+#define X_(N_, M_) \
+  if (n == N_ && m == M_) \
+    return mpc_t<N_, M_>(mode, A, B, Q, R, P, lo, hi, S, dA, dB, N, T, npts, pts, x0, V, u0, M_V, J_T, X, U, flags, n_active);
+  HM_FOR_EACH_DIM(X_)
+#undef X_
+  return -1;
+}
+
+// matrices packed AoS here: M[s][n*n]
+int hm_spectral_radius(int n, int64_t S, const double* M, double* rho, int32_t* ok) {
+  switch (n) {
+    case 1: return rho_t<1>(S, M, rho, ok);
+    case 2: return rho_t<2>(S, M, rho, ok);
+    case 3: return rho_t<3>(S, M, rho, ok);
+    case 4: return rho_t<4>(S, M, rho, ok);
+    case 5: return rho_t<5>(S, M, rho, ok);
+    case 6: return rho_t<6>(S, M, rho, ok);
+    case 8: return rho_t<8>(S, M, rho, ok);
+  }
+  return -1;
+}
+
+int hm_sym_eig_minmax(int n, int64_t S, const double* M, double* lo, double* hi) {
+  switch (n) {
+    case 1: return symeig_t<1>(S, M, lo, hi);
+    case 2: return symeig_t<2>(S, M, lo, hi);
+    case 3: return symeig_t<3>(S, M, lo, hi);
+    case 4: return symeig_t<4>(S, M, lo, hi);
+    case 6: return symeig_t<6>(S, M, lo, hi);
+    case 8: return symeig_t<8>(S, M, lo, hi);
+  }
+  return -1;
+}
+
+}  // extern "C"
