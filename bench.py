@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py — headline benchmark of the lq_mpc hot path on B200 (see DESIGN.md "Measurement").
+
+Metric (BASELINE.json): MPC performance evals/sec, 1 eval = one (sample, horizon) pair = Riccati gain of that
+horizon on the estimated model + closed loop on the true plant + J_inf (Lyapunov doubling) + spectral-radius
+stability check + performance ratio.  Workload: cfg-synth-4-2-10 (n=4, m=2, N=10, Q=I, R=I, unconstrained),
+1.25e7 seeded samples (dA, dB, x0) PER GPU (= BASELINE's 1e8 samples at 8 GPUs; weak scaling), followed by the
+per-column worst-case statistics (K5) and — at N>1 — the engine's only collective, tiny NCCL all-reduces of them.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (torchrun launches it for N > 1)
+  python bench.py --impl reference ...                         the CPU arm: the numpy oracle port on all host cores
+
+One JSON line on stdout (rank 0).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_DIM, M_DIM, HORIZON = 4, 2, 10
+S_PER_GPU = 12_500_000
+SEED_PROBLEM, SEED_SAMPLES = 0, 1
+
+
+def flops_per_eval(n, m, N, lyap_iters=8):
+    """dense algorithmic FP64 flops of one eval (FMA = 2 flops, no symmetry savings)."""
+    f_ric = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
+    return N * f_ric + 2 * n * n * m + (2 * n * n * m + 2 * n * m * m) + lyap_iters * 6 * n ** 3 + 10 * n ** 3 + (
+        2 * n * n + 2 * n)
+
+
+def bytes_per_eval(n, m):
+    """compulsory HBM traffic of one eval: read dA, dB, x0; write J, rho, ratio, flags."""
+    return (n * n + n * m + n) * 8 + 4 * 8
+
+
+# ---------------------------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+              "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except (ValueError, IndexError):
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------- CPU arm
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    first, count = args
+    import numpy as np  # noqa
+    from oracle import np_batched as nb
+    A, B, Q, R = nb.synth_problem(N_DIM, M_DIM, seed=SEED_PROBLEM)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    dA, dB, x0 = nb.synth_samples(N_DIM, M_DIM, count, seed=SEED_SAMPLES, first=first)
+    t = time.perf_counter()
+    out = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, HORIZON, HORIZON)
+    return time.perf_counter() - t, float(out["ratio"].max())
+
+
+def cpu_port_throughput(per_worker, workers=None):
+    """The oracle port (oracle/np_batched.py) on `workers` host processes, `per_worker` samples each.
+    Returns (evals/s over the wall clock of the pool, workers, samples)."""
+    import multiprocessing as mp
+    workers = workers or max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        pool.map(_cpu_worker, [(0, 256)] * workers)                     # spawn + import warm-up
+        t = time.perf_counter()
+        pool.map(_cpu_worker, [(w * per_worker, per_worker) for w in range(workers)])
+        wall = time.perf_counter() - t
+    total = workers * per_worker
+    return total / wall, workers, total
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    per_worker = 20_000
+    vals = []
+    for _ in range(args.warmup):
+        cpu_port_throughput(2_000)
+    workers = total = 0
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        v, workers, total = cpu_port_throughput(per_worker)
+        vals.append(v)
+    wall = time.perf_counter() - t0
+    value = sum(vals) / len(vals)
+    line = {"impl": "reference", "metric": "mpc_evals_per_sec", "value": value, "unit": "evals/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus, note="CPU arm: bounded sample per step"),
+            "cpu_baseline": {"value": value, "unit": "evals/s", "cores": workers, "kind": "port",
+                             "sample": "%d samples per step (%d per process) of the same seeded workload; oracle/"
+                                       "np_batched.py (batched numpy/LAPACK), one process per host core" %
+                                       (total, per_worker)},
+            "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+    return 0
+
+
+def workload_config(n_gpus, note=None):
+    cfg = {"workload": "cfg-synth-4-2-10: n=4 m=2 N=10 Q=I R=I unconstrained, %.3g seeded (dA,dB,x0) samples per GPU "
+                       "(%.3g total), J_inf + rho + ratio + flags per sample, then per-column worst-case stats"
+                       % (S_PER_GPU, S_PER_GPU * n_gpus),
+           "n": N_DIM, "m": M_DIM, "N": HORIZON, "samples_per_gpu": S_PER_GPU, "evals_per_sample": 1,
+           "l2": "inputs (2.8 GB per step) exceed the 126 MB L2; no flush needed",
+           "parallelism": "sample-sharded x%d, one final all-reduce of statistics" % n_gpus}
+    if note:
+        cfg["note"] = note
+    return cfg
+
+
+# ---------------------------------------------------------------------------------------------------- our arm
+def run_ours(args):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from lq_mpc_b200 import sampling as sp
+    from lq_mpc_b200.engine import Engine
+    from lq_mpc_b200.stats import column_stats
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
+    torch.cuda.set_device(local)
+    eng = Engine(local)
+    A, B, Q, R = sp.synth_problem(N_DIM, M_DIM, seed=SEED_PROBLEM)
+    eng.set_problem(A, B, Q, R, Q, None, None, 30)
+    S = S_PER_GPU
+    n, m = N_DIM, M_DIM
+
+    # ---- this rank's shard of the seeded workload, generated on the host into pinned buffers
+    hA = torch.empty((n * n, S), dtype=torch.float64).pin_memory()
+    hB = torch.empty((n * m, S), dtype=torch.float64).pin_memory()
+    hx = torch.empty((n, S), dtype=torch.float64).pin_memory()
+    sp.synth_samples_soa(n, m, S, seed=SEED_SAMPLES, first=rank * S, out=(hA.numpy(), hB.numpy(), hx.numpy()))
+    dA, dB, x0 = hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), hx.cuda(non_blocking=True)
+    torch.cuda.synchronize()
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        r = eng.eval_batch(dA, dB, x0, HORIZON, HORIZON)
+        table = torch.stack([r["ratio"][0], r["J"][0], r["rho"][0]], dim=0)
+        st = column_stats(eng, table)
+        return r, st
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        t = torch.tensor([v], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    # ---- (1) device-resident throughput: W warm-up steps, K timed steps, CUDA events, max over ranks
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = eng.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        r, st = step()
+    e1.record()
+    barrier()
+    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
+    launches = eng.launch_count - launches0
+    # ---- (2) the dominant kernel alone (K1), same data, for the roofline
+    barrier()
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    k0.record()
+    for _ in range(args.steps):
+        eng.eval_batch(dA, dB, x0, HORIZON, HORIZON)
+    k1.record()
+    barrier()
+    ms_kernel = k0.elapsed_time(k1) / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- (3) end to end through the host-buffer entry point: pinned host -> H2D -> K1 -> D2H, every step
+    outb = None
+    for _ in range(2):
+        outb = eng.eval_batch_host(hA, hB, hx, HORIZON, HORIZON, out=outb, chunk=1 << 19)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        outb = eng.eval_batch_host(hA, hB, hx, HORIZON, HORIZON, out=outb, chunk=1 << 19)
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    same = bool(torch.equal(outb["J"][0, :4096], r["J"][0, :4096].cpu()))
+    peak_fp64 = eng.fp64_peak() if rank == 0 else 0.0
+    unstable = int((r["flags"] & 1).sum().item())
+    if world > 1:
+        dist.barrier()
+
+    if rank == 0:
+        evals = S * world
+        value = evals / (ms_step * 1e-3)
+        fl = flops_per_eval(n, m, HORIZON)
+        by = bytes_per_eval(n, m)
+        ach_tf = S * fl / (ms_kernel * 1e-3) / 1e12
+        ach_gb = S * by / (ms_kernel * 1e-3) / 1e9
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+        except (OSError, ValueError):
+            pass
+        line = {
+            "metric": "mpc_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(world),
+            "roofline": {
+                "bound": "fp64", "achieved": ach_tf, "peak": peak_fp64, "unit": "TFLOP/s",
+                "frac": ach_tf / peak_fp64 if peak_fp64 else None, "traffic": traffic,
+                "kernel": "eval_kernel<4,2>", "kernel_ms": ms_kernel,
+                "algorithmic_flops_per_eval": fl, "algorithmic_bytes_per_eval": by,
+                "peak_source": "measured in this run: DFMA-chain micro-benchmark (lqmpc_fp64_peak); "
+                               "MEASURED_PEAKS.json has no FP64 figure",
+                "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"}},
+            "e2e": {"value": evals / e2e_s, "unit": "evals/s",
+                    "h2d_bytes_per_step": int(S * (n * n + n * m + n) * 8),
+                    "d2h_bytes_per_step": int(S * (3 * 8 + 4)), "matches_device_path": same,
+                    "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "worst_case": {"ratio_max": float(st["max"][0]), "ratio_mean": float(st["mean"][0]),
+                           "rho_max": float(st["max"][2]), "unstable": unstable},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, workers, total = cpu_port_throughput(8_000)
+            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
+                                    "sample": "%d samples of the same seeded workload (8000 per process); "
+                                              "oracle/np_batched.py, one process per host core" % total}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_ours(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -39,6 +39,7 @@ extern "C" {
 #define LQMPC_FLAG_LYAP_NOCONV 64
 #define LQMPC_FLAG_EIG_NOCONV 128
 #define LQMPC_FLAG_CHOL_FAIL 256
+#define LQMPC_FLAG_DOMAIN_ERROR 512
 
 typedef struct lqmpc_ctx lqmpc_ctx;
 
@@ -104,6 +105,49 @@ int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const dou
 int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int T,
                          const double* x0_shared, const double* x0, double* J_T, double* X, double* U,
                          int32_t* flags, int32_t* n_active);
+
+/* K3 — batched bound coefficients: LQ_RDP_Calculator.energy_decreasing (utils_class.py:344-373) and
+ * .energy_bound (utils_class.py:308-342) with every helper they call (utils.py: local_radius, ex_stability_lq,
+ * ex_stability_bounds, fc_omega_eta, fc_ec_h, fc_ec_E, fc_ec_theta, fc_ec_g_*, geo_M, my_eigen, sl_syn_*,
+ * bar_u_solve, bar_d_u_solve) and the final J_bound = (alpha V_expert + beta)/(1 - xi - eta)
+ * (utils_class.py:858-859), for the estimated model (A+dA_s, B+dB_s) of every sample.
+ *   N                      horizon of this launch
+ *   e_A, e_B               device [S] (per-sample error level) or NULL -> the scalar arguments
+ *   M_V                    device [S] (from lqmpc_mpc_solve_batch) or NULL -> M_V_scalar
+ *   x_shared / x           the state energy_bound is evaluated at: device [n] shared, or device [n][S]
+ *   K_in / K_shared        terminal gain in the u = +K x convention: device [m*n][S], or device [m*n] shared;
+ *                          both NULL: -K_dlqr of the sample's own model (DARE solved in-kernel, utils_class.py:840-844)
+ *   p3_host                the three scalars p (HOST), V_expert (utils_class.py:786)
+ *   bar_u, bar_d_u         max||u||^2, max||u1-u2||^2 over the input set; negative = derive from the box
+ *   strict_reference       keep the literal kron(Q, I) / kron(R, I) ordering of utils.py:317-318 (immaterial when
+ *                          Q and R are multiples of the identity)
+ * Outputs (device, any may be NULL): alpha, beta, xi, eta, bound [S]; detail [lqmpc_bounds_fields()][S] with every
+ * intermediate in the order of `enum BoundField` (bounds.cuh; mirrored in lq_mpc_b200/engine.py); K_out [m*n][S];
+ * P_out [n*n][S] (DARE solution, only when the gain is computed in-kernel); flags [S].
+ * A reference ValueError (math.log / math.sqrt domain, utils.py:506-507,514) maps to LQMPC_FLAG_DOMAIN_ERROR;
+ * 1 - xi - eta <= 0 (void bound, computed silently by the reference) sets LQMPC_FLAG_BOUND_INVALID. */
+int lqmpc_bounds_fields(void);
+int lqmpc_bounds_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, const double* e_A,
+                       const double* e_B, double e_A_scalar, double e_B_scalar, const double* M_V,
+                       double M_V_scalar, const double* x_shared, const double* x, const double* K_in,
+                       const double* K_shared, const double* p3_host, double V_expert, double bar_u, double bar_d_u,
+                       int strict_reference, double* alpha, double* beta, double* xi, double* eta, double* bound,
+                       double* detail, double* K_out, double* P_out, int32_t* flags);
+
+/* Batched control.dlqr (utils_class.py:761,840,923): stabilising DARE solution P and K = (R+B'PB)^-1 B'PA
+ * (convention u = -Kx) of (A+dA_s, B+dB_s); dA/dB NULL = the true model. K_out [m*n][S], P_out [n*n][S], flags [S]. */
+int lqmpc_dlqr_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K_out, double* P_out,
+                     int32_t* flags);
+
+/* K5 — per-column statistics of a column-contiguous result table `table[c*ld + s]` (c < cols, s < S): the four
+ * reductions the reference's plotters take over axis 0 of every table (utils.py:895-898: max, min, mean, std).
+ *   lqmpc_column_stats : stats [cols][5] = { max, min, sum, count_finite, count_nonfinite } over the finite entries
+ *   lqmpc_column_sqdev : sqdev [cols]    = sum over finite entries of (x - mean[c])^2   (np.std is two-pass)
+ * Both are deterministic (fixed reduction order). Multi-GPU: all-reduce {max, -min} with MAX and
+ * {sum, counts} with SUM between the two calls, then all-reduce sqdev with SUM (lq_mpc_b200/stats.py). */
+int lqmpc_column_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats);
+int lqmpc_column_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
+                       double* sqdev);
 
 /* DFMA-chain micro-benchmark: achieved FP64 FMA throughput of this device in TFLOP/s (2 flop per FMA), used as the
  * measured denominator of the FP64 roofline (MEASURED_PEAKS.json has none). Synchronises. */

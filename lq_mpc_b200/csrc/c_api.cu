@@ -6,6 +6,7 @@
 
 #include "../../include/lqmpc_b200.h"
 #include "engine.h"
+#include "bounds.cuh"
 
 int lq_set_error(lqmpc_ctx* ctx, int code, const char* what) {
   if (ctx) ctx->err = what ? what : "";
@@ -307,6 +308,60 @@ int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const doub
   a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.T = T; a.npts = 1; a.pts = x0_shared; a.x0 = x0;
   a.J_T = J_T; a.X = X; a.U = U; a.flags = flags; a.n_active = n_active;
   return lq_launch_mpc(ctx, a, true);
+}
+
+int lqmpc_bounds_fields(void) { return (int)lq::BF_COUNT; }
+
+int lqmpc_bounds_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, const double* e_A,
+                       const double* e_B, double e_A_scalar, double e_B_scalar, const double* M_V,
+                       double M_V_scalar, const double* x_shared, const double* x, const double* K_in,
+                       const double* K_shared, const double* p3_host, double V_expert, double bar_u, double bar_d_u,
+                       int strict_reference, double* alpha, double* beta, double* xi, double* eta, double* bound,
+                       double* detail, double* K_out, double* P_out, int32_t* flags) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || N < 1) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N");
+  if (S == 0) return LQMPC_OK;
+  if ((x_shared == nullptr) == (x == nullptr)) return lq_set_error(ctx, LQMPC_EINVAL, "give exactly one of x_shared / x");
+  if (K_in && K_shared) return lq_set_error(ctx, LQMPC_EINVAL, "give at most one of K_in / K_shared");
+  if (!p3_host) return lq_set_error(ctx, LQMPC_EINVAL, "null p");
+  cudaSetDevice(ctx->device);
+  BoundsArgs a{};
+  a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.eA = e_A; a.eB = e_B; a.eA_s = e_A_scalar; a.eB_s = e_B_scalar;
+  a.MV = M_V; a.MV_s = M_V_scalar; a.x_shared = x_shared; a.x = x; a.K_in = K_in; a.K_shared = K_shared;
+  a.p[0] = p3_host[0]; a.p[1] = p3_host[1]; a.p[2] = p3_host[2];
+  a.V_expert = V_expert; a.bar_u = bar_u; a.bar_d_u = bar_d_u; a.strict = strict_reference;
+  a.alpha = alpha; a.beta = beta; a.xi = xi; a.eta = eta; a.bound = bound; a.detail = detail; a.K_out = K_out;
+  a.P_out = P_out; a.flags = flags;
+  return lq_launch_bounds(ctx, a);
+}
+
+int lqmpc_dlqr_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K_out, double* P_out,
+                     int32_t* flags) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0) return lq_set_error(ctx, LQMPC_EINVAL, "bad S");
+  if (S == 0) return LQMPC_OK;
+  cudaSetDevice(ctx->device);
+  return lq_launch_dlqr(ctx, S, dA, dB, K_out, P_out, flags);
+}
+
+int lqmpc_column_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!table || !stats || cols < 1 || S < 0 || ld < S) return lq_set_error(ctx, LQMPC_EINVAL, "bad table/cols/S/ld");
+  if (cols > 65535) return lq_set_error(ctx, LQMPC_EINVAL, "too many columns");
+  cudaSetDevice(ctx->device);
+  return lq_launch_stats(ctx, table, cols, S, ld, stats);
+}
+
+int lqmpc_column_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
+                       double* sqdev) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!table || !mean || !sqdev || cols < 1 || S < 0 || ld < S)
+    return lq_set_error(ctx, LQMPC_EINVAL, "bad table/cols/S/ld");
+  if (cols > 65535) return lq_set_error(ctx, LQMPC_EINVAL, "too many columns");
+  cudaSetDevice(ctx->device);
+  return lq_launch_sqdev(ctx, table, cols, S, ld, mean, sqdev);
 }
 
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out) {

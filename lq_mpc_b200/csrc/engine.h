@@ -71,6 +71,32 @@ struct MpcArgs {
   double* ws;         // filled by the launcher
 };
 
+struct BoundsArgs {
+  int64_t S;
+  const double* dA;
+  const double* dB;
+  int N;
+  const double* eA;       // [S] or NULL -> eA_s
+  const double* eB;
+  double eA_s, eB_s;
+  const double* MV;       // [S] or NULL -> MV_s
+  double MV_s;
+  const double* x_shared; // [n] or NULL -> x [n][S]
+  const double* x;
+  const double* K_in;     // [m*n][S] (u = +Kx) or NULL
+  const double* K_shared; // [m*n] or NULL; both NULL -> -K_dlqr of the sample's model
+  double p[3];
+  double V_expert;
+  double bar_u, bar_d_u;
+  int strict;
+  double *alpha, *beta, *xi, *eta, *bound;  // [S]
+  double* detail;         // [BF_COUNT][S]
+  double* K_out;          // [m*n][S]
+  double* P_out;          // [n*n][S] (DARE solution; only when the gain is computed here)
+  int32_t* flags;
+  double* ws;
+};
+
 int lq_set_error(lqmpc_ctx* ctx, int code, const char* what);
 int lq_check_cuda(lqmpc_ctx* ctx, cudaError_t e, const char* what);
 int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes);
@@ -80,3 +106,9 @@ int lq_launch_prepare(lqmpc_ctx* ctx);
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);
+int lq_launch_bounds(lqmpc_ctx* ctx, const BoundsArgs& a);
+int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats);
+int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
+                    double* out);
+int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
+                   int32_t* flags);

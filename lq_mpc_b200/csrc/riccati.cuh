@@ -23,10 +23,11 @@ enum Flags : int {
   FLAG_QP_MAXITER = 4,     // active-set iteration budget exhausted
   FLAG_DARE_NOCONV = 8,    // doubling iteration for the DARE did not converge
   FLAG_NONFINITE = 16,     // NaN/Inf produced
-  FLAG_BOUND_INVALID = 32, // 1 - xi - eta <= 0, or log/sqrt domain error (reference raises ValueError)
+  FLAG_BOUND_INVALID = 32, // 1 - xi - eta <= 0: the performance bound is void (the reference still computes it)
   FLAG_LYAP_NOCONV = 64,   // Lyapunov doubling hit its iteration cap
   FLAG_EIG_NOCONV = 128,   // QR iteration did not converge
-  FLAG_CHOL_FAIL = 256     // R + B'PB not positive definite
+  FLAG_CHOL_FAIL = 256,    // R + B'PB not positive definite
+  FLAG_DOMAIN_ERROR = 512  // math.log / math.sqrt domain error (the reference raises ValueError, utils.py:506-507,514)
 };
 
 template <int n, int m>

@@ -12,11 +12,11 @@
 
 #if defined(__CUDACC__)
 #define LQ_HD __host__ __device__ __forceinline__
-#define LQ_HD_NOINLINE __host__ __device__ __noinline__
+#define LQ_HD_NOINLINE static __host__ __device__ __noinline__
 #define LQ_UNROLL _Pragma("unroll")
 #else
 #define LQ_HD inline
-#define LQ_HD_NOINLINE
+#define LQ_HD_NOINLINE static
 #define LQ_UNROLL
 #endif
 

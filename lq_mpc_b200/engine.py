@@ -24,6 +24,7 @@ FLAG_BOUND_INVALID = 32
 FLAG_LYAP_NOCONV = 64
 FLAG_EIG_NOCONV = 128
 FLAG_CHOL_FAIL = 256
+FLAG_DOMAIN_ERROR = 512
 
 _c_double_p = ctypes.POINTER(ctypes.c_double)
 _c_int32_p = ctypes.POINTER(ctypes.c_int32)
@@ -45,9 +46,22 @@ ABI = {
     "lqmpc_eval_batch_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64]),
     "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
     "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
+    "lqmpc_bounds_fields": (_int, []),
+    "lqmpc_bounds_batch": (_int, [_vp, _i64, _vp, _vp, _int, _vp, _vp, ctypes.c_double, ctypes.c_double, _vp,
+                                  ctypes.c_double, _vp, _vp, _vp, _vp, _vp, ctypes.c_double, ctypes.c_double,
+                                  ctypes.c_double, _int] + [_vp] * 9),
+    "lqmpc_dlqr_batch": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
+    "lqmpc_column_stats": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
+    "lqmpc_column_sqdev": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp]),
     "lqmpc_fp64_peak": (_int, [_vp, _c_double_p]),
     "lqmpc_launch_count": (_i64, [_vp]),
 }
+
+# order of `enum BoundField` in csrc/bounds.cuh (rows of the `detail` output of lqmpc_bounds_batch)
+BOUND_FIELDS = ['alpha', 'beta', 'xi', 'eta', 'bound', 'E_psi', 'E_u', 'E_psi_u', 'theta_u', 'theta_x_u', 'C_K',
+                'rho_K', 'gamma', 'rho_gamma', 'L_V', 'N_0', 'omega_N1', 'omega_N0d5', 'err_th', 'N_min', 'h',
+                'epsilon_K', 'norm_A', 'norm_B', 'norm_K', 'norm_Gamma', 'norm_Phi', 'min_H', 'rho_cl', 'bar_u',
+                'bar_d_u']
 
 _lib = None
 
@@ -274,6 +288,98 @@ class Engine:
                                            _ptr(out.get("J_T")), _ptr(out.get("X")), _ptr(out.get("U")),
                                            _ptr(out.get("flags")), _ptr(out.get("n_active")))
         self._check(rc, "lqmpc_simulate_batch")
+        return out
+
+    # ------------------------------------------------------------------------------------------------ K3
+    def bounds_batch(self, dA, dB, N: int, e_A, e_B, M_V, x, p, V_expert: float, K=None, S: Optional[int] = None,
+                     bar_u: float = -1.0, bar_d_u: float = -1.0, strict_reference: bool = True, want_K=False,
+                     want_P=False):
+        """Batched energy_decreasing + energy_bound + J_bound. e_A/e_B/M_V: python scalars or [S] arrays;
+        x: (n,) shared or [n][S]; K: None (-> -K_dlqr per sample), (m,n)/(m*n,) shared, or [m*n][S] (u = +Kx)."""
+        torch = self.torch
+        n, m = self.n, self.m
+        dA, dB = self._opt_dev(dA), self._opt_dev(dB)
+        if S is None:
+            S = dA.shape[-1] if dA is not None else 1
+
+        def per_sample(v):
+            if np.isscalar(v) or (hasattr(v, "ndim") and v.ndim == 0):
+                return None, float(v)
+            return self._dev(v).reshape(S), 0.0
+
+        eA_d, eA_s = per_sample(e_A)
+        eB_d, eB_s = per_sample(e_B)
+        MV_d, MV_s = per_sample(M_V)
+        x_arr = x if isinstance(x, torch.Tensor) else np.asarray(x, dtype=np.float64)
+        x_sh = x_ps = None
+        if int(np.prod(x_arr.shape)) == n:          # one state shared by every sample
+            x_sh = self._dev(x_arr).reshape(n)
+        else:
+            x_ps = self._dev(x_arr).reshape(n, S)
+        K_sh = K_ps = None
+        if K is not None:
+            K_arr = K if isinstance(K, torch.Tensor) else np.asarray(K, dtype=np.float64)
+            if K_arr.size == m * n:
+                K_sh = self._dev(K_arr).reshape(m * n)
+            else:
+                K_ps = self._dev(K_arr).reshape(m * n, S)
+        NF = int(self.lib.lqmpc_bounds_fields())
+        assert NF == len(BOUND_FIELDS)
+        detail = torch.empty((NF, S), dtype=torch.float64, device=self.device)
+        flags = torch.empty((S,), dtype=torch.int32, device=self.device)
+        K_out = torch.empty((m * n, S), dtype=torch.float64, device=self.device) if want_K else None
+        P_out = torch.empty((n * n, S), dtype=torch.float64, device=self.device) if want_P else None
+        p3 = _np_f64(p, (3,))
+        rc = self.lib.lqmpc_bounds_batch(self._h, S, _ptr(dA), _ptr(dB), int(N), _ptr(eA_d), _ptr(eB_d), eA_s, eB_s,
+                                         _ptr(MV_d), MV_s, _ptr(x_sh), _ptr(x_ps), _ptr(K_ps), _ptr(K_sh), _ptr(p3),
+                                         float(V_expert), float(bar_u), float(bar_d_u), int(bool(strict_reference)),
+                                         None, None, None, None, None, _ptr(detail), _ptr(K_out), _ptr(P_out),
+                                         _ptr(flags))
+        self._check(rc, "lqmpc_bounds_batch")
+        out = {k: detail[i] for i, k in enumerate(BOUND_FIELDS)}
+        out["flags"] = flags
+        if want_K:
+            out["K"] = K_out
+        if want_P:
+            out["P"] = P_out
+        return out
+
+    def dlqr_batch(self, dA=None, dB=None, S: Optional[int] = None):
+        """Batched control.dlqr: returns K [m*n][S] (u = -Kx), P [n*n][S], flags [S]."""
+        torch = self.torch
+        n, m = self.n, self.m
+        dA, dB = self._opt_dev(dA), self._opt_dev(dB)
+        if S is None:
+            S = dA.shape[-1] if dA is not None else 1
+        K = torch.empty((m * n, S), dtype=torch.float64, device=self.device)
+        P = torch.empty((n * n, S), dtype=torch.float64, device=self.device)
+        fl = torch.empty((S,), dtype=torch.int32, device=self.device)
+        self._check(self.lib.lqmpc_dlqr_batch(self._h, S, _ptr(dA), _ptr(dB), _ptr(K), _ptr(P), _ptr(fl)),
+                    "lqmpc_dlqr_batch")
+        return {"K": K, "P": P, "flags": fl}
+
+    # ------------------------------------------------------------------------------------------------ K5
+    def column_stats_raw(self, table):
+        """table: [cols][S] device tensor (rows contiguous). Returns [cols][5] = max, min, sum, n_finite, n_bad."""
+        torch = self.torch
+        t = self._dev(table)
+        if t.ndim == 1:
+            t = t.reshape(1, -1)
+        cols, S = t.shape
+        stats = torch.empty((cols, 5), dtype=torch.float64, device=self.device)
+        self._check(self.lib.lqmpc_column_stats(self._h, _ptr(t), cols, S, S, _ptr(stats)), "lqmpc_column_stats")
+        return stats
+
+    def column_sqdev_raw(self, table, mean):
+        torch = self.torch
+        t = self._dev(table)
+        if t.ndim == 1:
+            t = t.reshape(1, -1)
+        cols, S = t.shape
+        mean = self._dev(mean).reshape(cols)
+        out = torch.empty((cols,), dtype=torch.float64, device=self.device)
+        self._check(self.lib.lqmpc_column_sqdev(self._h, _ptr(t), cols, S, S, _ptr(mean), _ptr(out)),
+                    "lqmpc_column_sqdev")
         return out
 
     def fp64_peak(self) -> float:

@@ -1,0 +1,64 @@
+import json
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "slow: long CPU test")
+
+
+@pytest.fixture(scope="session")
+def golden():
+    """The reference's shipped result file + input grids (tests/golden/multiple_sys.npz)."""
+    return dict(np.load(os.path.join(GOLD, "multiple_sys.npz")))
+
+
+@pytest.fixture(scope="session")
+def known():
+    """Answers produced by the untouched reference behind shims (oracle/make_golden.py)."""
+    with open(os.path.join(GOLD, "ref_known_answers.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def golden_norm2():
+    return dict(np.load(os.path.join(GOLD, "ref_norm2_subset.npz")))
+
+
+@pytest.fixture(scope="session")
+def example():
+    """Constants of working_example_single.py:20-27 / working_example_multiple.py:13-76."""
+    A = np.array([[1, 0.7], [0.12, 0.4]])
+    B = np.array([[1], [1.2]])
+    return dict(A=A, B=B, Q=2 * np.eye(2), R=np.eye(1), lo=np.array([-0.1]), hi=np.array([0.1]),
+                F_u=np.array([[10.0], [-10.0]]), p=np.array([0.1, 1, 0.6]),
+                info_N={'N_min': 6, 'N_max': 10, 'N_nominal': 7, 'N_opc': 30, 'N_mpc': 30},
+                info_e={'e_min': 1e-3, 'e_max': 1e-2, 'e_nominal': 5e-3})
+
+
+@pytest.fixture(scope="session")
+def engine():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from lq_mpc_b200.engine import Engine
+    return Engine(0)
+
+
+def relerr(a, b):
+    a = np.asarray(a, dtype=float)
+    b = np.asarray(b, dtype=float)
+    fin = np.isfinite(b)
+    assert np.array_equal(np.isfinite(a), fin), "finite masks differ"
+    if not fin.any():
+        return 0.0
+    return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)))

@@ -6,7 +6,7 @@
 
 #include <vector>
 
-#include "../../lq_mpc_b200/csrc/clqr.cuh"
+#include "../../lq_mpc_b200/csrc/bounds.cuh"
 
 #define HM_FOR_EACH_DIM(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 4) X(6, 2) X(8, 2)
 
@@ -124,6 +124,43 @@ int mpc_t(int mode, const double* A, const double* B, const double* Q, const dou
   return 0;
 }
 
+// bounds for S samples (SoA operands); K_in may be NULL (-> -K_dlqr by SDA). scal: N,eA,eB,MV (per sample arrays)
+template <int n, int m>
+int bounds_t(const double* A, const double* B, const double* Q, const double* R, const double* P, const double* lo,
+             const double* hi, int64_t S, const double* dA, const double* dB, int N, const double* eA,
+             const double* eB, const double* MV, const double* x, const double* K_in, const double* p3,
+             double V_expert, int strict, double* detail, double* K_out, double* P_out, int32_t* flags) {
+  lq::Problem<n, m> pb;
+  fill_problem<n, m>(pb, A, B, Q, R, P, lo, hi, 1);
+  std::vector<double> wsbuf((size_t)lq::bounds_ws_doubles<n, m>(N));
+  const lq::WsView ws{wsbuf.data(), 1};
+  for (int64_t s = 0; s < S; ++s) {
+    double Ah[n * n], Bh[n * m], K[m * n], xx[n], X[n * n];
+    for (int e = 0; e < n * n; ++e) Ah[e] = pb.A[e] + (dA ? dA[e * S + s] : 0.0);
+    for (int e = 0; e < n * m; ++e) Bh[e] = pb.B[e] + (dB ? dB[e * S + s] : 0.0);
+    int fl = 0;
+    if (K_in) {
+      for (int e = 0; e < m * n; ++e) K[e] = K_in[e * S + s];
+    } else {
+      if (!lq::dare_sda<n, m>(Ah, Bh, pb.Q, pb.R, X)) fl |= lq::FLAG_DARE_NOCONV;
+      lq::dlqr_gain<n, m>(Ah, Bh, pb.R, X, K);
+      for (int e = 0; e < m * n; ++e) K[e] = -K[e];
+      if (P_out) for (int e = 0; e < n * n; ++e) P_out[e * S + s] = X[e];
+    }
+    for (int i = 0; i < n; ++i) xx[i] = x[i * S + s];
+    lq::BoundsScalars sc;
+    sc.N = N; sc.e_A = eA[s]; sc.e_B = eB[s]; sc.M_V = MV[s];
+    sc.p[0] = p3[0]; sc.p[1] = p3[1]; sc.p[2] = p3[2];
+    sc.V_expert = V_expert; sc.bar_u = -1.0; sc.bar_d_u = -1.0; sc.strict_reference = strict;
+    double out[lq::BF_COUNT];
+    fl |= lq::bounds_sample<n, m>(pb, Ah, Bh, K, xx, sc, ws, out);
+    for (int f = 0; f < lq::BF_COUNT; ++f) detail[(int64_t)f * S + s] = out[f];
+    if (K_out) for (int e = 0; e < m * n; ++e) K_out[e * S + s] = K[e];
+    flags[s] = fl;
+  }
+  return 0;
+}
+
 template <int n>
 int rho_t(int64_t S, const double* M, double* rho, int32_t* okf) {
   for (int64_t s = 0; s < S; ++s) {
@@ -163,6 +200,21 @@ int hm_mpc(int mode, int n, int m, const double* A, const double* B, const doubl
 #define X_(N_, M_) \
   if (n == N_ && m == M_) \
     return mpc_t<N_, M_>(mode, A, B, Q, R, P, lo, hi, S, dA, dB, N, T, npts, pts, x0, V, u0, M_V, J_T, X, U, flags, n_active);
+  HM_FOR_EACH_DIM(X_)
+#undef X_
+  return -1;
+}
+
+int hm_bounds_fields(void) { return (int)lq::BF_COUNT; }
+
+int hm_bounds(int n, int m, const double* A, const double* B, const double* Q, const double* R, const double* P,
+              const double* lo, const double* hi, int64_t S, const double* dA, const double* dB, int N,
+              const double* eA, const double* eB, const double* MV, const double* x, const double* K_in,
+              const double* p3, double V_expert, int strict, double* detail, double* K_out, double* P_out,
+              int32_t* flags) {
+#define X_(N_, M_) \
+  if (n == N_ && m == M_) \
+    return bounds_t<N_, M_>(A, B, Q, R, P, lo, hi, S, dA, dB, N, eA, eB, MV, x, K_in, p3, V_expert, strict, detail, K_out, P_out, flags);
   HM_FOR_EACH_DIM(X_)
 #undef X_
   return -1;

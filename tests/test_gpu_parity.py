@@ -1,0 +1,458 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`). Everything goes through the C ABI
+(lq_mpc_b200.engine -> liblqmpc_b200.so) or through the drop-in classes on top of it, and is compared with
+  * the reference's shipped golden file and the answers generated from the untouched reference (tests/golden/),
+  * the CPU oracle (oracle/np_oracle.py, oracle/np_batched.py) on the same seeded inputs.
+Tolerance: 1e-9 relative (BASELINE.json north_star) unless a test states a tighter one.
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from tests.conftest import relerr
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-9
+
+
+def _soa(dA, dB, x0):
+    from oracle import np_batched as nb
+    return nb.to_soa(dA, dB, x0)
+
+
+# ------------------------------------------------------------------------------------------------------- K1
+@pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
+                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02)])
+def test_k1_matches_oracle(engine, n, m, e):
+    from oracle import np_batched as nb
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    S = 4099                                            # ragged: not a multiple of the block size
+    dA, dB, x0 = nb.synth_samples(n, m, S, seed=1, e=e)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, 2, 11, T=25, want_K=True)
+    got = engine.eval_batch(*_soa(dA, dB, x0), 2, 11, T=25, want=("J", "rho", "ratio", "flags", "V_N", "J_T", "K0"))
+    g = {k: v.cpu().numpy() for k, v in got.items()}
+    assert relerr(engine.prepared()["Pexp"], Pexp) < 1e-12
+    # samples whose closed loop is within 1e-6 of the stability boundary have an ill-conditioned J_inf
+    well = np.abs(ref["rho"] - 1.0) > 1e-6
+    assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"])
+    for k, kr in (("rho", "rho"), ("V_N", "Vn"), ("J_T", "JT")):
+        assert relerr(g[k], ref[kr]) < TOL, k
+    for k in ("J", "ratio"):
+        assert relerr(np.where(well, g[k], 0.0), np.where(well, ref[k], 0.0)) < 1e-8, k
+    K = g["K0"].reshape(10, m, n, S).transpose(0, 3, 1, 2)
+    assert np.max(np.abs(K - ref["K0"])) < 1e-10 * max(1.0, np.max(np.abs(ref["K0"])))
+    assert not np.any(g["flags"] & ~1)
+
+
+def test_k1_per_sample_oracle_and_edges(engine):
+    """Independent per-sample oracle (scipy Lyapunov/eig) + edge cases: S=1, S=0, N=1, nested == single horizon."""
+    from oracle import np_batched as nb, np_oracle as o
+    A, B, Q, R = nb.synth_problem(4, 2, seed=3)
+    engine.set_problem(A, B, Q, R, Q, None, None, 0)          # N_opc <= 0: DARE limit for the expert cost
+    P_inf = o.dlqr(A, B, Q, R)[1]
+    assert relerr(engine.prepared()["Pexp"], P_inf) < 1e-10
+    dA, dB, x0 = nb.synth_samples(4, 2, 64, seed=5, e=0.05)
+    got = engine.eval_batch(*_soa(dA, dB, x0), 1, 6, want=("J", "rho", "ratio", "flags"))
+    J, rho, ratio = (got[k].cpu().numpy() for k in ("J", "rho", "ratio"))
+    for s in range(0, 64, 7):
+        for N in (1, 3, 6):
+            K = o.riccati(A + dA[s], B + dB[s], Q, R, Q, N)[0][0]
+            Jr, rr = o.closed_loop_inf_cost(A, B, K, Q, R, x0[s])
+            assert abs(rho[N - 1, s] - rr) <= TOL * rr
+            if math.isinf(Jr):
+                assert math.isinf(J[N - 1, s]) and math.isinf(ratio[N - 1, s])
+                continue
+            assert abs(J[N - 1, s] - Jr) <= TOL * abs(Jr)
+            assert abs(ratio[N - 1, s] - Jr / (x0[s] @ P_inf @ x0[s])) <= TOL * ratio[N - 1, s]
+    one = engine.eval_batch(*_soa(dA[:1], dB[:1], x0[:1]), 6, 6)
+    assert one["J"].shape == (1, 1) and float(one["J"][0, 0]) == J[5, 0]         # nested == single, bit for bit
+    empty = engine.eval_batch(np.zeros((16, 0)), np.zeros((8, 0)), np.zeros((4, 0)), 1, 2)
+    assert empty["J"].shape == (2, 0)
+
+
+def test_k1_unstable_flagged(engine):
+    """An estimated model far from the plant gives an unstable closed loop: J = +inf, flag bit 0, rho >= 1."""
+    A = np.array([[1.2, 0.5], [0.0, 1.1]])
+    B = np.array([[0.0], [1.0]])
+    engine.set_problem(A, B, np.eye(2), np.eye(1), np.eye(2), None, None, 30)
+    dA = np.zeros((4, 2)); dB = np.zeros((2, 2)); x0 = np.ones((2, 2))
+    dB[1, 1] = -2.5                                     # controller believes the input gain has the opposite sign
+    got = engine.eval_batch(dA, dB, x0, 5, 5)
+    J, rho, fl = (got[k].cpu().numpy()[0] for k in ("J", "rho", "flags"))
+    assert np.isfinite(J[0]) and fl[0] == 0 and rho[0] < 1
+    assert np.isinf(J[1]) and (fl[1] & 1) and rho[1] >= 1
+
+
+def test_k1_full_size_properties(engine):
+    """BASELINE size (1.25e7 samples per GPU): size-independent properties instead of an oracle run.
+    J is quadratic in x0 (J(2 x0) = 4 J(x0) exactly in binary FP), rho and ratio do not depend on the scaling,
+    the host-buffer pipeline returns exactly the device-resident result, a subsample matches the oracle."""
+    import torch
+    from lq_mpc_b200 import sampling as sp
+    from oracle import np_batched as nb
+    S = 12_500_000
+    A, B, Q, R = sp.synth_problem(4, 2, seed=0)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    g = torch.Generator(device="cuda").manual_seed(7)
+    dA = (torch.rand((16, S), device="cuda", dtype=torch.float64, generator=g) - 0.5) * 0.02
+    dB = (torch.rand((8, S), device="cuda", dtype=torch.float64, generator=g) - 0.5) * 0.02
+    x0 = torch.randn((4, S), device="cuda", dtype=torch.float64, generator=g)
+    r1 = engine.eval_batch(dA, dB, x0, 10, 10)
+    r2 = engine.eval_batch(dA, dB, 2.0 * x0, 10, 10)
+    assert torch.equal(r2["J"], 4.0 * r1["J"])
+    assert torch.equal(r2["rho"], r1["rho"])
+    assert torch.equal(r2["ratio"], r1["ratio"])
+    assert int((r1["flags"] != 0).sum()) == 0
+    assert float(r1["ratio"].min()) >= 1.0 - 1e-9       # the expert (N_opc=30, true model) is at least as good ... to 1e-9
+    idx = torch.arange(0, S, 9973, device="cuda")
+    sub = [t[:, idx].cpu().numpy() for t in (dA, dB, x0)]
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, sub[0].T.reshape(-1, 4, 4), sub[1].T.reshape(-1, 4, 2), sub[2].T, 10, 10)
+    assert relerr(r1["J"][:, idx].cpu().numpy(), ref["J"]) < TOL
+    assert relerr(r1["rho"][:, idx].cpu().numpy(), ref["rho"]) < TOL
+    # host path on a slice (pinned host buffers, chunked pipeline)
+    Sh = 1_000_003
+    h = [t[:, :Sh].contiguous().cpu().pin_memory() for t in (dA, dB, x0)]
+    out = engine.eval_batch_host(h[0], h[1], h[2], 10, 10, chunk=1 << 18)
+    assert torch.equal(out["J"], r1["J"][:, :Sh].cpu())
+    assert torch.equal(out["ratio"], r1["ratio"][:, :Sh].cpu())
+    assert torch.equal(out["flags"], r1["flags"][:, :Sh].cpu())
+
+
+# ------------------------------------------------------------------------------------------------------- K2
+def test_mpc_test_scenario(known):
+    """mpc_test.py:13-56 through the drop-in classes vs the untouched reference."""
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_MPC_Simulator
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q = 2 * np.eye(2); R = np.eye(1)
+    x0 = np.array([0.1125, 0.19])
+    F_u = np.vstack((10 * np.eye(1), -10 * np.eye(1)))
+    info = LQ_MPC_Controller(20, A, B, Q, R, Q, F_u).solve(x0, np.zeros((2, 20)), np.zeros((1, 20)))
+    k = known["mpc_test"]
+    assert abs(info["V_N"] - k["V_N"]) < TOL * k["V_N"]
+    assert info["u_0"].shape == (1,) and abs(info["u_0"][0] - k["u_0"][0]) < 1e-12
+    A_true = np.array([[1.01, 0.7], [0.12, 0.41]]); B_true = np.array([[1], [1.21]])
+    sim = LQ_MPC_Simulator(20, 6, A, B, Q, R, Q, F_u)
+    r = sim.simulate(x0, A_true, B_true, np.zeros((2, 20)), np.zeros((1, 20)))
+    assert abs(r["J_T"] - k["J_T"]) < TOL * k["J_T"]
+    assert r["X"] is sim.X and r["U"] is sim.U                       # aliasing of instance buffers, as the reference
+    assert np.max(np.abs(r["X"] - np.array(k["X"]))) < 1e-12
+    assert np.max(np.abs(r["U"] - np.array(k["U"]))) < 1e-12
+
+
+def test_random_api_cases(known):
+    """Randomised reference calls (n in {2,3}, m in {1,2}): solve, simulate, energy_bound / energy_decreasing."""
+    from lq_mpc_b200.control import dlqr
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_MPC_Simulator, LQ_RDP_Calculator
+    n_raise = 0
+    for c in known["random_api"]:
+        n, m, N, T = c["n"], c["m"], c["N"], c["T"]
+        A, B, dA, dB = (np.array(c[k]) for k in ("A", "B", "dA", "dB"))
+        Q, R = c["q"] * np.eye(n), c["r"] * np.eye(m)
+        F_u = np.vstack((np.eye(m) / c["ub"], -np.eye(m) / c["ub"]))
+        x0 = np.array(c["x0"])
+        xr, ur = np.zeros((n, N)), np.zeros((m, N))
+        sol = LQ_MPC_Controller(N, A + dA, B + dB, Q, R, Q, F_u).solve(x0, xr, ur)
+        assert abs(sol["V_N"] - c["V_N"]) < TOL * abs(c["V_N"])
+        assert np.max(np.abs(sol["u_0"] - np.array(c["u_0"]))) < 1e-10
+        sim = LQ_MPC_Simulator(T, N, A + dA, B + dB, Q, R, Q, F_u).simulate(x0, A, B, xr, ur)
+        assert abs(sim["J_T"] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"] - np.array(c["U"]))) < 1e-10
+        if "K_dlqr" in c:
+            K, _, _ = dlqr(A + dA, B + dB, Q, R)
+            assert np.max(np.abs(K - np.array(c["K_dlqr"]))) < 1e-9 * max(1.0, np.max(np.abs(K)))
+            calc = LQ_RDP_Calculator(A + dA, B + dB, Q, R, F_u)
+            if "raises" in c:
+                with pytest.raises(ValueError):
+                    calc.energy_decreasing(N, c["e"], c["e"], -K, c["M_V"])
+                n_raise += 1
+            else:
+                dec = calc.energy_decreasing(N, c["e"], c["e"], -K, c["M_V"])
+                bnd = calc.energy_bound(N, c["e"], c["e"], x0, np.array([0.1, 1, 0.6]))
+                for k, v in (("xi", dec["xi"]), ("eta", dec["eta"]), ("alpha", bnd["alpha"]), ("beta", bnd["beta"])):
+                    assert abs(v - c[k]) < TOL * abs(c[k]), (k, v, c[k])
+    assert n_raise > 0
+
+
+def test_clqr_stress_vs_dense_qp(engine):
+    """Heavily saturated random problems: batched K2 vs the dense Cholesky+BVLS oracle (per problem: one engine
+    problem, 48 initial states)."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(11)
+    n_active = 0
+    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1)]:
+        for rep in range(3):
+            N = int(rng.integers(2, min(24, 64 // m) + 1))
+            A = rng.normal(size=(n, n))
+            A *= rng.uniform(0.6, 1.25) / np.max(np.abs(np.linalg.eigvals(A)))
+            B = rng.normal(size=(n, m))
+            Mq, Mr = rng.normal(size=(n, n)), rng.normal(size=(m, m))
+            Q = Mq @ Mq.T + 0.3 * np.eye(n) if rep == 2 else rng.uniform(0.5, 3) * np.eye(n)
+            R = Mr @ Mr.T + 0.2 * np.eye(m) if rep == 2 else rng.uniform(0.1, 2) * np.eye(m)
+            lo, hi = -rng.uniform(0.05, 0.4, size=m), rng.uniform(0.05, 0.4, size=m)
+            engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+            S = 48
+            x0 = rng.normal(size=(n, S)) * rng.uniform(0.2, 2.0)
+            dA = rng.uniform(-0.03, 0.03, size=(n * n, S)); dB = rng.uniform(-0.03, 0.03, size=(n * m, S))
+            got = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+            V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
+            assert not np.any(fl & ~2)
+            n_active += int(np.sum(fl & 2) // 2)
+            for s in range(0, S, 5):
+                ur, Vr, _ = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi,
+                                        x0[:, s], exact_fast=False)
+                assert abs(V[0, s] - Vr) < 1e-8 * abs(Vr)
+                assert np.max(np.abs(u0[0, :, s] - ur)) < 1e-8
+    assert n_active > 100
+
+
+def test_clqr_max_working_set_size(engine):
+    """N*m = 64 is the largest working set (64-bit mask); N*m = 65 with an active bound must flag QP_MAXITER."""
+    A = np.array([[1.0, 0.3], [0.0, 1.0]]); B = np.array([[0.0], [1.0]])
+    engine.set_problem(A, B, np.eye(2), np.eye(1), np.eye(2), [-0.05], [0.05], 10)
+    from oracle import np_oracle as o
+    x0 = np.array([[1.0], [0.5]])
+    got = engine.mpc_solve_batch(None, None, 64, x0=x0, S=1)
+    ur, Vr, act = o.mpc_solve(64, A, B, np.eye(2), np.eye(1), np.eye(2), np.array([-0.05]), np.array([0.05]), x0[:, 0],
+                              exact_fast=False)
+    assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
+    over = engine.mpc_solve_batch(None, None, 65, x0=x0, S=1)
+    assert int(over["flags"][0, 0]) & 4
+
+
+# ------------------------------------------------------------------------------------------------------- K3
+def test_working_example_single(known):
+    """working_example_single.py:20-108 through the drop-in modules vs the untouched reference."""
+    from lq_mpc_b200 import control as ct
+    from lq_mpc_b200.utils import (circle_generator, ex_stability_bounds, ex_stability_lq, fc_ec_E, fc_ec_theta,
+                                   fc_omega_eta, local_radius, bar_u_solve, bar_d_u_solve)
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_RDP_Behavior, LQ_RDP_Calculator
+    k = known["single"]
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q = 2 * np.eye(2); R = np.eye(1); F_u = np.array([[10], [-10]])
+    K_lqr, P_lqr, _ = ct.dlqr(A, B, Q, R)
+    assert relerr(K_lqr, k["K_lqr"]) < TOL and relerr(P_lqr, k["P_lqr"]) < TOL
+    eps = local_radius(F_u, -K_lqr, Q)
+    assert abs(eps - k["epsilon_lqr"]) < TOL * eps
+    x0_vec = circle_generator(8, 1.5, eps, Q)
+    assert np.max(np.abs(x0_vec - np.array(k["x0_vec"]))) < 1e-12
+    N = 6
+    x_ref, u_ref = np.zeros((2, N)), np.zeros((1, N))
+    beh = LQ_RDP_Behavior(A, B, Q, R, F_u, -K_lqr, 6, 10, -6, -2)
+    M_V = beh.OL_energy_bound(N, 8, 1.5, x_ref, u_ref)
+    assert abs(M_V - k["M_V"]) < TOL * M_V
+    mpc = LQ_MPC_Controller(N, A, B, Q, R, Q, F_u)
+    for i in range(8):
+        r = mpc.solve(x0_vec[:, i], x_ref, u_ref)
+        assert abs(r["V_N"] - k["ring_V"][i]) < TOL * r["V_N"]
+        assert abs(r["u_0"][0] - k["ring_u0"][i][0]) < 1e-11
+    ex = ex_stability_lq(A, B, Q, R, -K_lqr)
+    for f in ("C_K", "lambda_K", "rho_K", "gamma", "rho_gamma"):
+        assert abs(ex[f] - k["ex"][f]) < TOL * abs(k["ex"][f]), f
+    bar = ex_stability_bounds(ex["gamma"], eps, M_V)
+    assert bar["N_0"] == k["bar"]["N_0"] and abs(bar["L_V"] - k["bar"]["L_V"]) < TOL * bar["L_V"]
+    err = fc_omega_eta(N, A, B, Q, R, -K_lqr, bar["L_V"], bar["N_0"])
+    for f in ("omega_N1", "omega_N0d5", "eta", "err_th", "N_min"):
+        assert abs(err[f] - k["omega_eta"][f]) < TOL * abs(k["omega_eta"][f]), f
+    calc = LQ_RDP_Calculator(A, B, Q, R, F_u)
+    dec = calc.energy_decreasing(N, 0.01, 0.01, -K_lqr, M_V)
+    bnd = calc.energy_bound(N, 0.01, 0.01, x0_vec[:, 0], np.array([0.1, 1, 0.6]))
+    assert abs(dec["xi"] - k["decrease"]["xi"]) < TOL and abs(dec["eta"] - k["decrease"]["eta"]) < TOL
+    assert abs(bnd["alpha"] - k["bound"]["alpha"]) < TOL * bnd["alpha"]
+    assert abs(bnd["beta"] - k["bound"]["beta"]) < TOL * bnd["beta"]
+    assert bar_u_solve(F_u) == k["bar_u"] and abs(bar_d_u_solve(F_u) - k["bar_d_u"]) < 1e-15
+    E = fc_ec_E(N, 0.01, 0.01, A, B, Q, R, x0_vec[:, 0], bar_u_solve(F_u), bar_d_u_solve(F_u))
+    th = fc_ec_theta(N, 0.01, 0.01, A, B, 2.0)
+    for f in ("E_psi", "E_u", "E_psi_u"):
+        assert abs(E[f] - k["E"][f]) < TOL * abs(k["E"][f]), f
+    for f in ("theta_u", "theta_x_u"):
+        assert abs(th[f] - k["theta"][f]) < TOL * abs(k["theta"][f]), f
+
+
+def test_behavior_test_scenario(known):
+    """behavior_test.py:15-103 (curves + 4x4 mesh + two rings) through the drop-in LQ_RDP_Behavior."""
+    from lq_mpc_b200 import control as ct
+    from lq_mpc_b200.utils import circle_generator, local_radius
+    from lq_mpc_b200.utils_class import LQ_RDP_Behavior
+    k = known["behavior"]
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q = 2 * np.eye(2); R = np.eye(1); F_u = np.array([[10], [-10]])
+    K_lqr, _, _ = ct.dlqr(A, B, Q, R)
+    eps = local_radius(F_u, -K_lqr, Q)
+    N = 6
+    x_ref, u_ref = np.zeros((2, N)), np.zeros((1, N))
+    err_nominal = {'e_A': 0.01, 'e_B': 0.01}
+    p = np.array([0.1, 1, 0.6])
+    beh = LQ_RDP_Behavior(A, B, Q, R, F_u, -K_lqr, 6, 10, -6, -2)
+    M_V = beh.OL_energy_bound(N, 8, 1.5, x_ref, u_ref)
+    x0_vec = circle_generator(8, 1.5, eps, Q)
+    xi = beh.data_generation_xi(-K_lqr, M_V, N, err_nominal)
+    al, be = beh.data_generation_alpha_beta(x0_vec[:, 1], p, N, err_nominal)
+    for name, got in (("xi", xi), ("alpha", al), ("beta", be)):
+        for part in ("error", "horizon"):
+            assert relerr(got[part], k[name][part]) < TOL, (name, part)
+    sys_true = {'A_true': np.array([[1.01, 0.7], [0.12, 0.41]]), 'B_true': np.array([[1], [1.21]])}
+    info_ref = {'x_ref': x_ref, 'u_ref': u_ref, 'x_ref_long': np.zeros((2, 20)), 'u_ref_long': np.zeros((1, 20))}
+    quad = {'x': np.array([0.12, 0.16]), 'y': np.array([0.12, 0.16])}
+    mesh = beh.data_generation_mesh(N, {'T_mpc': 20, 'N_opc': 20}, sys_true, err_nominal, info_ref, M_V, p, quad)
+    for f in ("X", "Y", "J_MPC_true", "J_MPC_bound", "V_OPC"):
+        assert relerr(mesh[f], k["mesh"][f]) < TOL, f
+    plane = beh.data_generation_plane(N, {'T_mpc': 20, 'N_opc': 20}, sys_true, err_nominal, info_ref, M_V, p, 8,
+                                      np.array(k["plane_ratio"]))
+    for f in ("X", "J_MPC_true", "J_MPC_bound", "V_OPC"):
+        assert relerr(plane[f], k["plane"][f]) < TOL, f
+
+
+def _run_data_generation(tmp_path, golden, norm_type, N_matrix, example):
+    from lq_mpc_b200.utils_class import LQ_RDP_Behavior_Multiple
+    np.save(tmp_path / ("error_A_%s.npy" % norm_type), golden["error_A_" + norm_type])
+    np.save(tmp_path / ("error_B_%s.npy" % norm_type), golden["error_B_" + norm_type])
+    old = os.getcwd()
+    os.chdir(tmp_path)
+    try:
+        info_opc = {'A': example["A"], 'B': example["B"], 'Q': example["Q"], 'R': example["R"],
+                    'F_u': np.vstack((10 * np.eye(1), -10 * np.eye(1)))}
+        info_ref = {'x_ref': np.zeros([2, 7]), 'u_ref': np.zeros([1, 7]), 'x_ref_long': np.zeros([2, 30]),
+                    'u_ref_long': np.zeros([1, 30])}
+        beh = LQ_RDP_Behavior_Multiple(info_opc, example["info_N"], example["info_e"], N_matrix, norm_type)
+        out = beh.data_generation(8, 1.5, info_ref, example["p"])
+        saved = dict(np.load(tmp_path / "data_lq_mpc_multipleSys.npz"))
+    finally:
+        os.chdir(old)
+    return out, saved
+
+
+GOLDEN_KEYS = ["error", "horizon", "V_expert", "alpha_table_error", "beta_table_error", "xi_table_error",
+               "bound_table_error", "true_cost_error", "alpha_table_horizon", "beta_table_horizon",
+               "xi_table_horizon", "bound_table_horizon", "true_cost_horizon"]
+
+
+def test_golden_file_reproduced(tmp_path, golden, example):
+    """THE parity test: LQ_RDP_Behavior_Multiple.data_generation (working_example_multiple.py:98-101) on the GPU vs
+    the reference's shipped data_lq_mpc_multipleSys.npz — all 13 arrays (authors' run: cvxpy/control/Gurobi)."""
+    out, saved = _run_data_generation(tmp_path, golden, "f", 20, example)
+    assert sorted(out.keys()) == sorted(GOLDEN_KEYS) and sorted(saved.keys()) == sorted(GOLDEN_KEYS)
+    for k in GOLDEN_KEYS:
+        assert np.asarray(out[k]).shape == golden[k].shape, k
+        assert relerr(out[k], golden[k]) < TOL, k
+        assert relerr(saved[k], golden[k]) < TOL, k
+    # tighter where the reference's own third-party tolerances allow it
+    assert relerr(out["true_cost_error"], golden["true_cost_error"]) < 1e-13
+    assert relerr(out["alpha_table_error"], golden["alpha_table_error"]) < 1e-13
+
+
+def test_norm2_grid_subset(tmp_path, golden, golden_norm2, example):
+    """`_2` grids have no shipped outputs: compare with the untouched reference run on their first 5 systems."""
+    out, _ = _run_data_generation(tmp_path, golden, "2", 1, example)
+    for k in GOLDEN_KEYS:
+        assert relerr(out[k], golden_norm2[k]) < TOL, k
+
+
+def test_bounds_detail_vs_oracle(engine):
+    """Every intermediate of K3 vs the oracle, m in {1,2}, general (non-scalar) Q/R in both kron conventions."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(5)
+    checked = 0
+    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1), (1, 1)]:
+        for general in (False, True):
+            for strict in ((True, False) if general else (True,)):
+                N = int(rng.integers(1, 13))
+                A = rng.normal(size=(n, n)); A *= rng.uniform(0.3, 0.9) / np.max(np.abs(np.linalg.eigvals(A)))
+                B = rng.normal(size=(n, m))
+                if general:
+                    Mq, Mr = rng.normal(size=(n, n)), rng.normal(size=(m, m))
+                    Q, R = Mq @ Mq.T + np.eye(n), Mr @ Mr.T + np.eye(m)
+                else:
+                    Q, R = rng.uniform(0.5, 3) * np.eye(n), rng.uniform(0.5, 2) * np.eye(m)
+                lo, hi = -rng.uniform(0.05, 0.4, size=m), rng.uniform(0.05, 0.4, size=m)
+                engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+                S = 6
+                dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
+                e = rng.uniform(1e-4, 1e-2, size=S); MV = rng.uniform(0.05, 2.0, size=S)
+                x = rng.normal(size=(n, S)) * 0.3
+                p = np.array([0.1, 1, 0.6])
+                got = engine.bounds_batch(dA, dB, N, e, e, MV, x, p, 0.37, strict_reference=strict, want_K=True)
+                g = {k: v.cpu().numpy() for k, v in got.items()}
+                for s in range(S):
+                    Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+                    K, P = o.dlqr(Ah, Bh, Q, R)
+                    assert np.max(np.abs(g["K"][:, s].reshape(m, n) + K)) < 1e-9 * max(1, np.max(np.abs(K)))
+                    bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, e[s], e[s], x[:, s], p, strict_reference=strict)
+                    for f, fo in (("alpha", "alpha"), ("beta", "beta"), ("E_psi", "E_psi"), ("E_u", "E_u"),
+                                  ("E_psi_u", "E_psi_u"), ("min_H", "min_H"), ("norm_Gamma", "norm_Gamma"),
+                                  ("theta_u", "theta_u"), ("theta_x_u", "theta_x_u")):
+                        assert abs(g[f][s] - bnd[fo]) <= TOL * abs(bnd[fo]), (n, m, general, strict, f)
+                    try:
+                        dec = o.energy_decreasing(Ah, Bh, Q, R, lo, hi, N, e[s], e[s], -K, MV[s])
+                    except ValueError:
+                        assert g["flags"][s] & 512
+                        continue
+                    for f in ("xi", "eta", "C_K", "rho_K", "gamma", "rho_gamma", "L_V", "N_0", "omega_N1",
+                              "omega_N0d5", "err_th", "N_min", "h", "epsilon_K"):
+                        assert abs(g[f][s] - dec[f]) <= TOL * abs(dec[f]), (n, m, general, f)
+                    bound = (bnd["alpha"] * 0.37 + bnd["beta"]) / (1 - dec["xi"] - dec["eta"])
+                    assert abs(g["bound"][s] - bound) <= 1e-8 * abs(bound)
+                    checked += 1
+    assert checked > 40
+
+
+def test_bounds_long_horizon(engine, example):
+    """N = 50 (cfg-sweep upper end): 50 x 50 Gram matrix through the in-kernel tridiagonal/bisection path."""
+    from oracle import np_oracle as o
+    A, B, Q, R, lo, hi = (example[k] for k in ("A", "B", "Q", "R", "lo", "hi"))
+    engine.set_problem(A, B, Q, R, Q, lo, hi, 30)
+    rng = np.random.default_rng(2)
+    S = 5
+    dA = rng.uniform(-0.005, 0.005, size=(4, S)); dB = rng.uniform(-0.005, 0.005, size=(2, S))
+    x = np.array([0.15, 0.1]); p = example["p"]
+    for N, e in ((50, 1e-7), (23, 1e-6), (50, 5e-3)):
+        got = engine.bounds_batch(dA, dB, N, e, e, 0.2, x, p, 0.2)
+        g = {k: v.cpu().numpy() for k, v in got.items()}
+        for s in range(S):
+            Ah, Bh = A + dA[:, s].reshape(2, 2), B + dB[:, s].reshape(2, 1)
+            bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, e, e, x, p)
+            for f in ("alpha", "beta", "min_H", "norm_Gamma", "E_u"):
+                assert abs(g[f][s] - bnd[f]) <= TOL * abs(bnd[f]), (N, e, f)
+
+
+# ------------------------------------------------------------------------------------------------------- K5
+def test_column_stats_match_numpy(engine):
+    from lq_mpc_b200.stats import column_stats
+    rng = np.random.default_rng(0)
+    for cols, S in ((1, 1), (3, 7), (10, 100), (5, 100_003), (50, 20_000), (2, 3_000_001)):
+        t = rng.normal(loc=0.2, scale=1e-3, size=(cols, S))
+        st = column_stats(engine, t)
+        assert np.array_equal(st["max"], t.max(axis=1)) and np.array_equal(st["min"], t.min(axis=1))
+        assert relerr(st["mean"], t.mean(axis=1)) < 1e-12
+        assert relerr(st["std"], t.std(axis=1) if S > 1 else np.zeros(cols) + 1e-300) < 1e-9 or S == 1
+        assert np.all(st["count"] == S) and np.all(st["n_nonfinite"] == 0)
+    t = rng.normal(size=(2, 1000)); t[0, 5] = np.inf; t[1, 7] = np.nan; t[1, 9] = -np.inf
+    st = column_stats(engine, t)
+    assert list(st["n_nonfinite"]) == [1, 2] and list(st["count"]) == [999, 998]
+    fin = np.where(np.isfinite(t), t, np.nan)
+    assert relerr(st["mean"], np.nanmean(fin, axis=1)) < 1e-12 and relerr(st["max"], np.nanmax(fin, axis=1)) == 0
+
+
+def test_golden_column_stats(engine, golden):
+    """The reduction spec itself (utils.py:895-898) on the shipped tables."""
+    from lq_mpc_b200.utils import column_statistics
+    for k in ("bound_table_error", "true_cost_horizon", "xi_table_error"):
+        mx, mn, mean, std = column_statistics(golden[k])
+        assert np.array_equal(mx, golden[k].max(axis=0)) and np.array_equal(mn, golden[k].min(axis=0))
+        assert relerr(mean, golden[k].mean(axis=0)) < 1e-13 and relerr(std, golden[k].std(axis=0)) < 1e-9
+
+
+def test_errors_are_loud(engine):
+    from lq_mpc_b200.engine import EngineError
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller
+    with pytest.raises(EngineError):
+        engine.set_problem(np.eye(5), np.ones((5, 1)), np.eye(5), np.eye(1))        # (5,1) is not compiled
+    with pytest.raises(NotImplementedError):
+        LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
+                          np.array([[1.0, 1.0]])).solve(np.ones(2), None, None)     # non-box F_u (m = 2 row)
+    with pytest.raises(NotImplementedError):
+        LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
+                          np.array([[10.0], [-10.0]])).solve(np.ones(2), np.ones((2, 3)), np.zeros((1, 3)))
