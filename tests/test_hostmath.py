@@ -1,0 +1,175 @@
+"""CPU tier — the ENGINE'S OWN per-sample math (the __host__ __device__ templates under lq_mpc_b200/csrc/*.cuh that
+the sm_100a kernels instantiate) compiled with g++ into a TEST-ONLY harness (tests/hostmath) and compared with the
+oracle and the golden vectors in the GPU-less build container. This is not a CPU path of the product: nothing under
+lq_mpc_b200/ loads the harness, and the harness has no SoA pipeline, no reductions and no ABI.
+The GPU tier (tests/test_gpu_parity.py) repeats the comparisons through the C ABI on the real kernels.
+"""
+import numpy as np
+import pytest
+
+from oracle import np_batched as nb
+from oracle import np_oracle as o
+from tests.conftest import relerr
+
+hm = pytest.importorskip("tests.hostmath.api")
+TOL = 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 4, 6, 8])
+def test_spectral_radius_vs_lapack(n):
+    rng = np.random.default_rng(n)
+    M = rng.normal(size=(300, n, n))
+    M[:20] *= 1e-3
+    M[20:40] *= 1e3
+    if n >= 2:
+        M[40] = np.eye(n)                                  # repeated eigenvalue
+        M[41] = np.triu(np.ones((n, n)))                   # defective (Jordan-like)
+        M[42] = 0.0
+        M[43] = np.diag(np.arange(1, n + 1.0))
+        rot = np.eye(n); rot[:2, :2] = [[0, -1], [1, 0]]   # eigenvalues on the unit circle
+        M[44] = rot
+    rho, ok = hm.spectral_radius(M)
+    ref = np.max(np.abs(np.linalg.eigvals(M)), axis=1)
+    assert np.all(ok == 1)
+    scale = np.maximum(ref, 1e-12 * np.linalg.norm(M, axis=(1, 2)))
+    err = np.abs(rho - ref) / np.where(scale > 0, scale, 1.0)
+    err[41] = min(err[41], 1e-12) if abs(rho[41] - 1.0) < 1e-4 else err[41]   # defective: sqrt(eps)-conditioned
+    assert err.max() < 1e-10, (int(err.argmax()), err.max())
+
+
+@pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
+                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02)])
+def test_k1_math_vs_batched_oracle(n, m, e):
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    S = 257
+    dA, dB, x0 = nb.synth_samples(n, m, S, seed=1, e=e)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, 2, 11, T=25, want_K=True)
+    got = hm.eval_batch(A, B, Q, R, Q, 30, *nb.to_soa(dA, dB, x0), 2, 11, 25)
+    assert relerr(got["prep"][:n * n].reshape(n, n), Pexp) < 1e-12
+    well = np.abs(ref["rho"] - 1.0) > 1e-6
+    assert np.array_equal((got["flags"] & 1) != 0, ref["unstable"])
+    for k, kr in (("rho", "rho"), ("V_N", "Vn"), ("J_T", "JT")):
+        assert relerr(got[k], ref[kr]) < TOL, k
+    for k in ("J", "ratio"):
+        assert relerr(np.where(well, got[k], 0.0), np.where(well, ref[k], 0.0)) < 1e-8, k
+    K = got["K0"].reshape(10, m, n, S).transpose(0, 3, 1, 2)
+    assert np.max(np.abs(K - ref["K0"])) < 1e-10 * max(1.0, np.max(np.abs(ref["K0"])))
+    assert not np.any(got["flags"] & ~1)
+
+
+def test_k2_math_mpc_test_and_random_api(known):
+    """Exact box-constrained solves / closed loops vs the untouched reference's answers."""
+    k = known["mpc_test"]
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q = 2 * np.eye(2); R = np.eye(1); lo, hi = np.array([-0.1]), np.array([0.1])
+    x0 = np.array([[0.1125], [0.19]])
+    sol = hm.mpc(0, A, B, Q, R, Q, lo, hi, None, None, 20, x0_soa=x0)
+    assert abs(sol["V"][0, 0] - k["V_N"]) < TOL * k["V_N"] and abs(sol["u0"][0, 0, 0] - k["u_0"][0]) < 1e-12
+    assert sol["flags"][0, 0] == 2
+    dA = (np.array([[1.01, 0.7], [0.12, 0.41]]) - A).reshape(4, 1)
+    dB = (np.array([[1], [1.21]]) - B).reshape(2, 1)
+    # plant = (A_true, B_true) is the PROBLEM; the controller model is plant + (A - A_true)
+    At, Bt = A + dA.reshape(2, 2), B + dB.reshape(2, 1)
+    sim = hm.mpc(1, At, Bt, Q, R, Q, lo, hi, -dA, -dB, 6, T=20, x0_soa=x0)
+    assert abs(sim["J_T"][0] - k["J_T"]) < TOL * k["J_T"]
+    assert np.max(np.abs(sim["X"][:, :, 0].T - np.array(k["X"]))) < 1e-12
+    assert np.max(np.abs(sim["U"][:, :, 0].T - np.array(k["U"]))) < 1e-12
+    for c in known["random_api"]:
+        n, m, N, T = c["n"], c["m"], c["N"], c["T"]
+        A, B, dA, dB = (np.array(c[x]) for x in ("A", "B", "dA", "dB"))
+        Q, R = c["q"] * np.eye(n), c["r"] * np.eye(m)
+        lo, hi = -c["ub"] * np.ones(m), c["ub"] * np.ones(m)
+        x0 = np.array(c["x0"]).reshape(n, 1)
+        sol = hm.mpc(0, A, B, Q, R, Q, lo, hi, dA.reshape(-1, 1), dB.reshape(-1, 1), N, x0_soa=x0)
+        assert abs(sol["V"][0, 0] - c["V_N"]) < TOL * abs(c["V_N"])
+        assert np.max(np.abs(sol["u0"][0, :, 0] - np.array(c["u_0"]))) < 1e-10
+        sim = hm.mpc(1, A, B, Q, R, Q, lo, hi, dA.reshape(-1, 1), dB.reshape(-1, 1), N, T=T, x0_soa=x0)
+        assert abs(sim["J_T"][0] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"][:, :, 0].T - np.array(c["U"]))) < 1e-10
+
+
+def _golden_inputs(golden, rows):
+    eA = np.ascontiguousarray(golden["error_A_f"][:, :, rows, :]).reshape(4, -1)
+    eB = np.ascontiguousarray(golden["error_B_f"][:, :, rows, :]).reshape(2, -1)
+    return eA, eB
+
+
+def test_k2_k3_math_reproduce_golden_error_tables(golden, example, known):
+    """True cost (K2 simulate), M_V (K2 solve over the ring) and alpha/beta/xi/bound (K3) for 12 systems x 10 levels."""
+    rows = slice(0, 12)
+    A, B, Q, R, lo, hi = (example[x] for x in ("A", "B", "Q", "R", "lo", "hi"))
+    eA, eB = _golden_inputs(golden, rows)
+    ring = np.array(known["single"]["x0_vec"])                        # (2, 8): circle_generator(8, 1.5, eps_lqr, Q)
+    x_start = ring[:, 1]
+    S = eA.shape[1]
+    sim = hm.mpc(1, A, B, Q, R, Q, lo, hi, eA, eB, 7, T=30, pts=x_start[None])
+    assert relerr(sim["J_T"].reshape(12, 10), golden["true_cost_error"][rows]) < TOL
+    mv = hm.mpc(0, A, B, Q, R, Q, lo, hi, eA, eB, 7, pts=ring.T)["M_V"]
+    e_per = np.tile(golden["error"], 12)
+    b = hm.bounds(A, B, Q, R, lo, hi, eA, eB, 7, e_per, e_per, mv, np.repeat(x_start[:, None], S, axis=1), None,
+                  example["p"], float(golden["V_expert"]))
+    for k, gk in (("alpha", "alpha_table_error"), ("beta", "beta_table_error"), ("xi", "xi_table_error"),
+                  ("bound", "bound_table_error")):
+        assert relerr(b[k].reshape(12, 10), golden[gk][rows]) < TOL, k
+
+
+def test_k3_math_horizon_tables_and_single_example(golden, example, known):
+    A, B, Q, R, lo, hi = (example[x] for x in ("A", "B", "Q", "R", "lo", "hi"))
+    ring = np.array(known["single"]["x0_vec"]); x_start = ring[:, 1]
+    rows = slice(0, 6)
+    eA = np.ascontiguousarray(golden["error_A_f"][:, :, rows, 4]).reshape(4, -1)     # level index 4 (utils_class.py:880)
+    eB = np.ascontiguousarray(golden["error_B_f"][:, :, rows, 4]).reshape(2, -1)
+    S = eA.shape[1]
+    for col, N in enumerate(golden["horizon"]):
+        N = int(N)
+        mv = hm.mpc(0, A, B, Q, R, Q, lo, hi, eA, eB, N, pts=ring.T)["M_V"]
+        e = np.full(S, 5e-3)
+        b = hm.bounds(A, B, Q, R, lo, hi, eA, eB, N, e, e, mv, np.repeat(x_start[:, None], S, axis=1), None,
+                      example["p"], float(golden["V_expert"]))
+        for k, gk in (("alpha", "alpha_table_horizon"), ("beta", "beta_table_horizon"), ("xi", "xi_table_horizon"),
+                      ("bound", "bound_table_horizon")):
+            assert relerr(b[k], golden[gk][rows, col]) < TOL, (k, N)
+        sim = hm.mpc(1, A, B, Q, R, Q, lo, hi, eA, eB, N, T=30, pts=x_start[None])
+        assert relerr(sim["J_T"], golden["true_cost_horizon"][rows, col]) < TOL
+    # working_example_single.py: every intermediate the script prints (zero perturbation, N=6, e=0.01, x = ring[:,0])
+    ks = known["single"]
+    z4, z2 = np.zeros((4, 1)), np.zeros((2, 1))
+    b = hm.bounds(A, B, Q, R, lo, hi, z4, z2, 6, np.array([0.01]), np.array([0.01]), np.array([ks["M_V"]]),
+                  ring[:, :1].copy(), None, example["p"], 0.2)
+    for key, ref in (("C_K", ks["ex"]["C_K"]), ("rho_K", ks["ex"]["rho_K"]), ("gamma", ks["ex"]["gamma"]),
+                     ("rho_gamma", ks["ex"]["rho_gamma"]), ("L_V", ks["bar"]["L_V"]), ("N_0", ks["bar"]["N_0"]),
+                     ("omega_N1", ks["omega_eta"]["omega_N1"]), ("omega_N0d5", ks["omega_eta"]["omega_N0d5"]),
+                     ("eta", ks["omega_eta"]["eta"]), ("err_th", ks["omega_eta"]["err_th"]),
+                     ("N_min", ks["omega_eta"]["N_min"]), ("xi", ks["decrease"]["xi"]),
+                     ("alpha", ks["bound"]["alpha"]), ("beta", ks["bound"]["beta"]), ("E_psi", ks["E"]["E_psi"]),
+                     ("E_u", ks["E"]["E_u"]), ("E_psi_u", ks["E"]["E_psi_u"]), ("theta_u", ks["theta"]["theta_u"]),
+                     ("theta_x_u", ks["theta"]["theta_x_u"]), ("epsilon_K", ks["epsilon_lqr"]),
+                     ("bar_u", ks["bar_u"]), ("bar_d_u", ks["bar_d_u"])):
+        assert abs(b[key][0] - ref) <= TOL * abs(ref), (key, b[key][0], ref)
+    assert relerr(-b["K"][:, 0], np.array(ks["K_lqr"]).ravel()) < TOL          # u = +Kx convention: K = -K_dlqr
+    assert relerr(b["P"][:, 0].reshape(2, 2), ks["P_lqr"]) < TOL
+
+
+def test_k3_math_vs_oracle_multi_input():
+    """m > 1 (where the reference itself raises, utils.py:356): the oracle restatement is the yardstick."""
+    for n, m, N in [(4, 2, 10), (3, 2, 6), (2, 2, 4)]:
+        A, B, Q, R = nb.synth_problem(n, m, seed=2)
+        Q = 1.5 * Q
+        lo, hi = -0.3 * np.ones(m), 0.4 * np.ones(m)
+        dA, dB, x0 = nb.synth_samples(n, m, 6, seed=4, e=0.01)
+        sA, sB, sx = nb.to_soa(dA, dB, x0)
+        e = np.full(6, 0.01); mv = np.linspace(0.5, 2.0, 6)
+        p = np.array([0.1, 1, 0.6])
+        b = hm.bounds(A, B, Q, R, lo, hi, sA, sB, N, e, e, mv, sx, None, p, 1.0)
+        for s in range(6):
+            Ah, Bh = A + dA[s], B + dB[s]
+            K, _ = o.dlqr(Ah, Bh, Q, R)
+            try:
+                dec = o.energy_decreasing(Ah, Bh, Q, R, lo, hi, N, 0.01, 0.01, -K, mv[s])
+            except ValueError:
+                assert b["flags"][s] & 512
+                continue
+            bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, 0.01, 0.01, x0[s], p)
+            for key, ref in (("xi", dec["xi"]), ("eta", dec["eta"]), ("alpha", bnd["alpha"]), ("beta", bnd["beta"])):
+                assert abs(b[key][s] - ref) <= TOL * abs(ref), (n, m, key)
