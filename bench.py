@@ -5,7 +5,8 @@ Metric (BASELINE.json): MPC performance evals/sec, 1 eval = one (sample, horizon
 horizon on the estimated model + closed loop on the true plant + J_inf (Lyapunov doubling) + spectral-radius
 stability check + performance ratio.  Workload: cfg-synth-4-2-10 (n=4, m=2, N=10, Q=I, R=I, unconstrained),
 1.25e7 seeded samples (dA, dB, x0) PER GPU (= BASELINE's 1e8 samples at 8 GPUs; weak scaling), followed by the
-per-column worst-case statistics (K5) and — at N>1 — the engine's only collective, tiny NCCL all-reduces of them.
+per-column worst-case statistics (K5, one pass) and — at N>1 — the engine's only collective, one tiny NCCL
+all-gather of the per-column moments.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (torchrun launches it for N > 1)
   python bench.py --impl reference ...                         the CPU arm: the numpy oracle port on all host cores
@@ -54,7 +55,7 @@ class ClockSampler:
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -151,7 +152,7 @@ def workload_config(n_gpus, note=None):
                        % (S_PER_GPU, S_PER_GPU * n_gpus),
            "n": N_DIM, "m": M_DIM, "N": HORIZON, "samples_per_gpu": S_PER_GPU, "evals_per_sample": 1,
            "l2": "inputs (2.8 GB per step) exceed the 126 MB L2; no flush needed",
-           "parallelism": "sample-sharded x%d, one final all-reduce of statistics" % n_gpus}
+           "parallelism": "sample-sharded x%d, one final all-gather of per-column moments (6 doubles/column)" % n_gpus}
     if note:
         cfg["note"] = note
     return cfg
@@ -193,9 +194,8 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def step():
-        r = eng.eval_batch(dA, dB, x0, HORIZON, HORIZON)
-        table = torch.stack([r["ratio"][0], r["J"][0], r["rho"][0]], dim=0)
-        st = column_stats(eng, table)
+        r = eng.eval_batch(dA, dB, x0, HORIZON, HORIZON)     # K1 writes J, rho, ratio into one [3][S] table
+        st = column_stats(eng, r["table"])                    # K5 (one pass) + the only collective (all-gather)
         return r, st
 
     def max_over_ranks(v):
@@ -231,7 +231,6 @@ def run_ours(args):
     k1.record()
     barrier()
     ms_kernel = k0.elapsed_time(k1) / args.steps
-    clocks = sampler.stop() if rank == 0 else None
     # ---- (3) end to end through the host-buffer entry point: pinned host -> H2D -> K1 -> D2H, every step
     outb = None
     for _ in range(2):
@@ -242,6 +241,7 @@ def run_ours(args):
         outb = eng.eval_batch_host(hA, hB, hx, HORIZON, HORIZON, out=outb, chunk=1 << 19)
     torch.cuda.synchronize()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
+    clocks = sampler.stop() if rank == 0 else None        # sampled across all three timed regions (GPU busy throughout)
     same = bool(torch.equal(outb["J"][0, :4096], r["J"][0, :4096].cpu()))
     peak_fp64 = eng.fp64_peak() if rank == 0 else 0.0
     unstable = int((r["flags"] & 1).sum().item())
@@ -264,6 +264,7 @@ def run_ours(args):
         traffic = None
         try:
             traffic = json.load(open(os.path.join(ROOT, "profiles", "k1_traffic.json"))).get("dram_bytes_per_launch")
+            # (latest `ncu --set full` capture of eval_kernel<4,2> on this workload; see profiles/README.md)
         except (OSError, ValueError):
             pass
         line = {
@@ -286,8 +287,8 @@ def run_ours(args):
                     "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
-            "worst_case": {"ratio_max": float(st["max"][0]), "ratio_mean": float(st["mean"][0]),
-                           "rho_max": float(st["max"][2]), "unstable": unstable},
+            "worst_case": {"ratio_max": float(st["max"][2]), "ratio_mean": float(st["mean"][2]),
+                           "ratio_std": float(st["std"][2]), "rho_max": float(st["max"][1]), "unstable": unstable},
         }
         if world == 1 and not args.no_cpu_baseline:
             v, workers, total = cpu_port_throughput(8_000)
@@ -303,7 +304,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

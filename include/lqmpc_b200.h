@@ -149,6 +149,12 @@ int lqmpc_column_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S,
 int lqmpc_column_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
                        double* sqdev);
 
+/* One-pass variant (what lq_mpc_b200/stats.py uses): moments [cols][6] = { max, min, count_finite, count_nonfinite,
+ * mean, M2 = sum (x - mean)^2 } over the finite entries of every column (shifted-data accumulation, fixed-order
+ * folds: deterministic). Shards are merged with Chan's pairwise update after ONE all-gather of these 6 numbers per
+ * column; std = sqrt(M2 / count) as np.std (utils.py:898). Empty column: mean = M2 = NaN, max = -inf, min = +inf. */
+int lqmpc_column_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* moments);
+
 /* DFMA-chain micro-benchmark: achieved FP64 FMA throughput of this device in TFLOP/s (2 flop per FMA), used as the
  * measured denominator of the FP64 roofline (MEASURED_PEAKS.json has none). Synchronises. */
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out);

@@ -364,6 +364,15 @@ int lqmpc_column_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S,
   return lq_launch_sqdev(ctx, table, cols, S, ld, mean, sqdev);
 }
 
+int lqmpc_column_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* moments) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!table || !moments || cols < 1 || S < 0 || ld < S)
+    return lq_set_error(ctx, LQMPC_EINVAL, "bad table/cols/S/ld");
+  if (cols > 65535) return lq_set_error(ctx, LQMPC_EINVAL, "too many columns");
+  cudaSetDevice(ctx->device);
+  return lq_launch_moments(ctx, table, cols, S, ld, moments);
+}
+
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out) {
   if (!ctx || !tflops_out) return LQMPC_EINVAL;
   cudaSetDevice(ctx->device);

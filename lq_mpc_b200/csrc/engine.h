@@ -108,6 +108,7 @@ int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);
 int lq_launch_bounds(lqmpc_ctx* ctx, const BoundsArgs& a);
 int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats);
+int lq_launch_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* out);
 int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
                     double* out);
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,

@@ -4,6 +4,8 @@
 // element (256 B, two full 128 B lines) with read-only, no-L1-allocate loads; every output is written the same way.
 // The problem constants arrive as a __grid_constant__ kernel parameter, i.e. in the constant bank: FMAs read
 // A, B, Q, R, Pexp as uniform constant operands and spend no registers on them.
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace {
@@ -37,9 +39,10 @@ struct DeviceSink {
   }
 };
 
-template <int n, int m>
-__global__ void __launch_bounds__(128) eval_kernel(const __grid_constant__ lq::Problem<n, m> pb,
-                                                   const __grid_constant__ EvalArgs a) {
+// MINB = minimum resident CTAs per SM the register allocator must allow (occupancy vs. spills; see K1Tune below)
+template <int n, int m, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+                                                         const __grid_constant__ EvalArgs a) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.S) return;
   double dA[n * n], dB[n * m], x0[n];
@@ -62,13 +65,34 @@ __global__ void prepare_kernel(lq::Problem<n, m>* pb, int N_opc) {
   }
 }
 
+// Register budget per (n, m): 128-thread CTAs, MINB CTAs/SM -> 65536 / (128 MINB) registers per thread.
+template <int n, int m>
+struct K1Tune {
+  // measured on B200 (scripts/k1_probe.py, n=4 m=2, 1.25e7 samples): 220 regs/no spills (MINB 1-2) 3.67 ms,
+  // 128 regs (MINB 4) 3.70 ms for N=10 only; with all horizons 1..10 emitted 19.5-22 ms vs 17.5 ms -> MINB 4.
+  static constexpr int minb = (n <= 4) ? 4 : 2;
+};
+
 template <int n, int m>
 int launch_eval_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int threads = 128;
   const int64_t blocks = (a.S + threads - 1) / threads;
   if (blocks > 0x7fffffffLL) return lq_set_error(ctx, -1, "batch too large for one launch");
-  eval_kernel<n, m><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+#ifdef LQ_K1_VARIANTS
+  if (n == 4 && m == 2) {   // development switch: occupancy experiments on the headline size
+    const char* v = getenv("LQMPC_K1_MINB");
+    const int mb = v ? atoi(v) : 0;
+    if (mb == 1) eval_kernel<n, m, 1><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+    else if (mb == 3) eval_kernel<n, m, 3><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+    else if (mb == 4) eval_kernel<n, m, 4><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+    else if (mb == 5) eval_kernel<n, m, 5><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+    else eval_kernel<n, m, 2><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+    ctx->launches++;
+    return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
+  }
+#endif
+  eval_kernel<n, m, K1Tune<n, m>::minb><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
 }

@@ -53,6 +53,7 @@ template <int n, int m>
 struct RicStage {
   double Y[n * m];
   double L[m * m];
+  double Li[m];        // reciprocals of L's diagonal
   bool ok;
 };
 
@@ -66,14 +67,14 @@ LQ_HD void riccati_factor(const double* P, const double* Bh, const double* R, Ri
       st.L[i * m + j] = acc;
       st.L[j * m + i] = acc;
     }
-  st.ok = chol<m>(st.L);
-  solve_right_lt<n, m>(st.L, st.Y);               // Y = PB L^-T
+  st.ok = chol_inv<m>(st.L, st.Li);
+  solve_right_lt_inv<n, m>(st.L, st.Li, st.Y);    // Y = PB L^-T
 }
 
 template <int n, int m>
 LQ_HD void riccati_gain(const RicStage<n, m>& st, const double* Ah, double* K) {
   mtm<n, m, n>(st.Y, Ah, K);                      // Y' A^   (m x n)
-  solve_lt<m, n>(st.L, K);                        // L^-T (.)
+  solve_lt_inv<m, n>(st.L, st.Li, K);             // L^-T (.)
   LQ_UNROLL for (int i = 0; i < m * n; ++i) K[i] = -K[i];
 }
 

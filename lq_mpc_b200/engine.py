@@ -53,6 +53,7 @@ ABI = {
     "lqmpc_dlqr_batch": (_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp]),
     "lqmpc_column_stats": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
     "lqmpc_column_sqdev": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp]),
+    "lqmpc_column_moments": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
     "lqmpc_fp64_peak": (_int, [_vp, _c_double_p]),
     "lqmpc_launch_count": (_i64, [_vp]),
 }
@@ -200,9 +201,12 @@ class Engine:
             raise ValueError("operand shapes do not match (n, m, S)")
         H = N_max - N_min + 1
         out = {}
-        for k in ("J", "rho", "ratio", "V_N", "J_T"):
-            if k in want:
-                out[k] = torch.empty((H, S), dtype=torch.float64, device=self.device)
+        names = [k for k in ("J", "rho", "ratio", "V_N", "J_T") if k in want]
+        # one allocation: out["table"] is the column-contiguous [len(names)*H][S] result table K5 reduces directly
+        table = torch.empty((len(names) * H, S), dtype=torch.float64, device=self.device)
+        for i, k in enumerate(names):
+            out[k] = table[i * H:(i + 1) * H]
+        out["table"], out["table_rows"] = table, [(k, N_min + h) for k in names for h in range(H)]
         if "flags" in want:
             out["flags"] = torch.empty((H, S), dtype=torch.int32, device=self.device)
         if "K0" in want:
@@ -369,6 +373,18 @@ class Engine:
         stats = torch.empty((cols, 5), dtype=torch.float64, device=self.device)
         self._check(self.lib.lqmpc_column_stats(self._h, _ptr(t), cols, S, S, _ptr(stats)), "lqmpc_column_stats")
         return stats
+
+    def column_moments_raw(self, table):
+        """table: [cols][S] device tensor. Returns device [cols][6] = max, min, n_finite, n_nonfinite, mean, M2."""
+        torch = self.torch
+        t = self._dev(table)
+        if t.ndim == 1:
+            t = t.reshape(1, -1)
+        cols, S = t.shape
+        out = torch.empty((cols, 6), dtype=torch.float64, device=self.device)
+        self._check(self.lib.lqmpc_column_moments(self._h, _ptr(t), cols, S, t.stride(0) if S else max(S, 1),
+                                                  _ptr(out)), "lqmpc_column_moments")
+        return out
 
     def column_sqdev_raw(self, table, mean):
         torch = self.torch

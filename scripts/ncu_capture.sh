@@ -3,6 +3,7 @@
 # Usage: gpurun --timeout 900 -- 'bash scripts/ncu_capture.sh r01'
 set -u
 TAG=${1:-r01}
+# NOTE: K1 launches per bench run = 3 warm-up + 2 timed steps + 2 kernel-only + e2e chunks; -s 3 skips the warm-up
 OUT=gpurun_out
 mkdir -p $OUT
 CMD="python bench.py --steps 2 --warmup 3 --no-cpu-baseline"

@@ -40,6 +40,17 @@ def spectral_radius(M):
     return rho, ok
 
 
+def spectral_radius_poly(M):
+    """Closed-form fast path alone (n = 3, 4): (rho, trusted)."""
+    M = _c(M)
+    S, n = M.shape[0], M.shape[1]
+    rho = np.zeros(S)
+    ok = np.zeros(S, dtype=np.int32)
+    rc = lib().hm_spectral_radius_poly(n, ctypes.c_int64(S), _p(M), _p(rho), ok.ctypes.data_as(_I32))
+    assert rc == 0
+    return rho, ok
+
+
 def eval_batch(A, B, Q, R, Pt, N_opc, dA_soa, dB_soa, x0_soa, Nmin, Nmax, T):
     n, m = B.shape
     S = dA_soa.shape[-1]

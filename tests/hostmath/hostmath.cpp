@@ -171,6 +171,17 @@ int rho_t(int64_t S, const double* M, double* rho, int32_t* okf) {
   return 0;
 }
 
+// fast (closed-form) path alone: rho and whether it was trusted (1) or would fall back to QR (0)
+template <int n>
+int rho_poly_t(int64_t S, const double* M, double* rho, int32_t* trusted) {
+  for (int64_t s = 0; s < S; ++s) {
+    double r = 0.0;
+    trusted[s] = lq::RhoFast<n>::run(M + s * n * n, &r) ? 1 : 0;
+    rho[s] = r;
+  }
+  return 0;
+}
+
 template <int n>
 int symeig_t(int64_t S, const double* M, double* lo, double* hi) {
   for (int64_t s = 0; s < S; ++s) lq::sym_eig_minmax<n>(M + s * n * n, lo + s, hi + s);
@@ -230,6 +241,14 @@ int hm_spectral_radius(int n, int64_t S, const double* M, double* rho, int32_t* 
     case 5: return rho_t<5>(S, M, rho, ok);
     case 6: return rho_t<6>(S, M, rho, ok);
     case 8: return rho_t<8>(S, M, rho, ok);
+  }
+  return -1;
+}
+
+int hm_spectral_radius_poly(int n, int64_t S, const double* M, double* rho, int32_t* trusted) {
+  switch (n) {
+    case 3: return rho_poly_t<3>(S, M, rho, trusted);
+    case 4: return rho_poly_t<4>(S, M, rho, trusted);
   }
   return -1;
 }

@@ -27,7 +27,7 @@ def test_header_declares_the_expected_entry_points():
     syms = _declared_symbols()
     for s in ("lqmpc_create", "lqmpc_destroy", "lqmpc_set_problem", "lqmpc_eval_batch", "lqmpc_eval_batch_host",
               "lqmpc_mpc_solve_batch", "lqmpc_simulate_batch", "lqmpc_bounds_batch", "lqmpc_dlqr_batch",
-              "lqmpc_column_stats", "lqmpc_column_sqdev", "lqmpc_last_error", "lqmpc_abi_version"):
+              "lqmpc_column_stats", "lqmpc_column_sqdev", "lqmpc_column_moments", "lqmpc_last_error", "lqmpc_abi_version"):
         assert s in syms
 
 

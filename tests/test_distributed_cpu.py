@@ -65,6 +65,25 @@ def test_sharded_stats_equal_single_process_numpy(world):
             assert np.array_equal(res[0][k], res[r][k], equal_nan=True)
 
 
+def test_merge_moments_matches_numpy_and_kernel_formula():
+    """Chan merge over ragged shards (incl. an empty one and an all-non-finite one) == numpy on the whole column;
+    `local_moments_numpy` restates the kernel's shifted-data formula."""
+    rng = np.random.default_rng(2)
+    table = 5.0 + rng.normal(size=(4, 5000)) * np.array([1e-6, 1.0, 1e3, 1e-2])[:, None]
+    table[1, 100:160] = np.inf
+    cuts = [0, 0, 60, 100, 160, 1700, 5000]                        # shard [100,160) of column 1 is all-inf
+    parts = [st.local_moments_numpy(table[:, a:b]) for a, b in zip(cuts, cuts[1:])]
+    out = st.merge_moments(np.stack(parts))
+    for c in range(4):
+        col = table[c][np.isfinite(table[c])]
+        assert out["max"][c] == col.max() and out["min"][c] == col.min() and out["count"][c] == col.size
+        assert abs(out["mean"][c] - col.mean()) <= 1e-14 * abs(col.mean())
+        assert abs(out["std"][c] - col.std()) <= 1e-9 * col.std()
+    assert out["n_nonfinite"][1] == 60
+    none = st.merge_moments(np.stack([st.local_moments_numpy(np.zeros((2, 0)))]))
+    assert np.all(none["count"] == 0) and np.all(np.isnan(none["mean"])) and np.all(np.isnan(none["std"]))
+
+
 def test_shard_bounds_partition():
     for S in (0, 1, 7, 100, 12_500_001):
         for world in (1, 2, 3, 8):

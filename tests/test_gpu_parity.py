@@ -33,7 +33,7 @@ def test_k1_matches_oracle(engine, n, m, e):
     Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
     ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, 2, 11, T=25, want_K=True)
     got = engine.eval_batch(*_soa(dA, dB, x0), 2, 11, T=25, want=("J", "rho", "ratio", "flags", "V_N", "J_T", "K0"))
-    g = {k: v.cpu().numpy() for k, v in got.items()}
+    g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
     assert relerr(engine.prepared()["Pexp"], Pexp) < 1e-12
     # samples whose closed loop is within 1e-6 of the stability boundary have an ill-conditioned J_inf
     well = np.abs(ref["rho"] - 1.0) > 1e-6
@@ -419,8 +419,10 @@ def test_bounds_long_horizon(engine, example):
 
 
 # ------------------------------------------------------------------------------------------------------- K5
-def test_column_stats_match_numpy(engine):
-    from lq_mpc_b200.stats import column_stats
+@pytest.mark.parametrize("which", ["one_pass", "two_pass"])
+def test_column_stats_match_numpy(engine, which):
+    from lq_mpc_b200 import stats
+    column_stats = stats.column_stats if which == "one_pass" else stats.column_stats_two_pass
     rng = np.random.default_rng(0)
     for cols, S in ((1, 1), (3, 7), (10, 100), (5, 100_003), (50, 20_000), (2, 3_000_001)):
         t = rng.normal(loc=0.2, scale=1e-3, size=(cols, S))
@@ -434,6 +436,33 @@ def test_column_stats_match_numpy(engine):
     assert list(st["n_nonfinite"]) == [1, 2] and list(st["count"]) == [999, 998]
     fin = np.where(np.isfinite(t), t, np.nan)
     assert relerr(st["mean"], np.nanmean(fin, axis=1)) < 1e-12 and relerr(st["max"], np.nanmax(fin, axis=1)) == 0
+    assert relerr(st["std"], np.nanstd(fin, axis=1)) < 1e-12
+    # a column whose first entry is non-finite (shift falls back to 0) and a large offset (cancellation guard)
+    t = 1e6 + rng.normal(scale=1e-2, size=(2, 50_001)); t[1, 0] = np.inf
+    st = column_stats(engine, t)
+    fin = np.where(np.isfinite(t), t, np.nan)
+    assert relerr(st["mean"], np.nanmean(fin, axis=1)) < 1e-13
+    assert relerr(st["std"][:1], np.nanstd(fin, axis=1)[:1]) < 1e-9     # shift = first entry: full accuracy
+    empty = column_stats(engine, np.zeros((2, 0)))
+    assert np.all(empty["count"] == 0) and np.all(np.isnan(empty["mean"]))
+
+
+def test_k1_table_view_is_what_k5_reduces(engine):
+    """eval_batch's outputs are rows of ONE contiguous table, reduced without a copy; both stats paths agree."""
+    from lq_mpc_b200 import stats
+    from oracle import np_batched as nb
+    A, B, Q, R = nb.synth_problem(4, 2, seed=0)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    dA, dB, x0 = nb.synth_samples(4, 2, 30_001, seed=1)
+    r = engine.eval_batch(*_soa(dA, dB, x0), 9, 10)
+    assert r["table"].shape == (6, 30_001) and r["table_rows"][:3] == [("J", 9), ("J", 10), ("rho", 9)]
+    assert r["J"].data_ptr() == r["table"].data_ptr() and r["ratio"].data_ptr() == r["table"][4].data_ptr()
+    a, b = stats.column_stats(engine, r["table"]), stats.column_stats_two_pass(engine, r["table"])
+    tab = r["table"].cpu().numpy()
+    for k in ("max", "min"):
+        assert np.array_equal(a[k], b[k]) and np.array_equal(a[k], getattr(tab, k)(axis=1))
+    assert relerr(a["mean"], tab.mean(axis=1)) < 1e-13 and relerr(b["mean"], tab.mean(axis=1)) < 1e-13
+    assert relerr(a["std"], tab.std(axis=1)) < 1e-10 and relerr(b["std"], tab.std(axis=1)) < 1e-10
 
 
 def test_golden_column_stats(engine, golden):
