@@ -180,6 +180,7 @@ class Engine:
         self.n, self.m = n, m
         self.A, self.B, self.Q, self.R, self.P = A, B, Q, R, P
         self.u_lo, self.u_hi = lo, hi
+        self.N_opc = int(N_opc)
         return self
 
     def prepared(self):
@@ -249,7 +250,12 @@ class Engine:
         dA, dB = self._opt_dev(dA), self._opt_dev(dB)
         if S is None:
             S = dA.shape[-1] if dA is not None else (x0.shape[-1] if x0 is not None else 1)
-        pts_d = None if pts is None else self._dev(np.asarray(pts, dtype=np.float64).reshape(-1, n))
+        if pts is None:
+            pts_d = None
+        elif isinstance(pts, torch.Tensor):
+            pts_d = self._dev(pts).reshape(-1, n)
+        else:
+            pts_d = self._dev(np.asarray(pts, dtype=np.float64).reshape(-1, n))
         x0_d = self._opt_dev(x0)
         P = pts_d.shape[0] if pts_d is not None else 1
         out = {}
@@ -370,6 +376,8 @@ class Engine:
         if t.ndim == 1:
             t = t.reshape(1, -1)
         cols, S = t.shape
+        if S == 0:
+            return torch.tensor([[-np.inf, np.inf, 0.0, 0.0, 0.0]] * cols, dtype=torch.float64, device=self.device)
         stats = torch.empty((cols, 5), dtype=torch.float64, device=self.device)
         self._check(self.lib.lqmpc_column_stats(self._h, _ptr(t), cols, S, S, _ptr(stats)), "lqmpc_column_stats")
         return stats
@@ -381,9 +389,11 @@ class Engine:
         if t.ndim == 1:
             t = t.reshape(1, -1)
         cols, S = t.shape
+        if S == 0:                                   # nothing to reduce (and no valid device pointer to pass)
+            return torch.tensor([[-np.inf, np.inf, 0.0, 0.0, np.nan, np.nan]] * cols, dtype=torch.float64,
+                                device=self.device)
         out = torch.empty((cols, 6), dtype=torch.float64, device=self.device)
-        self._check(self.lib.lqmpc_column_moments(self._h, _ptr(t), cols, S, t.stride(0) if S else max(S, 1),
-                                                  _ptr(out)), "lqmpc_column_moments")
+        self._check(self.lib.lqmpc_column_moments(self._h, _ptr(t), cols, S, S, _ptr(out)), "lqmpc_column_moments")
         return out
 
     def column_sqdev_raw(self, table, mean):
@@ -393,6 +403,8 @@ class Engine:
             t = t.reshape(1, -1)
         cols, S = t.shape
         mean = self._dev(mean).reshape(cols)
+        if S == 0:
+            return torch.zeros((cols,), dtype=torch.float64, device=self.device)
         out = torch.empty((cols,), dtype=torch.float64, device=self.device)
         self._check(self.lib.lqmpc_column_sqdev(self._h, _ptr(t), cols, S, S, _ptr(mean), _ptr(out)),
                     "lqmpc_column_sqdev")

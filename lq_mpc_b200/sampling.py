@@ -42,17 +42,23 @@ def reference_random_matrix(M, N_matrix, norm_bound, norm_type, rng=None, litera
                 k += 1
         return out
     rng = np.random.default_rng() if rng is None else rng
-    k = 0
-    while k < 5 * N_matrix:
-        T = rng.uniform(-norm_bound, norm_bound, size=(r, c))
-        nv = _norm(T, norm_type)
-        if k < N_matrix:
-            if nv > 0:
-                out[:, :, k] = T * (norm_bound / nv)
-                k += 1
-        elif nv <= norm_bound:
-            out[:, :, k] = T
-            k += 1
+    # vectorised: candidates are drawn in blocks (same stream order as one-by-one draws) and classified at once
+    ordv = 'fro' if norm_type == 'f' else 2
+    k, total = 0, 5 * N_matrix
+    while k < total:
+        blk = max(64, 4 * (total - k))
+        T = rng.uniform(-norm_bound, norm_bound, size=(blk, r, c))
+        nv = np.linalg.norm(T, ord=ordv, axis=(1, 2))
+        if k < N_matrix:                      # boundary samples: rescale onto ||.|| = bound (no isclose rejection)
+            ok = np.flatnonzero(nv > 0)[:N_matrix - k]
+            out[:, :, k:k + len(ok)] = np.moveaxis(T[ok] * (norm_bound / nv[ok])[:, None, None], 0, -1)
+            k += len(ok)
+            if k < N_matrix:
+                continue
+            T, nv = T[ok[-1] + 1:], nv[ok[-1] + 1:]     # the rest of the block feeds the interior samples
+        ok = np.flatnonzero(nv <= norm_bound)[:total - k]
+        out[:, :, k:k + len(ok)] = np.moveaxis(T[ok], 0, -1)
+        k += len(ok)
     return out
 
 

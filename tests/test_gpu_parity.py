@@ -474,6 +474,52 @@ def test_golden_column_stats(engine, golden):
         assert relerr(mean, golden[k].mean(axis=0)) < 1e-13 and relerr(std, golden[k].std(axis=0)) < 1e-9
 
 
+# --------------------------------------------------------------------------------------------- sweep driver (cfg 2)
+def test_error_horizon_sweep_vs_golden_and_oracle(engine, golden, example):
+    """Full error-level x horizon grid (lq_mpc_b200/sweep.py): column N=7 is the shipped error table, row level 4
+    (e = 5e-3 = e_nominal) over N=6..10 is the shipped horizon table; N=1 and N=50 cells vs the per-sample oracle."""
+    from lq_mpc_b200.sweep import QUANTITIES, error_horizon_sweep
+    from oracle import np_oracle as o
+    A, B, Q, R, F_u, lo, hi = (example[x] for x in ("A", "B", "Q", "R", "F_u", "lo", "hi"))
+    engine.set_problem(A, B, Q, R, Q, lo, hi, 30)
+    horizons = [1, 6, 7, 8, 9, 10, 50]
+    eA, eB = golden["error_A_f"], golden["error_B_f"]
+    r = error_horizon_sweep(engine, eA, eB, golden["error"], horizons, F_u, Q, 8, 1.5, example["p"], 30,
+                            keep_tables=True)
+    assert abs(r["V_expert"] - float(golden["V_expert"])) < TOL * r["V_expert"]
+    assert r["evals"] == 100 * 10 * 7 and r["tables"].shape == (7, len(QUANTITIES), 10, 100)
+    qi = {q: i for i, q in enumerate(QUANTITIES)}
+    for q, gk in (("true_cost", "true_cost"), ("bound", "bound_table"), ("alpha", "alpha_table"),
+                  ("beta", "beta_table"), ("xi", "xi_table")):
+        ge = golden[gk + "_error"]; gh = golden[gk + "_horizon"]
+        assert relerr(r["tables"][2, qi[q]].T, ge) < TOL, q                      # N = 7: [level][sys] -> (100, 10)
+        assert relerr(r["tables"][1:6, qi[q], 4, :].T, gh) < TOL, q              # level 4, N = 6..10 -> (100, 5)
+        for s, f in (("max", np.max), ("min", np.min), ("mean", np.mean), ("std", np.std)):
+            assert relerr(r[q + "_" + s][:, 2], f(ge, axis=0)) < 1e-9, (q, s)    # K5 == the plotters' statistics
+    assert np.allclose(r["ratio_true_max"][:, 2], golden["true_cost_error"].max(axis=0) / r["V_expert"], rtol=1e-12)
+    # cells no shipped table covers: N = 1 and N = 50, three systems, two levels, vs the per-sample oracle
+    x0_vec = o.circle_generator(8, 1.5, r["epsilon_lqr"], Q)
+    for h, N in ((0, 1), (6, 50)):
+        for i in (0, 9):
+            for j in (0, 41, 99):
+                try:
+                    ref = o.eval_one(A + eA[:, :, j, i], B + eB[:, :, j, i], A, B, Q, R, lo, hi, N, 30,
+                                     float(golden["error"][i]), x0_vec, x0_vec[:, 1], r["V_expert"], example["p"])
+                except ValueError:                      # math domain error in the reference (utils.py:506-507)
+                    assert r["n_invalid"][i, h] > 0
+                    continue
+                for q, k in (("true_cost", "J"), ("M_V", "M_V"), ("alpha", "alpha"), ("beta", "beta"), ("xi", "xi"),
+                             ("eta", "eta"), ("bound", "bound")):
+                    got = r["tables"][h, qi[q], i, j]
+                    assert abs(got - ref[k]) <= TOL * abs(ref[k]), (N, i, j, q, got, ref[k])
+    # sharded == unsharded (two shards merged by hand through the same Chan rule)
+    from lq_mpc_b200 import stats as st
+    parts = [error_horizon_sweep(engine, eA, eB, golden["error"], [7], F_u, Q, 8, 1.5, example["p"], 30,
+                                 shard=(k, 2), keep_tables=True) for k in range(2)]
+    both = np.concatenate([pp["tables"][0] for pp in parts], axis=2)
+    assert np.array_equal(both, r["tables"][2])
+
+
 def test_errors_are_loud(engine):
     from lq_mpc_b200.engine import EngineError
     from lq_mpc_b200.utils_class import LQ_MPC_Controller
