@@ -88,6 +88,20 @@ int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host, cons
                           const double* x0_host, int N_min, int N_max, int T, double* J_host, double* rho_host,
                           double* ratio_host, int32_t* flags_host, int64_t chunk);
 
+/* K4 — the same evaluation for LARGER state dimensions (compiled: n x m = 32 x 8 — BASELINE cfg 5 — and 16 x 4),
+ * unconstrained law. One CTA per sample; the sample's operands are staged into shared memory by TMA bulk copies, so
+ * this path takes ARRAY-OF-MATRICES operands (one sample contiguous, 16-byte aligned):
+ *   dA [S][n*n], dB [S][n*m], x0 [S][n]   inputs (device)
+ *   J, rho, ratio, V_N : [H][S] (any may be NULL), flags [H][S] int32 (may be NULL)
+ * lqmpc_set_problem_tiled installs (A, B, Q, R, P, N_opc) (host pointers, row-major) and prepares the expert cost
+ * matrix on the device with the evaluation kernel itself; lqmpc_get_prepared_tiled copies it back (n*n doubles).
+ * Nested horizons (N_min < N_max) need the whole batch to fit one 4 GiB closed-loop scratch chunk. */
+int lqmpc_set_problem_tiled(lqmpc_ctx* ctx, int n, int m, const double* A_true_host, const double* B_true_host,
+                            const double* Q_host, const double* R_host, const double* P_term_host, int N_opc);
+int lqmpc_get_prepared_tiled(lqmpc_ctx* ctx, double* Pexp_host, int64_t capacity);
+int lqmpc_eval_batch_tiled(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, const double* x0, int N_min,
+                           int N_max, double* J, double* rho, double* ratio, double* V_N, int32_t* flags);
+
 /* K2a — batched LQ_MPC_Controller.solve (utils_class.py:48-91) with the input box of lqmpc_set_problem, zero
  * references, terminal weight P: for every sample the controller model is (A+dA_s, B+dB_s) (dA/dB NULL = the true
  * model, e.g. for V_expert, utils_class.py:786). The QP is solved EXACTLY (Riccati-structured primal active set).

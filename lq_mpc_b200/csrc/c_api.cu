@@ -113,6 +113,8 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
+  if (ctx->tiled_pb) cudaFree(ctx->tiled_pb);
+  if (ctx->tiled_zero) cudaFree(ctx->tiled_zero);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
@@ -153,6 +155,78 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   if (rc) return rc;
   ctx->has_problem = true;
   return LQMPC_OK;
+}
+
+int lqmpc_set_problem_tiled(lqmpc_ctx* ctx, int n, int m, const double* A, const double* B, const double* Q,
+                            const double* R, const double* P, int N_opc) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!A || !B || !Q || !R || !P) return lq_set_error(ctx, LQMPC_EINVAL, "null problem matrix");
+  if (!lq_tiled_supported(n, m)) return lq_set_error(ctx, LQMPC_EINVAL, "unsupported tiled (n, m): 32x8, 16x4");
+  cudaSetDevice(ctx->device);
+  ctx->has_tiled = false;
+  if (ctx->tiled_pb) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->tiled_pb); ctx->tiled_pb = nullptr; }
+  if (ctx->tiled_zero) { cudaFree(ctx->tiled_zero); ctx->tiled_zero = nullptr; }
+  const size_t nd = lq_tiled_pb_doubles(n, m);
+  const size_t nz = (size_t)(n * n + n * m + n);
+  int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->tiled_pb, nd * sizeof(double)), "cudaMalloc tiled problem");
+  if (rc) return rc;
+  rc = lq_check_cuda(ctx, cudaMalloc(&ctx->tiled_zero, nz * sizeof(double)), "cudaMalloc tiled zeros");
+  if (rc) return rc;
+  double* d = reinterpret_cast<double*>(ctx->tiled_pb);
+  cudaMemsetAsync(ctx->tiled_pb, 0, nd * sizeof(double), ctx->stream);
+  cudaMemsetAsync(ctx->tiled_zero, 0, nz * sizeof(double), ctx->stream);
+  size_t off = 0;
+  const double* src[5] = {A, B, Q, R, P};
+  const size_t len[5] = {(size_t)n * n, (size_t)n * m, (size_t)n * n, (size_t)m * m, (size_t)n * n};
+  for (int i = 0; i < 5; ++i) {
+    rc = lq_check_cuda(ctx, cudaMemcpyAsync(d + off, src[i], len[i] * sizeof(double), cudaMemcpyHostToDevice,
+                                            ctx->stream), "H2D tiled problem");
+    if (rc) return rc;
+    off += len[i];
+  }
+  ctx->tn = n; ctx->tm = m;
+  // expert cost matrix Pexp = N_opc-step Riccati cost-to-go of the TRUE model: the evaluation kernel itself on dA = dB = 0
+  TiledEval t;
+  const double* z = reinterpret_cast<const double*>(ctx->tiled_zero);
+  t.S = 1; t.dA = z; t.dB = z + n * n; t.x0 = z + n * n + n * m;
+  t.N_min = t.N_max = (N_opc > 0) ? N_opc : 1000;
+  t.J = t.rho = t.ratio = t.Vn = nullptr; t.flags = nullptr;
+  t.Pout = d + off;                                  // off == offset of Pexp
+  rc = lq_launch_tiled(ctx, t);
+  if (rc) return rc;
+  rc = lq_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "tiled prepare sync");
+  if (rc) return rc;
+  ctx->N_opc = N_opc;
+  ctx->has_tiled = true;
+  return LQMPC_OK;
+}
+
+int lqmpc_get_prepared_tiled(lqmpc_ctx* ctx, double* Pexp_host, int64_t capacity) {
+  if (!ctx || !Pexp_host) return LQMPC_EINVAL;
+  if (!ctx->has_tiled) return lq_set_error(ctx, LQMPC_ESTATE, "tiled problem not set");
+  const int n = ctx->tn, m = ctx->tm;
+  if (capacity < (int64_t)n * n) return lq_set_error(ctx, LQMPC_EINVAL, "capacity too small");
+  const double* d = reinterpret_cast<const double*>(ctx->tiled_pb) + (3 * n * n + n * m + m * m);
+  int rc = lq_check_cuda(ctx, cudaMemcpyAsync(Pexp_host, d, (size_t)n * n * sizeof(double), cudaMemcpyDeviceToHost,
+                                              ctx->stream), "D2H Pexp");
+  if (rc) return rc;
+  return lq_check_cuda(ctx, cudaStreamSynchronize(ctx->stream), "sync");
+}
+
+int lqmpc_eval_batch_tiled(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, const double* x0, int N_min,
+                           int N_max, double* J, double* rho, double* ratio, double* V_N, int32_t* flags) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_tiled) return lq_set_error(ctx, LQMPC_ESTATE, "tiled problem not set");
+  if (S < 0 || N_min < 1 || N_max < N_min) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N_min/N_max");
+  if (S == 0) return LQMPC_OK;
+  if (!dA || !dB || !x0) return lq_set_error(ctx, LQMPC_EINVAL, "null input");
+  if (((uintptr_t)dA | (uintptr_t)dB | (uintptr_t)x0) & 15)
+    return lq_set_error(ctx, LQMPC_EINVAL, "tiled inputs must be 16-byte aligned (TMA bulk copies)");
+  cudaSetDevice(ctx->device);
+  TiledEval t;
+  t.S = S; t.dA = dA; t.dB = dB; t.x0 = x0; t.N_min = N_min; t.N_max = N_max;
+  t.J = J; t.rho = rho; t.ratio = ratio; t.Vn = V_N; t.flags = flags; t.Pout = nullptr;
+  return lq_launch_tiled(ctx, t);
 }
 
 int lqmpc_get_prepared(lqmpc_ctx* ctx, double* out, int64_t capacity) {

@@ -26,6 +26,11 @@ struct lqmpc_ctx {
   void* pb_dev = nullptr;
   std::string err;
   int64_t launches = 0;
+  // tiled (large-n) problem: device doubles A | B | Q | R | Pt | Pexp, see k_tiled.cu
+  int tn = 0, tm = 0;
+  bool has_tiled = false;
+  void* tiled_pb = nullptr;
+  void* tiled_zero = nullptr;   // n*n + n*m + n zero doubles (problem preparation runs the kernel on dA = dB = 0)
   // scratch (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -97,6 +102,20 @@ struct BoundsArgs {
   double* ws;
 };
 
+struct TiledEval {
+  int64_t S;
+  const double* dA;   // [S][n*n] array of matrices
+  const double* dB;   // [S][n*m]
+  const double* x0;   // [S][n]
+  int N_min, N_max;
+  double* J;          // [H][S]  (any output may be NULL)
+  double* rho;
+  double* ratio;
+  double* Vn;
+  int32_t* flags;
+  double* Pout;       // [n*n]: final cost-to-go of sample 0 (problem preparation only)
+};
+
 int lq_set_error(lqmpc_ctx* ctx, int code, const char* what);
 int lq_check_cuda(lqmpc_ctx* ctx, cudaError_t e, const char* what);
 int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes);
@@ -111,5 +130,8 @@ int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, in
 int lq_launch_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* out);
 int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
                     double* out);
+bool lq_tiled_supported(int n, int m);
+size_t lq_tiled_pb_doubles(int n, int m);
+int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
                    int32_t* flags);

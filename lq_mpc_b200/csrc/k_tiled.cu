@@ -1,0 +1,742 @@
+// k_tiled.cu — K4: certainty-equivalent MPC evaluation for LARGER state dimensions (n = 16, 32; BASELINE cfg 5:
+// n = 32, m = 8, N = 30), where one system no longer fits one thread's registers.
+//
+// Same math as K1 (riccati.cuh; reference semantics utils_class.py:48-91, 245-285, stability check utils.py:358),
+// different mapping:
+//   * k4a `tiled_eval_kernel<n,m>`: ONE CTA (128 threads) PER SAMPLE, persistent over the batch. The sample's
+//     (dA, dB, x0) — contiguous in the array-of-matrices layout this path uses — are staged into shared memory by the
+//     TMA engine (cp.async.bulk + mbarrier complete_tx); A^, P and the n x n temporaries live in shared memory
+//     (leading dimension n+4: the MMA fragment footprints hit the 32 banks with the minimum 2 wavefronts); every
+//     matrix product — n x n x n and the skinny n x 8 ones alike — is a set of warp-level FP64 tensor-core MMAs
+//     (mma.sync m8n8k4.f64 -> DMMA; a DFMA evaluation of the same fragments is kept for A/B timing); the 8 x 8
+//     Cholesky runs on one warp, the triangular solves one row/column per thread. Lyapunov doubling accumulates M'(S M) straight into S from the
+//     GEMM epilogue. Writes J_raw = x0' S x0, V_expert(x0), optional V_N, flags and the closed-loop matrix A_cl.
+//   * k4b `tiled_rho_kernel<n>`: ONE WARP PER SAMPLE: Householder -> Hessenberg and the Francis double-shift QR
+//     iteration run warp-synchronously on a shared-memory copy of A_cl (lane = row or column of the 3-row/3-column
+//     reflector updates), scalars replicated across lanes. Finishes J = +inf / UNSTABLE when rho >= 1 and the ratio.
+// Two kernels because the QR iteration is latency-bound and sequential: as many independent warps per SM as fit
+// hide it, whereas inside k4a it would idle three quarters of every CTA.
+#include <stdlib.h>
+
+#include "engine.h"
+
+namespace {
+
+constexpr int kT = 128;
+#ifndef LQ_K4_DMMA_DEFAULT
+#define LQ_K4_DMMA_DEFAULT true   // measured: tensor-core MMAs beat the DFMA evaluation of the same tiles
+#endif
+
+// ------------------------------------------------------------------------------------------------ TMA / mbarrier
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_%=:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra DONE_%=;\n"
+      "bra WAIT_%=;\n"
+      "DONE_%=:\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+// ------------------------------------------------------------------------------------------------ block helpers
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// all threads get the result; `red` holds >= 2*kT/32 doubles; contains the barriers that order its reuse
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  v = warp_sum(v);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+  __syncthreads();
+  double t = red[0];
+#pragma unroll
+  for (int w = 1; w < kT / 32; ++w) t += red[w];
+  return t;
+}
+__device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
+  a = warp_max(a);
+  b = warp_max(b);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5] = a; red[kT / 32 + (threadIdx.x >> 5)] = b; }
+  __syncthreads();
+  double ta = red[0], tb = red[kT / 32];
+#pragma unroll
+  for (int w = 1; w < kT / 32; ++w) { ta = fmax(ta, red[w]); tb = fmax(tb, red[kT / 32 + w]); }
+  a = ta; b = tb;
+}
+
+// ------------------------------------------------------------------------------------------------ warp-level MMA
+// Every matrix product of the Riccati step and of the Lyapunov doubling goes through ONE routine: a warp accumulates an
+// (8 MT) x (8 NT) block of C = A B as m8n8k4 FP64 tensor-core MMAs (DM = true: mma.sync -> DMMA), operands read
+// straight from shared memory in fragment order:
+//     A fragment: lane (g = lane/4, tg = lane%4) holds A(row g, col tg)     B fragment: B(row tg, col g)
+//     C fragment: C(row g, cols 2 tg, 2 tg + 1)
+// Leading dimensions are chosen == 4 (mod 16) doubles (n + 4 for the n x n buffers, 12 for the n x 8 ones): the 8 x 4
+// and 4 x 8 fragment footprints then map onto the 32 banks with exactly 2 wavefronts per 256-byte fragment, the
+// minimum. (Round-1 profile of the first version — 2 x 4 DFMA register tiles, leading dimension n + 2 — showed the
+// kernel bound by shared-memory wavefronts: 84 % of the LSU peak, 55 % of them bank conflicts.)
+// DM = false keeps a DFMA evaluation of the same fragments (each lane accumulates its two C entries) for A/B timing.
+__device__ __forceinline__ void dmma_m8n8k4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+template <int MT, int NT, bool DM, class FA, class FB>
+__device__ __forceinline__ void warp_mma(int K, int r0, int c0, FA fa, FB fb, double (&c)[MT][NT][2]) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) c[i][j][0] = c[i][j][1] = 0.0;
+  if (DM) {
+#pragma unroll 2
+    for (int k0 = 0; k0 < K; k0 += 4) {
+      double av[MT], bv[NT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) av[i] = fa(r0 + 8 * i + g, k0 + tg);
+#pragma unroll
+      for (int j = 0; j < NT; ++j) bv[j] = fb(k0 + tg, c0 + 8 * j + g);
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) dmma_m8n8k4(c[i][j][0], c[i][j][1], av[i], bv[j]);
+    }
+  } else {
+    for (int k = 0; k < K; ++k) {
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const double av = fa(r0 + 8 * i + g, k);
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+          c[i][j][0] = fma(av, fb(k, c0 + 8 * j + 2 * tg), c[i][j][0]);
+          c[i][j][1] = fma(av, fb(k, c0 + 8 * j + 2 * tg + 1), c[i][j][1]);
+        }
+      }
+    }
+  }
+}
+
+// visit the C fragment: epi(row, col, value)
+template <int MT, int NT, class Epi>
+__device__ __forceinline__ void warp_mma_store(int r0, int c0, const double (&c)[MT][NT][2], Epi epi) {
+  const int lane = threadIdx.x & 31, g = lane >> 2, tg = lane & 3;
+#pragma unroll
+  for (int i = 0; i < MT; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j) {
+      epi(r0 + 8 * i + g, c0 + 8 * j + 2 * tg, c[i][j][0]);
+      epi(r0 + 8 * i + g, c0 + 8 * j + 2 * tg + 1, c[i][j][1]);
+    }
+}
+
+// C = opA * B for n x n shared-memory operands (leading dimension LD), 4 warps, warp tile (n/2) x (n/2)
+template <int n, bool TA, bool DM, class Epi>
+__device__ __forceinline__ void gemm_nn(const double* __restrict__ A, const double* __restrict__ B, Epi epi) {
+  constexpr int LD = n + 4, T = n / 16;
+  const int w = threadIdx.x >> 5;
+  const int r0 = (w >> 1) * (n / 2), c0 = (w & 1) * (n / 2);
+  double c[T][T][2];
+  warp_mma<T, T, DM>(n, r0, c0,
+                     [&](int i, int k) { return TA ? A[k * LD + i] : A[i * LD + k]; },
+                     [&](int k, int j) { return B[k * LD + j]; }, c);
+  warp_mma_store<T, T>(r0, c0, c, epi);
+}
+
+// ------------------------------------------------------------------------------------------------ k4a
+struct TiledArgs {
+  int64_t S;
+  const double* dA;      // [S][n*n]  (array of matrices: one sample contiguous)
+  const double* dB;      // [S][n*m]
+  const double* x0;      // [S][n]
+  const double* pb;      // device: A | B | Q | R | Pt | Pexp
+  int N_min, N_max;
+  double* Jraw;          // [H][S]
+  double* vexp;          // [S]
+  double* Vn;            // [H][S] or NULL
+  int32_t* flags;        // [H][S]
+  double* Acl;           // [H][S][n*n]
+  double* Pout;          // [n*n] or NULL: final cost-to-go of sample 0 (problem preparation: the expert matrix)
+};
+
+template <int n, int m>
+struct PbOff {
+  static constexpr int A = 0, B = n * n, Q = B + n * m, R = Q + n * n, Pt = R + m * m, Pexp = Pt + n * n;
+};
+
+// shared-memory plan (doubles). M8 = 8: the input dimension is padded to one MMA tile (m = 4 -> zero columns).
+template <int n, int m>
+struct K4Smem {
+  static constexpr int LD = n + 4, NN = n * LD, LS = 12, M8 = 8;
+  static constexpr int oBh = 0, oPB = oBh + n * LS, oY = oPB + n * LS, oKg = oY + n * LS, oRK = oKg + M8 * LD,
+                       oG = oRK + M8 * LD, oRs = oG + M8 * LS, oLi = oRs + M8 * LS, oxs = oLi + M8, ored = oxs + n,
+                       obar = ored + 2 * (kT / 32), total = obar + 2;
+  static_assert(M8 * LD >= n * m, "dB lands dense in the RK area");
+  static_assert((oxs % 2) == 0 && (oRK % 2) == 0, "TMA destinations must be 16-byte aligned");
+};
+
+template <int n, int m, bool DM>
+__global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const int nbig) {
+  using L = K4Smem<n, m>;
+  using O = PbOff<n, m>;
+  constexpr int LD = L::LD, NN = L::NN, LS = L::LS, M8 = L::M8, NW = n / 8;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  double* big[5];
+  for (int i = 0; i < 5; ++i) big[i] = sm + (i < nbig ? i : nbig - 1) * NN;
+  double* sk = sm + nbig * NN;
+  double* Bh = sk + L::oBh;             // n x 8 (ld 12), columns >= m are zero
+  double* PB = sk + L::oPB;             // n x 8
+  double* Y = sk + L::oY;               // n x 8
+  double* Kg = sk + L::oKg;             // 8 x n (ld LD), rows >= m are zero
+  double* RK = sk + L::oRK;             // 8 x n; also the TMA landing zone of dB and the Y'A^ temporary
+  double* G = sk + L::oG;               // 8 x 8 (ld 12): Cholesky factor in the lower triangle
+  double* Rs = sk + L::oRs;             // 8 x 8 (ld 12): R padded with the identity
+  double* Li = sk + L::oLi;             // reciprocals of diag(L)
+  double* xs = sk + L::oxs;             // n
+  double* red = sk + L::ored;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(sk + L::obar);
+  int* cflag = reinterpret_cast<int*>(bar + 1);
+
+  const int tid = threadIdx.x, w = tid >> 5;
+  const bool nested = (a.N_min != a.N_max);
+  double* Ah = big[0];
+  double* P = big[1];
+  double* X = big[2];
+  double* Mb = nested ? big[3] : big[0];     // single emit (last step): A^ and P are dead, reuse their storage
+  double* Sb = nested ? big[4] : big[1];
+  const double* gA = a.pb + O::A;
+  const double* gB = a.pb + O::B;
+  const double* gQ = a.pb + O::Q;
+  const double* gR = a.pb + O::R;
+  const double* gPt = a.pb + O::Pt;
+  const double* gPexp = a.pb + O::Pexp;
+
+  if (tid == 0) {
+    mbar_init(bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  for (int e = tid; e < M8 * LS; e += kT) {
+    const int i = e / LS, j = e % LS;
+    Rs[e] = (i < m && j < m) ? __ldg(gR + i * m + j) : ((i == j && j < M8) ? 1.0 : 0.0);
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  for (int64_t s = blockIdx.x; s < a.S; s += gridDim.x) {
+    // ---- stage this sample's perturbations through the TMA engine (dense), then build A^ = A + dA, B^ = B + dB
+    if (tid == 0) {
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // prior generic-proxy smem writes vs async proxy
+      mbar_expect_tx(bar, (uint32_t)((n * n + n * m + n) * sizeof(double)));
+      tma_bulk_g2s(X, a.dA + s * (int64_t)(n * n), n * n * sizeof(double), bar);
+      tma_bulk_g2s(RK, a.dB + s * (int64_t)(n * m), n * m * sizeof(double), bar);
+      tma_bulk_g2s(xs, a.x0 + s * (int64_t)n, n * sizeof(double), bar);
+    }
+    mbar_wait(bar, parity);
+    parity ^= 1;
+    for (int e = tid; e < n * n; e += kT) {
+      const int i = e / n, j = e % n;
+      Ah[i * LD + j] = __ldg(gA + e) + X[e];
+      P[i * LD + j] = __ldg(gPt + e);
+    }
+    for (int e = tid; e < n * M8; e += kT) {
+      const int i = e / M8, j = e % M8;
+      Bh[i * LS + j] = (j < m) ? __ldg(gB + i * m + j) + RK[i * m + j] : 0.0;
+    }
+    if (tid == 0) *cflag = 0;
+    __syncthreads();
+    for (int e = tid; e < M8 * LD; e += kT) { Kg[e] = 0.0; RK[e] = 0.0; }
+    // V_expert(x0) = x0' Pexp x0
+    double ve = 0.0;
+    for (int e = tid; e < n * n; e += kT) ve = fma(xs[e / n] * __ldg(gPexp + e), xs[e % n], ve);
+    ve = block_sum(ve, red);
+    if (tid == 0 && a.vexp) a.vexp[s] = ve;
+
+    for (int k = 1; k <= a.N_max; ++k) {
+      // ---- P B^  (n x 8): warp w < n/8 owns row tile w
+      if (w < NW) {
+        double c[1][1][2];
+        warp_mma<1, 1, DM>(n, 8 * w, 0, [&](int i, int q) { return P[i * LD + q]; },
+                           [&](int q, int j) { return Bh[q * LS + j]; }, c);
+        warp_mma_store<1, 1>(8 * w, 0, c, [&](int i, int j, double v) { PB[i * LS + j] = v; });
+      }
+      __syncthreads();
+      // ---- warp 0: G = R + B^' (P B^) (8 x 8), then its Cholesky G = L L' (lane i owns row i of the trailing update)
+      if (w == 0) {
+        double c[1][1][2];
+        warp_mma<1, 1, DM>(n, 0, 0, [&](int i, int q) { return Bh[q * LS + i]; },
+                           [&](int q, int j) { return PB[q * LS + j]; }, c);
+        warp_mma_store<1, 1>(0, 0, c, [&](int i, int j, double v) { G[i * LS + j] = Rs[i * LS + j] + v; });
+        __syncwarp();
+        const int i = tid;
+        for (int j = 0; j < M8; ++j) {
+          const double d = G[j * LS + j];
+          if (i == 0 && !(d > 0.0)) atomicOr(cflag, (int)lq::FLAG_CHOL_FAIL);
+          const double inv = rsqrt(d);
+          __syncwarp();
+          if (i == j) { G[j * LS + j] = d * inv; Li[j] = inv; }
+          if (i > j && i < M8) G[i * LS + j] *= inv;
+          __syncwarp();
+          if (i > j && i < M8)
+            for (int cc = j + 1; cc <= i; ++cc) G[i * LS + cc] = fma(-G[i * LS + j], G[cc * LS + j], G[i * LS + cc]);
+          __syncwarp();
+        }
+      }
+      __syncthreads();
+      // ---- Y = (P B^) L^-T : one thread per row
+      if (tid < n) {
+        double y[M8];
+#pragma unroll
+        for (int j = 0; j < M8; ++j) {
+          double sacc = PB[tid * LS + j];
+#pragma unroll
+          for (int cc = 0; cc < j; ++cc) sacc = fma(-y[cc], G[j * LS + cc], sacc);
+          y[j] = sacc * Li[j];
+        }
+#pragma unroll
+        for (int j = 0; j < M8; ++j) Y[tid * LS + j] = y[j];
+      }
+      __syncthreads();
+      const bool emit = (k >= a.N_min);
+      // ---- gain of horizon k: K = -L^-T (Y' A^)   (8 x n): warp w < n/8 owns column tile w, then a column per thread
+      if (emit) {
+        if (w < NW) {
+          double c[1][1][2];
+          warp_mma<1, 1, DM>(n, 0, 8 * w, [&](int i, int q) { return Y[q * LS + i]; },
+                             [&](int q, int j) { return Ah[q * LD + j]; }, c);
+          warp_mma_store<1, 1>(0, 8 * w, c, [&](int i, int j, double v) { RK[i * LD + j] = v; });
+        }
+        __syncthreads();
+        if (tid < n) {
+          double z[M8];
+#pragma unroll
+          for (int i = M8 - 1; i >= 0; --i) {
+            double sacc = RK[i * LD + tid];
+#pragma unroll
+            for (int cc = i + 1; cc < M8; ++cc) sacc = fma(-G[cc * LS + i], z[cc], sacc);
+            z[i] = sacc * Li[i];
+          }
+#pragma unroll
+          for (int i = 0; i < M8; ++i) Kg[i * LD + tid] = -z[i];
+        }
+      }
+      // ---- P <- P - Y Y'
+      {
+        constexpr int T = n / 16;
+        const int r0 = (w >> 1) * (n / 2), c0 = (w & 1) * (n / 2);
+        double c[T][T][2];
+        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return Y[i * LS + q]; },
+                           [&](int q, int j) { return Y[j * LS + q]; }, c);
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { P[i * LD + j] -= v; });
+      }
+      __syncthreads();
+      if (k < a.N_max || a.Vn || a.Pout) {
+        // ---- X = M A^ ; P+ = Q + A^' X
+        gemm_nn<n, false, DM>(P, Ah, [&](int i, int j, double v) { X[i * LD + j] = v; });
+        __syncthreads();
+        gemm_nn<n, true, DM>(Ah, X, [&](int i, int j, double v) { P[i * LD + j] = __ldg(gQ + i * n + j) + v; });
+        __syncthreads();
+        if (a.Pout && s == 0 && k == a.N_max) {            // problem preparation: the horizon-N cost-to-go itself
+          for (int e = tid; e < n * n; e += kT) a.Pout[e] = P[(e / n) * LD + e % n];
+        }
+      }
+      if (!emit) continue;
+      const int h = k - a.N_min;
+      const int64_t o = (int64_t)h * a.S + s;
+      if (a.Vn) {
+        double vn = 0.0;
+        for (int e = tid; e < n * n; e += kT) vn = fma(xs[e / n] * P[(e / n) * LD + e % n], xs[e % n], vn);
+        vn = block_sum(vn, red);
+        if (tid == 0) a.Vn[o] = vn;
+      }
+      // ---- closed loop on the TRUE plant: R K (8 x n), then A_cl = A + B K -> Mb (and global), W = Q + K' R K -> Sb
+      if (w < NW) {
+        double c[1][1][2];
+        warp_mma<1, 1, DM>(M8, 0, 8 * w, [&](int i, int q) { return Rs[i * LS + q]; },
+                           [&](int q, int j) { return Kg[q * LD + j]; }, c);
+        warp_mma_store<1, 1>(0, 8 * w, c, [&](int i, int j, double v) { RK[i * LD + j] = v; });
+      }
+      __syncthreads();
+      {
+        constexpr int T = n / 16;
+        const int r0 = (w >> 1) * (n / 2), c0 = (w & 1) * (n / 2);
+        double c[T][T][2];
+        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return (q < m) ? __ldg(gB + i * m + q) : 0.0; },
+                           [&](int q, int j) { return Kg[q * LD + j]; }, c);
+        double* gout = a.Acl + o * (int64_t)(n * n);
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) {
+          const double acl = __ldg(gA + i * n + j) + v;
+          Mb[i * LD + j] = acl;
+          gout[i * n + j] = acl;
+        });
+        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return Kg[q * LD + i]; },
+                           [&](int q, int j) { return RK[q * LD + j]; }, c);
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { Sb[i * LD + j] = __ldg(gQ + i * n + j) + v; });
+      }
+      __syncthreads();
+      // ---- Lyapunov squared doubling: S += M' (S M), M <- M^2
+      int lflag = lq::FLAG_LYAP_NOCONV;
+      double* Mc = Mb;
+      double* Xc = X;
+      for (int it = 0; it < 64; ++it) {
+        gemm_nn<n, false, DM>(Sb, Mc, [&](int i, int j, double v) { Xc[i * LD + j] = v; });
+        __syncthreads();
+        double tmax = 0.0, smax = 0.0;
+        gemm_nn<n, true, DM>(Mc, Xc, [&](int i, int j, double v) {
+          const double nv = Sb[i * LD + j] + v;
+          Sb[i * LD + j] = nv;
+          tmax = fmax(tmax, fabs(v));
+          smax = fmax(smax, fabs(nv));
+        });
+        block_max2(tmax, smax, red);                       // (contains the barriers ordering Sb / Xc reuse)
+        if (!(tmax > 1e-18 * smax)) {
+          lflag = (tmax == tmax && smax == smax) ? 0 : (int)lq::FLAG_NONFINITE;
+          break;
+        }
+        if (!(smax < 1e300)) { lflag = lq::FLAG_NONFINITE; break; }   // diverging (unstable loop): k4b decides
+        gemm_nn<n, false, DM>(Mc, Mc, [&](int i, int j, double v) { Xc[i * LD + j] = v; });
+        __syncthreads();
+        double* t = Mc; Mc = Xc; Xc = t;
+      }
+      double J = 0.0;
+      for (int e = tid; e < n * n; e += kT) J = fma(xs[e / n] * Sb[(e / n) * LD + e % n], xs[e % n], J);
+      J = block_sum(J, red);
+      if (tid == 0) {
+        a.Jraw[o] = J;
+        a.flags[o] = lflag | *cflag;
+      }
+      __syncthreads();
+    }
+    __syncthreads();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ k4b
+struct RhoArgs {
+  int64_t total;          // H * S matrices
+  const double* Acl;      // [total][n*n]
+  const double* Jraw;     // [total]
+  const double* vexp;     // [S]
+  int64_t S;
+  double* J;              // [total] or NULL
+  double* rho;            // [total] or NULL
+  double* ratio;          // [total] or NULL
+  int32_t* flags;         // [total] in/out
+};
+
+__device__ __forceinline__ double block2_rho_d(double y, double x, double w) {
+  const double p = 0.5 * (y - x);
+  const double q = fma(p, p, w);
+  const double z = sqrt(fabs(q));
+  if (q >= 0.0) {
+    const double zz = p + (p >= 0.0 ? z : -z);
+    const double r1 = x + zz;
+    const double r2 = (zz != 0.0) ? x - w / zz : r1;
+    return fmax(fabs(r1), fabs(r2));
+  }
+  const double re = x + p;
+  return sqrt(fma(re, re, z * z));
+}
+
+// Warp-synchronous spectral radius of the n x n matrix `a` (shared memory, leading dimension n+1, destroyed).
+template <int n>
+__device__ double warp_spectral_radius(double* a, double* v, bool* ok) {
+  constexpr int LDA = n + 1;
+  const int lane = threadIdx.x & 31;
+#define A_(i, j) a[(i) * LDA + (j)]
+  // ---- Householder reduction to upper Hessenberg form
+  for (int k = 0; k < n - 2; ++k) {
+    const double xi = (lane > k && lane < n) ? A_(lane, k) : 0.0;
+    const double alpha = warp_sum(xi * xi);
+    const double x0 = __shfl_sync(0xffffffffu, xi, k + 1);
+    if (alpha - x0 * x0 > 0.0) {
+      const double nrm = sqrt(alpha);
+      const double beta = (x0 >= 0.0) ? -nrm : nrm;
+      const double vi = (lane == k + 1) ? x0 - beta : xi;
+      const double tau = 2.0 / warp_sum(vi * vi);
+      v[lane] = vi;
+      __syncwarp();
+      if (lane < n) {                                   // A <- (I - tau v v') A : lane = column
+        double sacc = 0.0;
+        for (int i = k + 1; i < n; ++i) sacc = fma(v[i], A_(i, lane), sacc);
+        sacc *= tau;
+        for (int i = k + 1; i < n; ++i) A_(i, lane) = fma(-sacc, v[i], A_(i, lane));
+      }
+      __syncwarp();
+      if (lane < n) {                                   // A <- A (I - tau v v') : lane = row
+        double sacc = 0.0;
+        for (int j = k + 1; j < n; ++j) sacc = fma(A_(lane, j), v[j], sacc);
+        sacc *= tau;
+        for (int j = k + 1; j < n; ++j) A_(lane, j) = fma(-sacc, v[j], A_(lane, j));
+      }
+      __syncwarp();
+      if (lane > k + 1 && lane < n) A_(lane, k) = 0.0;
+      __syncwarp();
+    }
+  }
+  double an = 0.0;
+  if (lane < n)
+    for (int j = (lane > 0 ? lane - 1 : 0); j < n; ++j) an += fabs(A_(lane, j));
+  const double anorm = warp_sum(an);
+  // ---- Francis double-shift QR with deflation (EISPACK hqr, eigenvalues only); scalars replicated across lanes
+  double rho = 0.0, t = 0.0;
+  int nn = n - 1, its = 0, guard = 0;
+  *ok = true;
+  while (nn >= 0 && guard < 150 * n) {
+    ++guard;
+    // ---- deflation search, one sub-diagonal per lane: l = highest i <= nn with a negligible a(i, i-1)
+    int l = 0;
+    {
+      bool small = false;
+      if (lane >= 1 && lane <= nn) {
+        double sd = fabs(A_(lane - 1, lane - 1)) + fabs(A_(lane, lane));
+        if (sd == 0.0) sd = anorm;
+        small = (fabs(A_(lane, lane - 1)) + sd == sd);
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, small);
+      if (bal) l = 31 - __clz(bal);
+    }
+    if (l > 0 && lane == 0) A_(l, l - 1) = 0.0;
+    __syncwarp();
+    double x = A_(nn, nn);
+    if (l == nn) { rho = fmax(rho, fabs(x + t)); nn -= 1; its = 0; continue; }
+    double y = A_(nn - 1, nn - 1);
+    double w = A_(nn, nn - 1) * A_(nn - 1, nn);
+    if (l == nn - 1) { rho = fmax(rho, block2_rho_d(y + t, x + t, w)); nn -= 2; its = 0; continue; }
+    if (its >= 120) { *ok = false; break; }
+    if (its == 10 || its == 20) {                       // exceptional shift
+      t += x;
+      __syncwarp();
+      if (lane <= nn) A_(lane, lane) -= x;
+      __syncwarp();
+      const double sd = fabs(A_(nn, nn - 1)) + fabs(A_(nn - 1, nn - 2));
+      x = y = 0.75 * sd;
+      w = -0.4375 * sd * sd;
+    }
+    ++its;
+    // ---- start row of the bulge, one candidate row per lane: the highest mm in [l, nn-2] whose first reflector
+    //      column (p, q, r) passes EISPACK's two-small-subdiagonals test (mm = l always qualifies)
+    double p = 0.0, q = 0.0, r = 0.0;
+    int mst = l;
+    {
+      bool cand = false;
+      if (lane >= l && lane <= nn - 2) {
+        const int mm = lane;
+        const double z = A_(mm, mm);
+        const double rr = x - z, ss = y - z;
+        p = (rr * ss - w) / A_(mm + 1, mm) + A_(mm, mm + 1);
+        q = A_(mm + 1, mm + 1) - z - rr - ss;
+        r = A_(mm + 2, mm + 1);
+        const double isc = 1.0 / (fabs(p) + fabs(q) + fabs(r));
+        p *= isc; q *= isc; r *= isc;
+        cand = (mm == l);
+        if (!cand) {
+          const double u = fabs(A_(mm, mm - 1)) * (fabs(q) + fabs(r));
+          const double vv = fabs(p) * (fabs(A_(mm - 1, mm - 1)) + fabs(z) + fabs(A_(mm + 1, mm + 1)));
+          cand = (u + vv == vv);
+        }
+      }
+      const unsigned bal = __ballot_sync(0xffffffffu, cand);
+      mst = 31 - __clz(bal);                            // lane l always votes
+      p = __shfl_sync(0xffffffffu, p, mst);
+      q = __shfl_sync(0xffffffffu, q, mst);
+      r = __shfl_sync(0xffffffffu, r, mst);
+    }
+    __syncwarp();
+    if (lane >= mst + 2 && lane <= nn) {
+      A_(lane, lane - 2) = 0.0;
+      if (lane != mst + 2) A_(lane, lane - 3) = 0.0;
+    }
+    __syncwarp();
+    for (int k = mst; k <= nn - 1; ++k) {
+      const bool last = (k == nn - 1);
+      double xsc = 0.0;
+      if (k != mst) {
+        p = A_(k, k - 1);
+        q = A_(k + 1, k - 1);
+        r = last ? 0.0 : A_(k + 2, k - 1);
+        xsc = fabs(p) + fabs(q) + fabs(r);
+        if (xsc != 0.0) { const double ix = lq::rcp(xsc); p *= ix; q *= ix; r *= ix; }
+      }
+      const double s2 = fma(p, p, fma(q, q, r * r));
+      if (s2 == 0.0) continue;
+      const double isq = rsqrt(s2);                     // |s| = s2 * isq, 1/|s| = isq (p, q, r are scaled to O(1))
+      const double sg = (p >= 0.0) ? s2 * isq : -(s2 * isq);
+      const double isg = (p >= 0.0) ? isq : -isq;
+      __syncwarp();
+      if (lane == 0) {
+        if (k == mst) { if (l != mst) A_(k, k - 1) = -A_(k, k - 1); }
+        else A_(k, k - 1) = -sg * xsc;
+      }
+      p += sg;                                          // |p + sg| >= |sg| > 0: same signs
+      const double ip = lq::rcp(p);
+      const double hx = p * isg, hy = q * isg, hz = r * isg;
+      q *= ip; r *= ip;
+      if (lane >= k && lane <= nn) {                    // row modification: lane = column
+        double pp = A_(k, lane) + q * A_(k + 1, lane);
+        if (!last) { pp += r * A_(k + 2, lane); A_(k + 2, lane) -= pp * hz; }
+        A_(k + 1, lane) -= pp * hy;
+        A_(k, lane) -= pp * hx;
+      }
+      __syncwarp();
+      const int imax = (nn < k + 3) ? nn : k + 3;
+      if (lane >= l && lane <= imax) {                  // column modification: lane = row
+        double pp = hx * A_(lane, k) + hy * A_(lane, k + 1);
+        if (!last) { pp += hz * A_(lane, k + 2); A_(lane, k + 2) -= pp * r; }
+        A_(lane, k + 1) -= pp * q;
+        A_(lane, k) -= pp;
+      }
+      __syncwarp();
+    }
+  }
+  if (nn >= 0) *ok = false;
+#undef A_
+  return rho;
+}
+
+template <int n>
+__global__ void __launch_bounds__(kT) tiled_rho_kernel(const RhoArgs a) {
+  constexpr int LDA = n + 1, PER = n * LDA + 32;
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sm = reinterpret_cast<double*>(smem_raw);
+  const int wib = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double* am = sm + wib * PER;
+  double* v = am + n * LDA;
+  const int64_t wid = (int64_t)blockIdx.x * (kT / 32) + wib, nw = (int64_t)gridDim.x * (kT / 32);
+  for (int64_t e = wid; e < a.total; e += nw) {
+    const double* src = a.Acl + e * (int64_t)(n * n);
+    for (int q = lane; q < n * n; q += 32) am[(q / n) * LDA + q % n] = src[q];
+    __syncwarp();
+    bool ok;
+    const double rho = warp_spectral_radius<n>(am, v, &ok);
+    __syncwarp();
+    if (lane == 0) {
+      int fl = a.flags[e];
+      if (!ok) fl |= lq::FLAG_EIG_NOCONV;
+      double J = a.Jraw[e];
+      if (!(rho < 1.0)) {
+        fl = (fl & ~(lq::FLAG_LYAP_NOCONV | lq::FLAG_NONFINITE)) | lq::FLAG_UNSTABLE;
+        J = HUGE_VAL;
+      } else if (!(fabs(J) <= 1.79e308)) {
+        fl |= lq::FLAG_NONFINITE;
+      }
+      if (a.J) a.J[e] = J;
+      if (a.rho) a.rho[e] = rho;
+      if (a.ratio) a.ratio[e] = J / a.vexp[e % a.S];
+      a.flags[e] = fl;
+    }
+  }
+}
+
+template <int n, int m>
+size_t k4a_smem_bytes(int nbig) {
+  return (size_t)(nbig * K4Smem<n, m>::NN + K4Smem<n, m>::total) * sizeof(double) + 16;
+}
+
+template <int n, int m>
+int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int H = t.N_max - t.N_min + 1;
+  const int nbig = (H > 1) ? 5 : 3;
+  const size_t smem = k4a_smem_bytes<n, m>(nbig);
+  // FP64 tensor-core variant of the n x n x n products (n = 32): default decided by measurement;
+  // LQMPC_K4_DMMA=0/1 overrides it for A/B runs.
+  const char* dmv = getenv("LQMPC_K4_DMMA");
+  const bool use_dmma = dmv ? atoi(dmv) != 0 : LQ_K4_DMMA_DEFAULT;
+  auto kern = use_dmma ? tiled_eval_kernel<n, m, true> : tiled_eval_kernel<n, m, false>;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[H > 1]) {
+    cudaFuncSetAttribute(tiled_eval_kernel<n, m, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)k4a_smem_bytes<n, m>(5));
+    cudaFuncSetAttribute(tiled_eval_kernel<n, m, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)k4a_smem_bytes<n, m>(5));
+    cudaFuncSetAttribute(tiled_rho_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                         (int)((kT / 32) * (n * (n + 1) + 32) * sizeof(double)));
+    attr_done[H > 1] = true;
+  }
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT, smem);
+  if (per_sm < 1) per_sm = 1;
+  // A_cl scratch: [H][chunk][n*n]; chunk the batch so that the scratch stays below 4 GiB
+  int64_t chunk = t.S;
+  const int64_t max_mats = ((int64_t)4 << 30) / (int64_t)(n * n * sizeof(double));
+  if ((int64_t)H * chunk > max_mats) chunk = max_mats / H;
+  if (chunk < 1) chunk = 1;
+  const size_t acl_bytes = (size_t)H * chunk * n * n * sizeof(double);
+  const size_t need = acl_bytes + (size_t)(H + 1) * chunk * sizeof(double) + (size_t)H * chunk * sizeof(int32_t);
+  int rc = lq_reserve_ws(ctx, need);
+  if (rc) return rc;
+  double* acl = reinterpret_cast<double*>(ctx->ws);
+  double* jraw = acl + (size_t)H * chunk * n * n;
+  double* vexp = jraw + (size_t)H * chunk;
+  int32_t* fscratch = reinterpret_cast<int32_t*>(vexp + chunk);
+  if (t.S > chunk && H > 1)
+    return lq_set_error(ctx, -1, "tiled path: nested horizons need the batch to fit one chunk (reduce S or H)");
+  for (int64_t s0 = 0; s0 < t.S; s0 += chunk) {
+    const int64_t cs = (s0 + chunk <= t.S) ? chunk : t.S - s0;
+    TiledArgs a;
+    a.S = cs;
+    a.dA = t.dA + s0 * (int64_t)(n * n); a.dB = t.dB + s0 * (int64_t)(n * m); a.x0 = t.x0 + s0 * (int64_t)n;
+    a.pb = reinterpret_cast<const double*>(ctx->tiled_pb);
+    a.N_min = t.N_min; a.N_max = t.N_max;
+    a.Jraw = jraw; a.vexp = vexp; a.Vn = t.Vn ? t.Vn + s0 : nullptr; a.flags = t.flags ? t.flags + s0 : fscratch; a.Acl = acl;
+    a.Pout = t.Pout;
+    int64_t blocks = (int64_t)sms * per_sm;
+    if (blocks > cs) blocks = cs;
+    kern<<<(unsigned)blocks, kT, smem, ctx->stream>>>(a, nbig);
+    RhoArgs r;
+    r.total = (int64_t)H * cs; r.Acl = acl; r.Jraw = jraw; r.vexp = vexp; r.S = cs;
+    r.J = t.J ? t.J + s0 : nullptr; r.rho = t.rho ? t.rho + s0 : nullptr; r.ratio = t.ratio ? t.ratio + s0 : nullptr;
+    r.flags = a.flags;
+    const size_t rsmem = (size_t)(kT / 32) * (n * (n + 1) + 32) * sizeof(double);
+    int rper = 1;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&rper, tiled_rho_kernel<n>, kT, rsmem);
+    if (rper < 1) rper = 1;
+    int64_t rblocks = (int64_t)sms * rper;
+    const int64_t wantb = (r.total + kT / 32 - 1) / (kT / 32);
+    if (rblocks > wantb) rblocks = wantb;
+    tiled_rho_kernel<n><<<(unsigned)rblocks, kT, rsmem, ctx->stream>>>(r);
+    ctx->launches += 2;
+    rc = lq_check_cuda(ctx, cudaGetLastError(), "tiled kernels launch");
+    if (rc) return rc;
+  }
+  return 0;
+}
+
+}  // namespace
+
+bool lq_tiled_supported(int n, int m) { return (n == 32 && m == 8) || (n == 16 && m == 4); }
+
+size_t lq_tiled_pb_doubles(int n, int m) { return (size_t)(4 * n * n + n * m + m * m); }
+
+int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t) {
+  if (ctx->tn == 32 && ctx->tm == 8) return launch_tiled_t<32, 8>(ctx, t);
+  if (ctx->tn == 16 && ctx->tm == 4) return launch_tiled_t<16, 4>(ctx, t);
+  return lq_set_error(ctx, -1, "unsupported tiled (n, m): 32x8 and 16x4 are compiled");
+}

@@ -44,6 +44,9 @@ ABI = {
     "lqmpc_get_prepared": (_int, [_vp, _vp, _i64]),
     "lqmpc_eval_batch": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int] + [_vp] * 7),
     "lqmpc_eval_batch_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64]),
+    "lqmpc_set_problem_tiled": (_int, [_vp, _int, _int] + [_vp] * 5 + [_int]),
+    "lqmpc_get_prepared_tiled": (_int, [_vp, _vp, _i64]),
+    "lqmpc_eval_batch_tiled": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int] + [_vp] * 5),
     "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
     "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
     "lqmpc_bounds_fields": (_int, []),
@@ -182,6 +185,50 @@ class Engine:
         self.u_lo, self.u_hi = lo, hi
         self.N_opc = int(N_opc)
         return self
+
+    # ------------------------------------------------------------------------------------------------ K4
+    TILED_DIMS = ((32, 8), (16, 4))
+
+    def set_problem_tiled(self, A, B, Q, R, P=None, N_opc: int = 30):
+        """Large-n path (K4; n x m in TILED_DIMS): unconstrained law, array-of-matrices operands."""
+        A = _np_f64(A)
+        n = A.shape[0]
+        B = _np_f64(B, (n, -1))
+        m = B.shape[1]
+        Q = _np_f64(Q, (n, n))
+        R = _np_f64(R, (m, m))
+        P = Q if P is None else _np_f64(P, (n, n))
+        rc = self.lib.lqmpc_set_problem_tiled(self._h, n, m, _ptr(A), _ptr(B), _ptr(Q), _ptr(R), _ptr(P), int(N_opc))
+        self._check(rc, "lqmpc_set_problem_tiled")
+        self.tn, self.tm = n, m
+        return self
+
+    def prepared_tiled(self):
+        out = np.zeros(self.tn * self.tn)
+        self._check(self.lib.lqmpc_get_prepared_tiled(self._h, _ptr(out), out.size), "lqmpc_get_prepared_tiled")
+        return {"Pexp": out.reshape(self.tn, self.tn)}
+
+    def eval_batch_tiled(self, dA, dB, x0, N_min: int, N_max: int, want=("J", "rho", "ratio", "flags")):
+        """dA [S][n][n], dB [S][n][m], x0 [S][n] (array of matrices, device or host). Returns [H][S] device tensors
+        plus the contiguous `table` like eval_batch."""
+        torch = self.torch
+        n, m = self.tn, self.tm
+        dA, dB, x0 = self._dev(dA), self._dev(dB), self._dev(x0)
+        S = x0.shape[0]
+        if dA.numel() != n * n * S or dB.numel() != n * m * S or x0.numel() != n * S:
+            raise ValueError("operand shapes do not match (n, m, S)")
+        H = N_max - N_min + 1
+        names = [k for k in ("J", "rho", "ratio", "V_N") if k in want]
+        table = torch.empty((len(names) * H, S), dtype=torch.float64, device=self.device)
+        out = {k: table[i * H:(i + 1) * H] for i, k in enumerate(names)}
+        out["table"], out["table_rows"] = table, [(k, N_min + h) for k in names for h in range(H)]
+        if "flags" in want:
+            out["flags"] = torch.empty((H, S), dtype=torch.int32, device=self.device)
+        rc = self.lib.lqmpc_eval_batch_tiled(self._h, S, _ptr(dA), _ptr(dB), _ptr(x0), N_min, N_max,
+                                             _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
+                                             _ptr(out.get("V_N")), _ptr(out.get("flags")))
+        self._check(rc, "lqmpc_eval_batch_tiled")
+        return out
 
     def prepared(self):
         n = self.n

@@ -474,6 +474,44 @@ def test_golden_column_stats(engine, golden):
         assert relerr(mean, golden[k].mean(axis=0)) < 1e-13 and relerr(std, golden[k].std(axis=0)) < 1e-9
 
 
+# ------------------------------------------------------------------------------------------------------- K4
+@pytest.mark.parametrize("n,m,e,dmma", [(32, 8, 1e-3, "0"), (32, 8, 1e-3, "1"), (16, 4, 5e-3, "0"), (32, 8, 0.2, "1")])
+def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
+    """Large-n path (CTA per sample, TMA-staged operands, warp-synchronous QR) vs the batched oracle: nested
+    horizons, the single-horizon buffer plan, DFMA and FP64-tensor-core GEMM variants, and (e = 0.2) a batch
+    with unstable closed loops."""
+    from oracle import np_batched as nb
+    monkeypatch.setenv("LQMPC_K4_DMMA", dmma)
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    N = 30 if n == 32 else 12
+    engine.set_problem_tiled(A, B, Q, R, Q, 30)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    assert relerr(engine.prepared_tiled()["Pexp"], Pexp) < 1e-11
+    S = 301                                              # ragged vs the persistent grid
+    dA, dB, x0 = nb.synth_samples(n, m, S, seed=1, e=e)
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, N - 2, N)
+    got = engine.eval_batch_tiled(dA, dB, x0, N - 2, N, want=("J", "rho", "ratio", "flags", "V_N"))
+    g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
+    assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"])
+    if e >= 0.2:
+        assert ref["unstable"].any() and not ref["unstable"].all()
+    well = np.abs(ref["rho"] - 1.0) > 1e-6
+    # e = 0.2 drives the 30-step recursion of a 32-state, open-loop-unstable model to costs ~1e2-1e3 with a
+    # conditioning of ~1e7: two FP64 summation orders agree to ~1e-9 only; that case checks flags / stability logic.
+    tol = 1e-7 if e >= 0.2 else TOL
+    assert relerr(g["rho"], ref["rho"]) < tol
+    assert relerr(g["V_N"], ref["Vn"]) < tol
+    for k in ("J", "ratio"):
+        assert relerr(np.where(well, g[k], 0.0), np.where(well, ref[k], 0.0)) < 10 * tol, k
+    assert not np.any(g["flags"] & ~1)
+    one = engine.eval_batch_tiled(dA, dB, x0, N, N)      # 3-buffer plan (A^ and P storage reused by the doubling)
+    assert relerr(one["J"].cpu().numpy()[0], g["J"][2]) < 1e-12
+    assert relerr(one["rho"].cpu().numpy()[0], g["rho"][2]) < 1e-12
+    assert np.array_equal(one["flags"].cpu().numpy()[0], g["flags"][2])
+    empty = engine.eval_batch_tiled(np.zeros((0, n, n)), np.zeros((0, n, m)), np.zeros((0, n)), N, N)
+    assert empty["J"].shape == (1, 0)
+
+
 # --------------------------------------------------------------------------------------------- sweep driver (cfg 2)
 def test_error_horizon_sweep_vs_golden_and_oracle(engine, golden, example):
     """Full error-level x horizon grid (lq_mpc_b200/sweep.py): column N=7 is the shipped error table, row level 4
