@@ -293,18 +293,31 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
                            [&](int q, int j) { return PB[q * LS + j]; }, c);
         warp_mma_store<1, 1>(0, 0, c, [&](int i, int j, double v) { G[i * LS + j] = Rs[i * LS + j] + v; });
         __syncwarp();
-        const int i = tid;
+        // Cholesky in registers: lane i (< 8) holds row i of G; column j is broadcast with shuffles (no shared-memory
+        // round trips on this serial stretch of the step — it was 42 % of the stall samples of the first version).
+        const int i = tid & 7;                            // lanes >= 8 mirror rows 0..7 (keeps the shuffles uniform)
+        double grow[M8];
+#pragma unroll
+        for (int j = 0; j < M8; ++j) grow[j] = G[i * LS + j];
+        bool bad = false;
+#pragma unroll
         for (int j = 0; j < M8; ++j) {
-          const double d = G[j * LS + j];
-          if (i == 0 && !(d > 0.0)) atomicOr(cflag, (int)lq::FLAG_CHOL_FAIL);
+          const double d = __shfl_sync(0xffffffffu, grow[j], j);
+          bad = bad || !(d > 0.0);
           const double inv = rsqrt(d);
-          __syncwarp();
-          if (i == j) { G[j * LS + j] = d * inv; Li[j] = inv; }
-          if (i > j && i < M8) G[i * LS + j] *= inv;
-          __syncwarp();
-          if (i > j && i < M8)
-            for (int cc = j + 1; cc <= i; ++cc) G[i * LS + cc] = fma(-G[i * LS + j], G[cc * LS + j], G[i * LS + cc]);
-          __syncwarp();
+          const double lij = (i == j) ? d * inv : grow[j] * inv;    // L(i, j) for i >= j
+          grow[j] = lij;
+          if (tid == j) Li[j] = inv;
+#pragma unroll
+          for (int cc = j + 1; cc < M8; ++cc) {
+            const double lcj = __shfl_sync(0xffffffffu, lij, cc);
+            if (i >= cc) grow[cc] = fma(-lij, lcj, grow[cc]);
+          }
+        }
+        if (bad && tid == 0) atomicOr(cflag, (int)lq::FLAG_CHOL_FAIL);
+        if (tid < M8) {
+#pragma unroll
+          for (int j = 0; j < M8; ++j) G[i * LS + j] = grow[j];     // lower triangle = L (upper entries unused)
         }
       }
       __syncthreads();

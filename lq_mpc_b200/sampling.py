@@ -99,13 +99,16 @@ def synth_problem(n=4, m=2, seed=0, rho_target=1.05):
             return A, B, np.eye(n), np.eye(m)
 
 
-def synth_samples_soa(n, m, S, seed=1, first=0, e=0.01, block=1 << 16, out=None):
+def synth_samples_soa(n, m, S, seed=1, first=0, e=0.01, block=1 << 16, out=None, aos=False):
     """Seeded, shard-invariant synthetic samples in the engine's SoA layout: dA [n*n][S], dB [n*m][S] ~ U[-e, e],
     x0 [n][S] ~ N(0, I). Block b (of `block` samples) comes from Philox(key=[seed, stream], counter=[0,0,0,b]), so a
     rank asking for global samples [first, first+S) gets exactly what a single-GPU run would see there.
-    `out` = (dA, dB, x0) preallocated arrays (e.g. views of pinned tensors)."""
+    `out` = (dA, dB, x0) preallocated arrays (e.g. views of pinned tensors).
+    aos=True writes the array-of-matrices layout of the large-n path (K4) instead: dA [S][n*n], dB [S][n*m], x0 [S][n]
+    (the same stream, transposed)."""
     if out is None:
-        out = (np.empty((n * n, S)), np.empty((n * m, S)), np.empty((n, S)))
+        out = (np.empty((S, n * n)), np.empty((S, n * m)), np.empty((S, n))) if aos else \
+            (np.empty((n * n, S)), np.empty((n * m, S)), np.empty((n, S)))
     dA, dB, x0 = out
     b0, b1 = first // block, (first + S - 1) // block
     pos = 0
@@ -117,8 +120,13 @@ def synth_samples_soa(n, m, S, seed=1, first=0, e=0.01, block=1 << 16, out=None)
         lo = max(first, b * block) - b * block
         hi = min(first + S, (b + 1) * block) - b * block
         cnt = hi - lo
-        dA[:, pos:pos + cnt] = a[lo:hi].T
-        dB[:, pos:pos + cnt] = bb[lo:hi].T
-        x0[:, pos:pos + cnt] = xx[lo:hi].T
+        if aos:
+            dA[pos:pos + cnt] = a[lo:hi]
+            dB[pos:pos + cnt] = bb[lo:hi]
+            x0[pos:pos + cnt] = xx[lo:hi]
+        else:
+            dA[:, pos:pos + cnt] = a[lo:hi].T
+            dB[:, pos:pos + cnt] = bb[lo:hi].T
+            x0[:, pos:pos + cnt] = xx[lo:hi].T
         pos += cnt
     return dA, dB, x0
