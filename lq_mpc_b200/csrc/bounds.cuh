@@ -210,18 +210,19 @@ template <int n, int m>
 struct BoundsLayout {
   int N, k;
   int64_t oG, oC, od, oe, total;
-  LQ_HD explicit BoundsLayout(int N_) : N(N_), k(N_ * m) {
+  // compact: the Gram spectrum comes precomputed (warp-per-sample kernel, k_gram.cu) — only G_d is kept per thread
+  LQ_HD explicit BoundsLayout(int N_, bool compact = false) : N(N_), k(N_ * m) {
     oG = 0;
     oC = oG + (int64_t)N * n * m;
-    od = oC + (int64_t)k * k;
-    oe = od + k;
-    total = oe + k;
+    od = oC + (compact ? 0 : (int64_t)k * k);
+    oe = od + (compact ? 0 : k);
+    total = oe + (compact ? 0 : k);
   }
 };
 
 template <int n, int m>
-LQ_HD int64_t bounds_ws_doubles(int N) {
-  return BoundsLayout<n, m>(N).total;
+LQ_HD int64_t bounds_ws_doubles(int N, bool compact = false) {
+  return BoundsLayout<n, m>(N, compact).total;
 }
 
 struct BoundsScalars {
@@ -231,6 +232,8 @@ struct BoundsScalars {
   double V_expert;
   double bar_u, bar_d_u;   // < 0: derive from the input box
   int strict_reference;    // literal kron ordering of utils.py:317-318 (only matters when Q, R are not scalar)
+  int has_gram = 0;        // extreme eigenvalues of Gamma'Gamma supplied by gram_extremes_kernel (Q = qI, R = rI only)
+  double cmin = 0.0, cmax = 0.0;
 };
 
 // Gamma[(t, r), (j, s)] for t = 0..N, j = 0..N-1 from the stored G_d = A^d B.
@@ -244,7 +247,7 @@ LQ_HD double gamma_entry(const WsView& ws, const BoundsLayout<n, m>& L, int t, i
 template <int n, int m>
 LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double* Bh, const double* K,
                         const double* x, const BoundsScalars& sc, const WsView& ws, double* out) {
-  const BoundsLayout<n, m> L(sc.N);
+  const BoundsLayout<n, m> L(sc.N, sc.has_gram != 0);
   const int N = sc.N, k = L.k;
   int flags = 0;
   LQ_UNROLL for (int i = 0; i < BF_COUNT; ++i) out[i] = 0.0;
@@ -343,6 +346,8 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     out[BF_NORM_PHI] = sqrt(dmax(hi, 0.0));
   }
   // ---------------- Gamma'Gamma by the block recurrence C[j][j'] = C[j+1][j'+1] + G_{N-1-j}' G_{N-1-j'}
+  double cmin = sc.cmin, cmax = sc.cmax;
+  if (!sc.has_gram) {
   for (int j = N - 1; j >= 0; --j)
     for (int jp = j; jp >= 0; --jp) {
       double ga[n * m], gb[n * m];
@@ -358,9 +363,9 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
           if (j == jp) ws[L.oC + (int64_t)(jp * m + b) * k + (j * m + a)] = acc;
         }
     }
-  double cmin, cmax;
   ws_tridiagonalize(ws, L.oC, L.od, L.oe, k);
   ws_tridiag_extremes(ws, L.od, L.oe, k, &cmin, &cmax);
+  }
   const double nG = sqrt(dmax(cmax, 0.0));
   out[BF_NORM_GAMMA] = nG;
   double min_H;

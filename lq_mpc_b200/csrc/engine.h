@@ -100,6 +100,8 @@ struct BoundsArgs {
   double* P_out;          // [n*n][S] (DARE solution; only when the gain is computed here)
   int32_t* flags;
   double* ws;
+  const double* gmin = nullptr;   // [S] extreme eigenvalues of Gamma'Gamma from gram_extremes_kernel, or NULL
+  const double* gmax = nullptr;
 };
 
 struct TiledEval {
@@ -133,5 +135,7 @@ int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, in
 bool lq_tiled_supported(int n, int m);
 size_t lq_tiled_pb_doubles(int n, int m);
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);
+bool lq_gram_warp_eligible(int n, int m, int N);
+int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax);
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
                    int32_t* flags);

@@ -1,6 +1,8 @@
 // k_bounds.cu — K3: batched bound coefficients (alpha, beta, xi, eta, J_bound) and batched dlqr.
 // One sample per thread, grid-stride; Gram matrix / tridiagonal scratch in the [element][thread] workspace.
 #include "bounds.cuh"
+#include <stdlib.h>
+
 #include "engine.h"
 
 namespace {
@@ -52,6 +54,7 @@ __global__ void __launch_bounds__(128) bounds_kernel(const __grid_constant__ lq:
     sc.V_expert = a.V_expert;
     sc.bar_u = a.bar_u; sc.bar_d_u = a.bar_d_u;
     sc.strict_reference = a.strict;
+    if (a.gmin) { sc.has_gram = 1; sc.cmin = a.gmin[s]; sc.cmax = a.gmax[s]; }
     double out[lq::BF_COUNT];
     flags |= lq::bounds_sample<n, m>(pb, Ah, Bh, K, x, sc, ws, out);
     if (a.alpha) a.alpha[s] = out[lq::BF_ALPHA];
@@ -104,10 +107,21 @@ int launch_bounds_t(lqmpc_ctx* ctx, BoundsArgs a) {
   int64_t blocks = (a.S + threads - 1) / threads;
   const int64_t cap = (int64_t)sms * 8;
   if (blocks > cap) blocks = cap;
-  const int64_t per = lq::bounds_ws_doubles<n, m>(a.N);
-  int rc = lq_reserve_ws(ctx, (size_t)(per * blocks * threads) * sizeof(double));
+  // Large N m with scalar weights: the Gram spectrum comes from the warp-per-sample shared-memory kernel (k_gram.cu)
+  // and the per-thread workspace shrinks to G_d; otherwise everything stays in the per-thread global workspace.
+  const bool gram = pb.qr_scalar && lq_gram_warp_eligible(n, m, a.N) && getenv("LQMPC_K3_NO_GRAM_KERNEL") == nullptr;
+  const int64_t per = lq::bounds_ws_doubles<n, m>(a.N, gram);
+  const size_t ws_main = (size_t)(per * blocks * threads) * sizeof(double);
+  int rc = lq_reserve_ws(ctx, ws_main + (gram ? (size_t)2 * a.S * sizeof(double) : 0));
   if (rc) return rc;
   a.ws = reinterpret_cast<double*>(ctx->ws);
+  if (gram) {
+    double* g = a.ws + per * blocks * threads;
+    rc = lq_launch_gram(ctx, a.S, a.dA, a.dB, a.N, g, g + a.S);
+    if (rc) return rc;
+    a.gmin = g;
+    a.gmax = g + a.S;
+  }
   bounds_kernel<n, m><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "bounds_kernel launch");

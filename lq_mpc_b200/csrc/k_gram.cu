@@ -1,0 +1,257 @@
+// k_gram.cu — K3g: extreme eigenvalues of the Gram matrix Gamma'Gamma, ONE WARP PER SAMPLE, matrix in shared memory.
+//
+// energy_bound needs ||Gamma||_2 and lambda_min(H^) (reference utils.py:248-258, 316-322: np.linalg.norm(Gamma, 2)
+// and np.min(np.linalg.eigvals(hatH)) on (N m) x (N m) matrices). For Q = qI, R = rI (every shipped scenario)
+// H^ = rI + q Gamma'Gamma, so both come from the extreme eigenvalues of C = Gamma'Gamma (k = N m).
+// The thread-per-sample kernel (bounds.cuh) keeps C in a per-thread slice of a global workspace; that is fine for
+// k ~ 7 but at k = 50 (cfg-sweep, N = 50) the Householder reduction re-reads 20 kB per sample k times: ncu showed
+// 108 GB of DRAM traffic per launch of 2e5 samples (61.6 ms, fp64 pipe 4 %) against ~20 MB of algorithmic bytes.
+// Here a warp owns the sample: G_d = A^d B and C ((k+1)-strided, both triangles: conflict-free row access) live in
+// shared memory, the Householder tridiagonalisation (EISPACK tred1 arithmetic) runs lane-parallel over rows, and
+// the two extreme eigenvalues are located by 32-way Sturm multisection (each lane counts at its own shift).
+// HBM traffic drops to the operands (n^2 + n m doubles in, 2 doubles out per sample).
+#include "engine.h"
+
+namespace {
+
+constexpr int kWarps = 4;
+
+__device__ __forceinline__ double wsum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ double wmin(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double wmax(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+struct GramArgs {
+  int64_t S;
+  const double* dA;   // SoA [n*n][S] or NULL
+  const double* dB;   // SoA [n*m][S] or NULL
+  int N;
+  double* cmin;       // [S]
+  double* cmax;       // [S]
+};
+
+__device__ __forceinline__ int sturm_count_smem(const double* d, const double* e2, int k, double x, double pivmin) {
+  int cnt = 0;
+  double q = d[0] - x;
+  if (fabs(q) < pivmin) q = -pivmin;
+  cnt += (q < 0.0);
+  for (int i = 1; i < k; ++i) {
+    q = d[i] - x - e2[i] / q;
+    if (fabs(q) < pivmin) q = -pivmin;
+    cnt += (q < 0.0);
+  }
+  return cnt;
+}
+
+// smallest x in [lo, hi] (to rounding) with count(x) >= target, by 32-way multisection of the monotone predicate
+__device__ double multisect(const double* d, const double* e2, int k, double lo, double hi, int target, double pivmin) {
+  const int lane = threadIdx.x & 31;
+  for (int it = 0; it < 64; ++it) {
+    const double w = hi - lo;
+    if (!(w > 4.5e-16 * fmax(fabs(lo), fabs(hi)))) break;
+    const double x = lo + w * ((double)(lane + 1) * (1.0 / 33.0));
+    const bool ok = (x > lo) && (x < hi);
+    const bool pred = ok && (sturm_count_smem(d, e2, k, x, pivmin) >= target);
+    const unsigned bt = __ballot_sync(0xffffffffu, pred);        // predicate true  => root <= x
+    const unsigned bv = __ballot_sync(0xffffffffu, ok);
+    if (!bv) break;                                              // interval no longer representable
+    // first lane (smallest x) whose predicate holds bounds the root from above; the valid lane before it from below
+    const int first = bt ? (__ffs(bt) - 1) : 32;
+    const unsigned below = bv & ~bt & ((first >= 32) ? 0xffffffffu : ((1u << first) - 1u));
+    const int last_false = below ? (31 - __clz(below)) : -1;
+    const double nhi = (first < 32) ? __shfl_sync(0xffffffffu, x, first) : hi;
+    const double nlo = (last_false >= 0) ? __shfl_sync(0xffffffffu, x, last_false) : lo;
+    if (nhi == hi && nlo == lo) break;
+    hi = nhi; lo = nlo;
+  }
+  return 0.5 * (lo + hi);
+}
+
+template <int n, int m>
+__global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+                                                                    const GramArgs a, const int per_warp) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int N = a.N, k = N * m, LDC = k + 1;
+  double* base = reinterpret_cast<double*>(smem_raw) + (int64_t)wib * per_warp;
+  double* C = base;                    // k x LDC
+  double* G = C + k * LDC;             // N x (n*m): G_d = A^d B
+  double* v = G + N * n * m;           // k
+  double* q = v + k;                   // k
+  double* dd = q + k;                  // k  diagonal of the tridiagonal form
+  double* e2 = dd + k;                 // k  squared off-diagonal
+  const int64_t wid = (int64_t)blockIdx.x * kWarps + wib, nw = (int64_t)gridDim.x * kWarps;
+#define C_(i, j) C[(i) * LDC + (j)]
+  for (int64_t s = wid; s < a.S; s += nw) {
+    // ---- G_d = A^^d B^ (every lane runs the tiny recurrence; lane d % 32 stores G_d)
+    {
+      double Ah[n * n], Gd[n * m];
+#pragma unroll
+      for (int e = 0; e < n * n; ++e) Ah[e] = pb.A[e] + (a.dA ? a.dA[(int64_t)e * a.S + s] : 0.0);
+#pragma unroll
+      for (int e = 0; e < n * m; ++e) Gd[e] = pb.B[e] + (a.dB ? a.dB[(int64_t)e * a.S + s] : 0.0);
+      for (int d = 0; d < N; ++d) {
+        if ((d & 31) == lane) {
+#pragma unroll
+          for (int e = 0; e < n * m; ++e) G[d * (n * m) + e] = Gd[e];
+        }
+        double Gn[n * m];
+        lq::mm<n, n, m>(Ah, Gd, Gn);
+#pragma unroll
+        for (int e = 0; e < n * m; ++e) Gd[e] = Gn[e];
+      }
+    }
+    __syncwarp();
+    // ---- C = Gamma'Gamma along its block diagonals: C[j][j-dl] = C[j+1][j+1-dl] + G_{N-1-j}' G_{N-1-j+dl}
+    for (int dl = lane; dl < N; dl += 32) {
+      double acc[m * m];
+#pragma unroll
+      for (int e = 0; e < m * m; ++e) acc[e] = 0.0;
+      for (int j = N - 1; j >= dl; --j) {
+        const int jp = j - dl;
+        const double* ga = G + (N - 1 - j) * (n * m);
+        const double* gb = G + (N - 1 - jp) * (n * m);
+#pragma unroll
+        for (int aa = 0; aa < m; ++aa)
+#pragma unroll
+          for (int bb = 0; bb < m; ++bb) {
+            double t = acc[aa * m + bb];
+#pragma unroll
+            for (int r = 0; r < n; ++r) t = fma(ga[r * m + aa], gb[r * m + bb], t);
+            acc[aa * m + bb] = t;
+            C_(j * m + aa, jp * m + bb) = t;
+            C_(jp * m + bb, j * m + aa) = t;
+          }
+      }
+    }
+    __syncwarp();
+    // ---- Householder tridiagonalisation (tred1 arithmetic), rows distributed over lanes
+    for (int i = k - 1; i >= 1; --i) {
+      const int l = i - 1;
+      if (l == 0) {
+        if (lane == 0) e2[i] = C_(i, 0) * C_(i, 0);
+        continue;
+      }
+      double sc = 0.0;
+      for (int j = lane; j <= l; j += 32) sc += fabs(C_(i, j));
+      sc = wsum(sc);
+      if (sc == 0.0) {
+        if (lane == 0) e2[i] = C_(i, l) * C_(i, l);
+        continue;
+      }
+      const double isc = 1.0 / sc;
+      double h = 0.0;
+      for (int j = lane; j <= l; j += 32) {
+        const double t = C_(i, j) * isc;
+        v[j] = t;
+        h = fma(t, t, h);
+      }
+      h = wsum(h);
+      __syncwarp();
+      const double f0 = v[l];
+      const double g0 = (f0 >= 0.0) ? -sqrt(h) : sqrt(h);
+      if (lane == 0) e2[i] = (sc * g0) * (sc * g0);
+      h -= f0 * g0;
+      __syncwarp();
+      if (lane == 0) v[l] = f0 - g0;
+      __syncwarp();
+      // p = C v / h on the leading (l+1) block; f = p . v
+      const double ih = 1.0 / h;
+      double fl = 0.0;
+      for (int j = lane; j <= l; j += 32) {
+        double g = 0.0;
+        const double* row = C + j * LDC;
+        for (int kk = 0; kk <= l; ++kk) g = fma(row[kk], v[kk], g);
+        g *= ih;
+        q[j] = g;
+        fl = fma(g, v[j], fl);
+      }
+      fl = wsum(fl);
+      const double hh = fl / (h + h);
+      __syncwarp();
+      for (int j = lane; j <= l; j += 32) q[j] -= hh * v[j];
+      __syncwarp();
+      // rank-2 update of the whole leading block (both triangles are kept)
+      for (int j = lane; j <= l; j += 32) {
+        const double vj = v[j], qj = q[j];
+        double* row = C + j * LDC;
+        for (int kk = 0; kk <= l; ++kk) row[kk] -= fma(vj, q[kk], qj * v[kk]);
+      }
+      __syncwarp();
+    }
+    for (int i = lane; i < k; i += 32) dd[i] = C_(i, i);
+    if (lane == 0) e2[0] = 0.0;
+    __syncwarp();
+    // ---- Gershgorin interval, then 32-way Sturm multisection for both ends of the spectrum
+    double gl = 1e300, gu = -1e300, emax = 0.0;
+    for (int i = lane; i < k; i += 32) {
+      const double e0 = sqrt(e2[i]);
+      const double e1 = (i + 1 < k) ? sqrt(e2[i + 1]) : 0.0;
+      gl = fmin(gl, dd[i] - e0 - e1);
+      gu = fmax(gu, dd[i] + e0 + e1);
+      emax = fmax(emax, e2[i]);
+    }
+    gl = wmin(gl); gu = wmax(gu); emax = wmax(emax);
+    const double span = fmax(fabs(gl), fabs(gu));
+    gl -= 2.2e-16 * span * k + 1e-300;
+    gu += 2.2e-16 * span * k + 1e-300;
+    const double pivmin = fmax(1e-300, 2.3e-308 * fmax(1.0, emax));
+    const double lmin = multisect(dd, e2, k, gl, gu, 1, pivmin);
+    const double lmax = multisect(dd, e2, k, gl, gu, k, pivmin);
+    if (lane == 0) {
+      a.cmin[s] = lmin;
+      a.cmax[s] = lmax;
+    }
+    __syncwarp();
+  }
+#undef C_
+}
+
+template <int n, int m>
+int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax) {
+  const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
+  const int k = N * m;
+  const int per_warp = ((k * (k + 1) + N * n * m + 4 * k) + 1) & ~1;
+  const size_t smem = (size_t)kWarps * per_warp * sizeof(double);
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  cudaFuncSetAttribute(gram_extremes_kernel<n, m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int per_sm = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_extremes_kernel<n, m>, kWarps * 32, smem);
+  if (per_sm < 1) per_sm = 1;
+  int64_t blocks = (int64_t)sms * per_sm;
+  const int64_t want = (S + kWarps - 1) / kWarps;
+  if (blocks > want) blocks = want;
+  GramArgs a{S, dA, dB, N, cmin, cmax};
+  gram_extremes_kernel<n, m><<<(unsigned)blocks, kWarps * 32, smem, ctx->stream>>>(pb, a, per_warp);
+  ctx->launches++;
+  return lq_check_cuda(ctx, cudaGetLastError(), "gram_extremes_kernel launch");
+}
+
+}  // namespace
+
+// shared-memory footprint decides eligibility: 4 warps x (k (k+1) + ...) doubles must fit one CTA
+bool lq_gram_warp_eligible(int n, int m, int N) {
+  const int k = N * m;
+  const size_t per_warp = (size_t)(k * (k + 1) + N * n * m + 4 * k + 2);
+  return k >= 12 && (size_t)kWarps * per_warp * sizeof(double) <= 200 * 1024;
+}
+
+int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax) {
+#define X(N_, M_) \
+  if (ctx->n == N_ && ctx->m == M_) return launch_gram_t<N_, M_>(ctx, S, dA, dB, N, cmin, cmax);
+  LQ_FOR_EACH_DIM(X)
+#undef X
+  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+}

@@ -418,6 +418,31 @@ def test_bounds_long_horizon(engine, example):
                 assert abs(g[f][s] - bnd[f]) <= TOL * abs(bnd[f]), (N, e, f)
 
 
+def test_k3_gram_warp_kernel_matches_thread_path(engine, monkeypatch):
+    """Large N m: the extreme eigenvalues of Gamma'Gamma come from the warp-per-sample shared-memory kernel
+    (k_gram.cu); it must agree with the thread-per-sample workspace path and with numpy on Gamma itself."""
+    from oracle import np_batched as nb, np_oracle as o
+    for n, m, N in [(4, 2, 10), (4, 2, 16), (2, 1, 50), (3, 3, 11), (2, 2, 33)]:
+        A, B, Q, R = nb.synth_problem(n, m, seed=5)
+        Q, R = 1.5 * Q, 0.7 * R
+        engine.set_problem(A, B, Q, R, Q, -0.3 * np.ones(m), 0.3 * np.ones(m), 10)
+        dA, dB, x0 = nb.synth_samples(n, m, 67, seed=2, e=0.02)
+        sA, sB, sx = _soa(dA, dB, x0)
+        args = (sA, sB, N, 0.01, 0.01, 1.0, sx, (0.1, 1, 0.6), 1.0)
+        new = engine.bounds_batch(*args)
+        monkeypatch.setenv("LQMPC_K3_NO_GRAM_KERNEL", "1")
+        old = engine.bounds_batch(*args)
+        monkeypatch.delenv("LQMPC_K3_NO_GRAM_KERNEL")
+        for k in ("norm_Gamma", "min_H", "alpha", "beta", "theta_u", "E_u"):
+            assert relerr(new[k].cpu().numpy(), old[k].cpu().numpy()) < 1e-11, (n, m, N, k)
+        assert np.array_equal(new["flags"].cpu().numpy(), old["flags"].cpu().numpy())
+        for s in (0, 33, 66):
+            G = o.sl_syn_Gamma(N, A + dA[s], B + dB[s])
+            sv = np.linalg.svd(G, compute_uv=False)
+            assert abs(float(new["norm_Gamma"][s]) - sv[0]) < 1e-11 * sv[0]
+            assert abs(float(new["min_H"][s]) - (R[0, 0] + Q[0, 0] * sv[-1] ** 2)) < 1e-10 * R[0, 0]
+
+
 # ------------------------------------------------------------------------------------------------------- K5
 @pytest.mark.parametrize("which", ["one_pass", "two_pass"])
 def test_column_stats_match_numpy(engine, which):
