@@ -100,8 +100,7 @@ struct BoundsArgs {
   double* P_out;          // [n*n][S] (DARE solution; only when the gain is computed here)
   int32_t* flags;
   double* ws;
-  const double* gmin = nullptr;   // [S] extreme eigenvalues of Gamma'Gamma from gram_extremes_kernel, or NULL
-  const double* gmax = nullptr;
+  const double* gtri = nullptr;   // [2 N m][S] tridiagonal form of Gamma'Gamma from gram_extremes_kernel, or NULL
 };
 
 struct TiledEval {
@@ -136,6 +135,6 @@ bool lq_tiled_supported(int n, int m);
 size_t lq_tiled_pb_doubles(int n, int m);
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);
 bool lq_gram_warp_eligible(int n, int m, int N);
-int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax);
+int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri);
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
                    int32_t* flags);

@@ -54,7 +54,12 @@ __global__ void __launch_bounds__(128) bounds_kernel(const __grid_constant__ lq:
     sc.V_expert = a.V_expert;
     sc.bar_u = a.bar_u; sc.bar_d_u = a.bar_d_u;
     sc.strict_reference = a.strict;
-    if (a.gmin) { sc.has_gram = 1; sc.cmin = a.gmin[s]; sc.cmax = a.gmax[s]; }
+    if (a.gtri) {   // tridiagonal form of Gamma'Gamma precomputed by the warp kernel: only the Sturm bisection is left
+      const int k = a.N * m;
+      const lq::WsView tv{const_cast<double*>(a.gtri) + s, a.S};
+      sc.has_gram = 1;
+      lq::ws_tridiag_extremes(tv, 0, k, k, &sc.cmin, &sc.cmax);
+    }
     double out[lq::BF_COUNT];
     flags |= lq::bounds_sample<n, m>(pb, Ah, Bh, K, x, sc, ws, out);
     if (a.alpha) a.alpha[s] = out[lq::BF_ALPHA];
@@ -112,15 +117,14 @@ int launch_bounds_t(lqmpc_ctx* ctx, BoundsArgs a) {
   const bool gram = pb.qr_scalar && lq_gram_warp_eligible(n, m, a.N) && getenv("LQMPC_K3_NO_GRAM_KERNEL") == nullptr;
   const int64_t per = lq::bounds_ws_doubles<n, m>(a.N, gram);
   const size_t ws_main = (size_t)(per * blocks * threads) * sizeof(double);
-  int rc = lq_reserve_ws(ctx, ws_main + (gram ? (size_t)2 * a.S * sizeof(double) : 0));
+  int rc = lq_reserve_ws(ctx, ws_main + (gram ? (size_t)2 * a.N * m * a.S * sizeof(double) : 0));
   if (rc) return rc;
   a.ws = reinterpret_cast<double*>(ctx->ws);
   if (gram) {
     double* g = a.ws + per * blocks * threads;
-    rc = lq_launch_gram(ctx, a.S, a.dA, a.dB, a.N, g, g + a.S);
+    rc = lq_launch_gram(ctx, a.S, a.dA, a.dB, a.N, g);
     if (rc) return rc;
-    a.gmin = g;
-    a.gmax = g + a.S;
+    a.gtri = g;
   }
   bounds_kernel<n, m><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a);
   ctx->launches++;

@@ -8,8 +8,8 @@
 // 108 GB of DRAM traffic per launch of 2e5 samples (61.6 ms, fp64 pipe 4 %) against ~20 MB of algorithmic bytes.
 // Here a warp owns the sample: G_d = A^d B and C ((k+1)-strided, both triangles: conflict-free row access) live in
 // shared memory, the Householder tridiagonalisation (EISPACK tred1 arithmetic) runs lane-parallel over rows, and
-// the two extreme eigenvalues are located by 32-way Sturm multisection (each lane counts at its own shift).
-// HBM traffic drops to the operands (n^2 + n m doubles in, 2 doubles out per sample).
+// the tridiagonal form (2k doubles per sample, SoA) goes back to the thread-per-sample kernel for the Sturm bisection.
+// HBM traffic drops to the operands plus that tridiagonal (n^2 + n m doubles in, 2k doubles out per sample).
 #include "engine.h"
 
 namespace {
@@ -21,62 +21,14 @@ __device__ __forceinline__ double wsum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ double wmin(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-__device__ __forceinline__ double wmax(double v) {
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
 
 struct GramArgs {
   int64_t S;
   const double* dA;   // SoA [n*n][S] or NULL
   const double* dB;   // SoA [n*m][S] or NULL
   int N;
-  double* cmin;       // [S]
-  double* cmax;       // [S]
+  double* tri;        // [2k][S]: diagonal d (k rows) then off-diagonal |e| (k rows; e[0] = 0) of the tridiagonal form
 };
-
-__device__ __forceinline__ int sturm_count_smem(const double* d, const double* e2, int k, double x, double pivmin) {
-  int cnt = 0;
-  double q = d[0] - x;
-  if (fabs(q) < pivmin) q = -pivmin;
-  cnt += (q < 0.0);
-  for (int i = 1; i < k; ++i) {
-    q = d[i] - x - e2[i] / q;
-    if (fabs(q) < pivmin) q = -pivmin;
-    cnt += (q < 0.0);
-  }
-  return cnt;
-}
-
-// smallest x in [lo, hi] (to rounding) with count(x) >= target, by 32-way multisection of the monotone predicate
-__device__ double multisect(const double* d, const double* e2, int k, double lo, double hi, int target, double pivmin) {
-  const int lane = threadIdx.x & 31;
-  for (int it = 0; it < 64; ++it) {
-    const double w = hi - lo;
-    if (!(w > 4.5e-16 * fmax(fabs(lo), fabs(hi)))) break;
-    const double x = lo + w * ((double)(lane + 1) * (1.0 / 33.0));
-    const bool ok = (x > lo) && (x < hi);
-    const bool pred = ok && (sturm_count_smem(d, e2, k, x, pivmin) >= target);
-    const unsigned bt = __ballot_sync(0xffffffffu, pred);        // predicate true  => root <= x
-    const unsigned bv = __ballot_sync(0xffffffffu, ok);
-    if (!bv) break;                                              // interval no longer representable
-    // first lane (smallest x) whose predicate holds bounds the root from above; the valid lane before it from below
-    const int first = bt ? (__ffs(bt) - 1) : 32;
-    const unsigned below = bv & ~bt & ((first >= 32) ? 0xffffffffu : ((1u << first) - 1u));
-    const int last_false = below ? (31 - __clz(below)) : -1;
-    const double nhi = (first < 32) ? __shfl_sync(0xffffffffu, x, first) : hi;
-    const double nlo = (last_false >= 0) ? __shfl_sync(0xffffffffu, x, last_false) : lo;
-    if (nhi == hi && nlo == lo) break;
-    hi = nhi; lo = nlo;
-  }
-  return 0.5 * (lo + hi);
-}
 
 template <int n, int m>
 __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid_constant__ lq::Problem<n, m> pb,
@@ -193,25 +145,12 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
     for (int i = lane; i < k; i += 32) dd[i] = C_(i, i);
     if (lane == 0) e2[0] = 0.0;
     __syncwarp();
-    // ---- Gershgorin interval, then 32-way Sturm multisection for both ends of the spectrum
-    double gl = 1e300, gu = -1e300, emax = 0.0;
+    // ---- hand the tridiagonal form (d, e) to the thread-per-sample bounds kernel, SoA [2k][S]: the Sturm bisection
+    //      is a sequential recurrence per shift — one sample per LANE (k_bounds.cu) uses every lane, one sample per
+    //      warp would idle 31 (a 32-way multisection variant here spent 70 % of this kernel's instructions on it)
     for (int i = lane; i < k; i += 32) {
-      const double e0 = sqrt(e2[i]);
-      const double e1 = (i + 1 < k) ? sqrt(e2[i + 1]) : 0.0;
-      gl = fmin(gl, dd[i] - e0 - e1);
-      gu = fmax(gu, dd[i] + e0 + e1);
-      emax = fmax(emax, e2[i]);
-    }
-    gl = wmin(gl); gu = wmax(gu); emax = wmax(emax);
-    const double span = fmax(fabs(gl), fabs(gu));
-    gl -= 2.2e-16 * span * k + 1e-300;
-    gu += 2.2e-16 * span * k + 1e-300;
-    const double pivmin = fmax(1e-300, 2.3e-308 * fmax(1.0, emax));
-    const double lmin = multisect(dd, e2, k, gl, gu, 1, pivmin);
-    const double lmax = multisect(dd, e2, k, gl, gu, k, pivmin);
-    if (lane == 0) {
-      a.cmin[s] = lmin;
-      a.cmax[s] = lmax;
+      a.tri[(int64_t)i * a.S + s] = dd[i];
+      a.tri[(int64_t)(k + i) * a.S + s] = sqrt(e2[i]);
     }
     __syncwarp();
   }
@@ -219,7 +158,7 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
 }
 
 template <int n, int m>
-int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax) {
+int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri) {
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int k = N * m;
   const int per_warp = ((k * (k + 1) + N * n * m + 4 * k) + 1) & ~1;
@@ -233,7 +172,7 @@ int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB,
   int64_t blocks = (int64_t)sms * per_sm;
   const int64_t want = (S + kWarps - 1) / kWarps;
   if (blocks > want) blocks = want;
-  GramArgs a{S, dA, dB, N, cmin, cmax};
+  GramArgs a{S, dA, dB, N, tri};
   gram_extremes_kernel<n, m><<<(unsigned)blocks, kWarps * 32, smem, ctx->stream>>>(pb, a, per_warp);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "gram_extremes_kernel launch");
@@ -248,9 +187,9 @@ bool lq_gram_warp_eligible(int n, int m, int N) {
   return k >= 12 && (size_t)kWarps * per_warp * sizeof(double) <= 200 * 1024;
 }
 
-int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* cmin, double* cmax) {
+int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri) {
 #define X(N_, M_) \
-  if (ctx->n == N_ && ctx->m == M_) return launch_gram_t<N_, M_>(ctx, S, dA, dB, N, cmin, cmax);
+  if (ctx->n == N_ && ctx->m == M_) return launch_gram_t<N_, M_>(ctx, S, dA, dB, N, tri);
   LQ_FOR_EACH_DIM(X)
 #undef X
   return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
