@@ -37,6 +37,35 @@ def test_spectral_radius_vs_lapack(n):
     assert err.max() < 1e-10, (int(err.argmax()), err.max())
 
 
+@pytest.mark.parametrize("n", [3, 4])
+def test_closed_form_spectral_radius_is_trusted_only_when_accurate(n):
+    """eig.cuh fast path (characteristic polynomial -> Ferrari -> Bairstow polish -> conditioning test) alone:
+    whatever it ACCEPTS must be within 1e-10 of LAPACK (the QR iteration takes the rest); generic matrices are
+    accepted, clustered spectra are not."""
+    rng = np.random.default_rng(10 + n)
+    S = 60_000
+    fam = {"gauss": rng.normal(size=(S, n, n)),
+           "scaled": rng.normal(size=(S, n, n)) * np.exp(rng.uniform(-3, 3, size=(S, n, 1))),
+           "sym": (lambda M: M + M.transpose(0, 2, 1))(rng.normal(size=(S, n, n))),
+           "cluster": 0.9 * np.eye(n)[None] + 0.02 * rng.normal(size=(S, n, n)),
+           "tight": 0.9 * np.eye(n)[None] + 1e-3 * rng.normal(size=(S, n, n)),
+           "huge_range": rng.normal(size=(S, n, n)) * 10.0 ** rng.integers(-100, 100, size=(S, 1, 1))}
+    for name, M in fam.items():
+        rho, ok = hm.spectral_radius_poly(M)
+        ref = np.max(np.abs(np.linalg.eigvals(M)), axis=1)
+        tr = ok == 1
+        if tr.any():
+            assert np.max(np.abs(rho[tr] - ref[tr]) / ref[tr]) < 1e-10, name
+        if name in ("gauss", "sym", "huge_range"):
+            assert tr.mean() > 0.999, (name, tr.mean())
+        if name == "tight":
+            assert tr.mean() < 0.01, (name, tr.mean())
+        full, okf = hm.spectral_radius(M)                      # dispatcher = fast path or QR fallback
+        assert np.all(okf == 1) and np.max(np.abs(full - ref) / ref) < 1e-9, name
+    z, okz = hm.spectral_radius_poly(np.zeros((3, n, n)))
+    assert np.all(z == 0.0) and np.all(okz == 1)
+
+
 @pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
                                    (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02)])
 def test_k1_math_vs_batched_oracle(n, m, e):
