@@ -169,6 +169,20 @@ int lqmpc_column_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S,
  * column; std = sqrt(M2 / count) as np.std (utils.py:898). Empty column: mean = M2 = NaN, max = -inf, min = +inf. */
 int lqmpc_column_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* moments);
 
+/* K6 — model-error grids generated on the device: the seeded, counter-based restatement of `random_matrix` /
+ * `error_matrix_generator` (utils.py:779-847). For every error level i < n_err (bounds levels_host[i]) and perturbation
+ * j in [j_first, j_first + N_sys): a rows x cols matrix with entries uniform in [-e, e], accepted when its Frobenius
+ * (norm_type 0) or spectral (norm_type 1) norm is <= e; perturbations j < n_boundary are rescaled ONTO the boundary
+ * (the reference obtains those by np.isclose rejection). Philox4x32-10 keyed by `seed`, counter = (j, level, attempt):
+ * the result does not depend on sharding. `which` (0 for the A grid, 1 for the B grid, ...) separates the streams.
+ *   out  device [rows*cols][N_sys*n_err], element (a, b) of pair (j, i) at out[(a*cols + b)*N_sys*n_err + (j-j_first)*n_err + i]
+ *        — byte-identical to the reference's error_X.npy array (rows, cols, N_sys, n_err) in C order AND the engine's
+ *        SoA operand layout.
+ *   stats_host (may be NULL; synchronises): [0] rejected draws, [1] samples projected after 256 rejections. */
+int lqmpc_sample_error_grid(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int cols, int64_t N_sys,
+                            int64_t j_first, int n_err, const double* levels_host, int64_t n_boundary, int norm_type,
+                            double* out, int64_t* stats_host);
+
 /* DFMA-chain micro-benchmark: achieved FP64 FMA throughput of this device in TFLOP/s (2 flop per FMA), used as the
  * measured denominator of the FP64 roofline (MEASURED_PEAKS.json has none). Synchronises. */
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out);

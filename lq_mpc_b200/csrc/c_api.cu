@@ -447,6 +447,19 @@ int lqmpc_column_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t 
   return lq_launch_moments(ctx, table, cols, S, ld, moments);
 }
 
+int lqmpc_sample_error_grid(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int cols, int64_t N_sys,
+                            int64_t j_first, int n_err, const double* levels_host, int64_t n_boundary, int norm_type,
+                            double* out, int64_t* stats_host) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!levels_host || !out || rows < 1 || cols < 1 || N_sys < 0 || j_first < 0 || n_err < 1 || n_err > 65535 ||
+      which < 0 || which > 15 || (norm_type != 0 && norm_type != 1))
+    return lq_set_error(ctx, LQMPC_EINVAL, "bad sampler arguments");
+  if (N_sys == 0) return LQMPC_OK;
+  cudaSetDevice(ctx->device);
+  return lq_launch_sampler(ctx, seed, which, rows, cols, N_sys, j_first, n_err, levels_host, n_boundary, norm_type,
+                           out, stats_host);
+}
+
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out) {
   if (!ctx || !tflops_out) return LQMPC_EINVAL;
   cudaSetDevice(ctx->device);

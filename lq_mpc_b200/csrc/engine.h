@@ -136,5 +136,8 @@ size_t lq_tiled_pb_doubles(int n, int m);
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);
 bool lq_gram_warp_eligible(int n, int m, int N);
 int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri);
+int lq_launch_sampler(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int cols, int64_t N_sys, int64_t j_first,
+                      int n_err, const double* levels_host, int64_t n_boundary, int norm_type, double* out,
+                      int64_t* stats_host);
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
                    int32_t* flags);

@@ -57,6 +57,8 @@ ABI = {
     "lqmpc_column_stats": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
     "lqmpc_column_sqdev": (_int, [_vp, _vp, _int, _i64, _i64, _vp, _vp]),
     "lqmpc_column_moments": (_int, [_vp, _vp, _int, _i64, _i64, _vp]),
+    "lqmpc_sample_error_grid": (_int, [_vp, ctypes.c_uint64, _int, _int, _int, _i64, _i64, _int, _vp, _i64, _int, _vp,
+                                       _vp]),
     "lqmpc_fp64_peak": (_int, [_vp, _c_double_p]),
     "lqmpc_launch_count": (_i64, [_vp]),
 }
@@ -456,6 +458,22 @@ class Engine:
         self._check(self.lib.lqmpc_column_sqdev(self._h, _ptr(t), cols, S, S, _ptr(mean), _ptr(out)),
                     "lqmpc_column_sqdev")
         return out
+
+    # ------------------------------------------------------------------------------------------------ K6
+    def sample_error_grid(self, seed: int, which: int, rows: int, cols: int, N_sys: int, levels, n_boundary: int,
+                          norm_type: str = "f", j_first: int = 0, want_stats: bool = False):
+        """Device-side `random_matrix` grid (utils.py:779-847 restated, seeded): returns the SoA tensor
+        [rows*cols][N_sys*n_err] (== the reference's (rows, cols, N_sys, n_err) array in C order)."""
+        torch = self.torch
+        lev = _np_f64(levels)
+        n_err = lev.size
+        out = torch.empty((rows * cols, N_sys * n_err), dtype=torch.float64, device=self.device)
+        st = np.zeros(2, dtype=np.int64) if want_stats else None
+        rc = self.lib.lqmpc_sample_error_grid(self._h, int(seed), int(which), rows, cols, N_sys, j_first, n_err,
+                                              _ptr(lev), int(n_boundary), {"f": 0, "2": 1}[norm_type], _ptr(out),
+                                              None if st is None else st.ctypes.data)
+        self._check(rc, "lqmpc_sample_error_grid")
+        return (out, {"rejected": int(st[0]), "projected": int(st[1])}) if want_stats else out
 
     def fp64_peak(self) -> float:
         v = ctypes.c_double(0.0)

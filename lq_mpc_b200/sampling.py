@@ -73,6 +73,18 @@ def seeded_error_grids(n, m, error_vec, N_matrix, norm_type, seed=20240522):
     return eA, eB
 
 
+def device_error_grids(engine, n, m, error_vec, N_matrix, norm_type, seed=20240522, j_first=0, N_sys=None):
+    """cfg-sweep grids generated in HBM by K6 (`lqmpc_sample_error_grid`): the counter-based restatement of
+    error_matrix_generator (utils.py:826-847). Returns SoA device tensors dA [n*n][N_sys*n_err], dB [n*m][N_sys*n_err]
+    (sample s = j*n_err + i) — reshape(n, n|m, N_sys, n_err) gives the reference's file layout. `j_first`/`N_sys`
+    select a shard of the 5*N_matrix perturbations per level; the first N_matrix (global) sit on the norm boundary."""
+    total = 5 * N_matrix
+    N_sys = total - j_first if N_sys is None else N_sys
+    dA = engine.sample_error_grid(seed, 0, n, n, N_sys, error_vec, N_matrix, norm_type, j_first=j_first)
+    dB = engine.sample_error_grid(seed, 1, n, m, N_sys, error_vec, N_matrix, norm_type, j_first=j_first)
+    return dA, dB
+
+
 def grids_to_soa(error_A, error_B, level=None):
     """(n,n,N_sys,n_err), (n,m,N_sys,n_err) -> engine SoA [n*n][S], [n*m][S].
     level=None: every (system j, level i) pair, S = N_sys*n_err with s = j*n_err + i (the file's own C order);

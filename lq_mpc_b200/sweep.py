@@ -41,8 +41,9 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
                         shard: Optional[tuple] = None):
     """Full error-level x horizon sweep on an engine whose TRUE problem (A, B, Q, R, box, N_opc) is already set.
 
-    error_A (n,n,N_sys,n_err), error_B (n,m,N_sys,n_err): the reference's grid layout (numpy). `shard` = (rank, world)
-    restricts this process to its contiguous slice of the N_sys axis. Returns a dict:
+    error_A (n,n,N_sys,n_err), error_B (n,m,N_sys,n_err): the reference's grid layout (numpy) — `shard` = (rank, world)
+    then restricts this process to its contiguous slice of the N_sys axis — or the SoA device tensors of
+    `sampling.device_error_grids` (this rank's shard, generated in HBM by K6). Returns a dict:
       'error', 'horizon', 'V_expert', 'x_start', 'epsilon_lqr',
       '<q>_<stat>' for q in QUANTITIES, stat in max/min/mean/std : arrays [n_err][n_horizons],
       'ratio_true_max' / 'ratio_bound_max' (performance ratios J / V_expert, worst case per cell),
@@ -50,21 +51,29 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
       'evals', 'seconds' (device time of the sweep loop), and with keep_tables the raw [n_horizons][q][n_err][N_sys].
     """
     import torch
-    n = error_A.shape[0]
     n_err = len(error_vec)
-    N_sys_all = error_A.shape[2]
-    if shard is not None:
-        lo, hi = _stats.shard_bounds(N_sys_all, shard[0], shard[1])
-        error_A, error_B = error_A[:, :, lo:hi, :], error_B[:, :, lo:hi, :]
-    N_sys = error_A.shape[2]
+    on_device = isinstance(error_A, torch.Tensor)          # SoA [n*n][N_sys*n_err] from K6 (already this rank's shard)
+    if on_device:
+        n = engine.n
+        N_sys = error_A.shape[1] // n_err
+    else:
+        n = error_A.shape[0]
+        N_sys_all = error_A.shape[2]
+        if shard is not None:
+            lo, hi = _stats.shard_bounds(N_sys_all, shard[0], shard[1])
+            error_A, error_B = error_A[:, :, lo:hi, :], error_B[:, :, lo:hi, :]
+        N_sys = error_A.shape[2]
     # ---- nominal quantities (utils_class.py:757-764, 782-786)
     K_lqr = engine.dlqr_batch(S=1)["K"].cpu().numpy()[:, 0].reshape(-1, n)
     eps_lqr = local_radius(F_u, -K_lqr, Q)
     x0_vec = circle_generator(N_points, ext_radius_max, eps_lqr, Q)
     x_start = x0_vec[:, 1].copy()
     V_expert = float(engine.mpc_solve_batch(None, None, engine.N_opc, pts=x_start[None], S=1)["V"][0, 0])
-    dA, dB = grids_to_soa(np.ascontiguousarray(error_A), np.ascontiguousarray(error_B))
-    dA, dB = engine._dev(dA), engine._dev(dB)
+    if on_device:
+        dA, dB = error_A, error_B
+    else:
+        dA, dB = grids_to_soa(np.ascontiguousarray(error_A), np.ascontiguousarray(error_B))
+        dA, dB = engine._dev(dA), engine._dev(dB)
     e_per = engine._dev(np.tile(np.asarray(error_vec, dtype=np.float64), N_sys))
     ring = engine._dev(x0_vec.T.copy())
     res = {q + "_" + s: np.zeros((n_err, len(horizons))) for q in QUANTITIES for s in ("max", "min", "mean", "std")}
@@ -91,12 +100,11 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
             tables.append(cols.reshape(len(QUANTITIES), n_err, N_sys).cpu().numpy())
     e1.record()
     torch.cuda.synchronize(engine.device)
-    if group is not None or (shard is not None and shard[1] > 1):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized():
-            t = torch.from_numpy(n_invalid).to(engine.device)
-            dist.all_reduce(t, group=group)
-            n_invalid = t.cpu().numpy()
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        t = torch.from_numpy(n_invalid).to(engine.device)            # (column_stats merged the moments already)
+        dist.all_reduce(t, group=group)
+        n_invalid = t.cpu().numpy()
     res.update({"error": np.asarray(error_vec, dtype=np.float64), "horizon": np.asarray(horizons),
                 "V_expert": V_expert, "x_start": x_start, "epsilon_lqr": eps_lqr, "n_invalid": n_invalid,
                 "ratio_true_max": res["true_cost_max"] / V_expert, "ratio_bound_max": res["bound_max"] / V_expert,

@@ -105,3 +105,21 @@ def bounds(A, B, Q, R, lo, hi, dA_soa, dB_soa, N, eA, eB, MV, x_soa, K_in, p, V_
     out = {k: det[i] for i, k in enumerate(BOUND_FIELDS)}
     out.update({"K": Ko, "P": Po, "flags": fl})
     return out
+
+
+def philox4x32_10(ctr, key):
+    c = np.asarray(ctr, dtype=np.uint32); k = np.asarray(key, dtype=np.uint32); o = np.zeros(4, dtype=np.uint32)
+    U32 = ctypes.POINTER(ctypes.c_uint32)
+    lib().hm_philox4x32_10(c.ctypes.data_as(U32), k.ctypes.data_as(U32), o.ctypes.data_as(U32))
+    return o
+
+
+def sample_error_grid(seed, which, rows, cols, N_sys, levels, n_boundary, norm_type="f", j_first=0):
+    lev = _c(levels)
+    out = np.zeros((rows * cols, N_sys * lev.size))
+    st = np.zeros(2, dtype=np.int64)
+    rc = lib().hm_sample_error_grid(ctypes.c_uint64(seed), which, rows, cols, ctypes.c_int64(N_sys),
+                                    ctypes.c_int64(j_first), lev.size, _p(lev), ctypes.c_int64(n_boundary),
+                                    {"f": 0, "2": 1}[norm_type], _p(out), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
+    assert rc == 0
+    return out.reshape(rows, cols, N_sys, lev.size), int(st[0]), int(st[1])

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../lq_mpc_b200/csrc/bounds.cuh"
+#include "../../lq_mpc_b200/csrc/sampler.cuh"
 
 #define HM_FOR_EACH_DIM(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 4) X(6, 2) X(8, 2)
 
@@ -251,6 +252,32 @@ int hm_spectral_radius_poly(int n, int64_t S, const double* M, double* rho, int3
     case 4: return rho_poly_t<4>(S, M, rho, trusted);
   }
   return -1;
+}
+
+void hm_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
+  const lq::Philox4 x = lq::philox4x32_10(ctr[0], ctr[1], ctr[2], ctr[3], key[0], key[1]);
+  for (int i = 0; i < 4; ++i) out[i] = x.v[i];
+}
+
+// the sampler core for the shapes of the reference example (2x2, 2x1) and the synthetic one (4x4, 4x2); SoA output
+int hm_sample_error_grid(uint64_t seed, int which, int rows, int cols, int64_t N_sys, int64_t j_first, int n_err,
+                         const double* levels, int64_t n_boundary, int norm_type, double* out, int64_t* stats) {
+  const int64_t S = N_sys * n_err;
+  stats[0] = stats[1] = 0;
+  for (int64_t s = 0; s < S; ++s) {
+    const int64_t j = j_first + s / n_err;
+    const int i = (int)(s % n_err);
+    double T[16];
+    int rc;
+    if (rows == 2 && cols == 2) rc = lq::sample_error_matrix<2, 2>(seed, which, j, i, levels[i], j < n_boundary, norm_type, T);
+    else if (rows == 2 && cols == 1) rc = lq::sample_error_matrix<2, 1>(seed, which, j, i, levels[i], j < n_boundary, norm_type, T);
+    else if (rows == 4 && cols == 4) rc = lq::sample_error_matrix<4, 4>(seed, which, j, i, levels[i], j < n_boundary, norm_type, T);
+    else if (rows == 4 && cols == 2) rc = lq::sample_error_matrix<4, 2>(seed, which, j, i, levels[i], j < n_boundary, norm_type, T);
+    else return -1;
+    if (rc < 0) { stats[1] += 1; stats[0] += -rc; } else stats[0] += rc;
+    for (int q = 0; q < rows * cols; ++q) out[(int64_t)q * S + s] = T[q];
+  }
+  return 0;
 }
 
 int hm_sym_eig_minmax(int n, int64_t S, const double* M, double* lo, double* hi) {
