@@ -261,16 +261,9 @@ def run_ours(args):
     ms_kernel = k0.elapsed_time(k1) / args.steps
     # ---- (3) end to end through the host-buffer entry point: pinned host -> H2D -> K1 -> D2H, every step
     outb = None
-    if tiled:       # K4: H2D of the pinned shard, evaluation, D2H of the result table — all inside the timed region
-        hout = torch.empty((3, S), dtype=torch.float64).pin_memory()
-        hfl = torch.empty((1, S), dtype=torch.int32).pin_memory()
-
-        def host_step(_):
-            rr = evaluate(hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), hx.cuda(non_blocking=True))
-            hout.copy_(rr["table"], non_blocking=True)
-            hfl.copy_(rr["flags"], non_blocking=True)
-            torch.cuda.synchronize()
-            return {"J": hout[0:1], "rho": hout[1:2], "ratio": hout[2:3], "flags": hfl}
+    if tiled:       # K4: chunked H2D -> K4a + K4b -> D2H pipeline from the pinned shard (lqmpc_eval_batch_tiled_host)
+        def host_step(prev):
+            return eng.eval_batch_tiled_host(hA, hB, hx, HORIZON, HORIZON, out=prev, chunk=16384)
     else:
         def host_step(prev):
             return eng.eval_batch_host(hA, hB, hx, HORIZON, HORIZON, out=prev, chunk=1 << 19)
@@ -327,7 +320,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": int(S * (n * n + n * m + n) * 8),
                     "d2h_bytes_per_step": int(S * (3 * 8 + 4)), "matches_device_path": same,
                     "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)" if not tiled
-                    else "pinned host arrays -> H2D -> lqmpc_eval_batch_tiled -> D2H of the result table"},
+                    else "lqmpc_eval_batch_tiled_host (pinned host array-of-matrices in, J/rho/ratio/flags tables out)"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "worst_case": {"ratio_max": float(st["max"][2]), "ratio_mean": float(st["mean"][2]),

@@ -102,6 +102,12 @@ int lqmpc_get_prepared_tiled(lqmpc_ctx* ctx, double* Pexp_host, int64_t capacity
 int lqmpc_eval_batch_tiled(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, const double* x0, int N_min,
                            int N_max, double* J, double* rho, double* ratio, double* V_N, int32_t* flags);
 
+/* Same from HOST buffers (array-of-matrices, ideally pinned; outputs [H][S] on the host): chunks are copied H2D,
+ * evaluated and copied back on three streams so that PCIe traffic overlaps the kernels. Synchronises. */
+int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host, const double* dB_host,
+                                const double* x0_host, int N_min, int N_max, double* J_host, double* rho_host,
+                                double* ratio_host, int32_t* flags_host, int64_t chunk);
+
 /* K2a — batched LQ_MPC_Controller.solve (utils_class.py:48-91) with the input box of lqmpc_set_problem, zero
  * references, terminal weight P: for every sample the controller model is (A+dA_s, B+dB_s) (dA/dB NULL = the true
  * model, e.g. for V_expert, utils_class.py:786). The QP is solved EXACTLY (Riccati-structured primal active set).

@@ -115,6 +115,8 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
   if (ctx->tiled_pb) cudaFree(ctx->tiled_pb);
   if (ctx->tiled_zero) cudaFree(ctx->tiled_zero);
+  for (int i = 0; i < 6; ++i)
+    if (ctx->tp_ev[i]) cudaEventDestroy(ctx->tp_ev[i]);
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe_buf[i]) cudaFree(ctx->pipe_buf[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
@@ -227,6 +229,78 @@ int lqmpc_eval_batch_tiled(lqmpc_ctx* ctx, int64_t S, const double* dA, const do
   t.S = S; t.dA = dA; t.dB = dB; t.x0 = x0; t.N_min = N_min; t.N_max = N_max;
   t.J = J; t.rho = rho; t.ratio = ratio; t.Vn = V_N; t.flags = flags; t.Pout = nullptr;
   return lq_launch_tiled(ctx, t);
+}
+
+int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const double* dB_h, const double* x0_h,
+                                int N_min, int N_max, double* J_h, double* rho_h, double* ratio_h, int32_t* flags_h,
+                                int64_t chunk) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_tiled) return lq_set_error(ctx, LQMPC_ESTATE, "tiled problem not set");
+  if (S < 0 || N_min < 1 || N_max < N_min) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/N_min/N_max");
+  if (S == 0) return LQMPC_OK;
+  if (!dA_h || !dB_h || !x0_h) return lq_set_error(ctx, LQMPC_EINVAL, "null input");
+  cudaSetDevice(ctx->device);
+  const int n = ctx->tn, m = ctx->tm, H = N_max - N_min + 1;
+  if (chunk <= 0) chunk = 16384;
+  if (chunk > S) chunk = S;
+  chunk = (chunk + 1) & ~(int64_t)1;                       // keeps every slot section 16-byte aligned (TMA sources)
+  const int64_t in_d = (int64_t)n * n + (int64_t)n * m + n;
+  const size_t slot = (size_t)chunk * 8 * (size_t)(in_d + 3 * H) + (size_t)chunk * 4 * (size_t)H + 64;
+  int rc = ensure_pipe(ctx, slot);
+  if (rc) return rc;
+  for (int i = 0; i < 6; ++i)
+    if (!ctx->tp_ev[i]) {
+      rc = lq_check_cuda(ctx, cudaEventCreateWithFlags(&ctx->tp_ev[i], cudaEventDisableTiming), "pipeline event");
+      if (rc) return rc;
+    }
+  cudaStream_t s_in = ctx->pipe_stream[0], s_out = ctx->pipe_stream[1], s_cmp = ctx->stream;
+  rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_cmp), "pre-pipeline sync");
+  if (rc) return rc;
+  // three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the two kernels of chunk c (which share one scratch)
+  const int64_t nchunks = (S + chunk - 1) / chunk;
+  for (int64_t c = 0; c < nchunks; ++c) {
+    const int b = (int)(c & 1);
+    cudaEvent_t ev_in = ctx->tp_ev[b], ev_cmp = ctx->tp_ev[2 + b], ev_out = ctx->tp_ev[4 + b];
+    const int64_t s0 = c * chunk;
+    const int64_t cs = (s0 + chunk <= S) ? chunk : (S - s0);
+    double* d_dA = reinterpret_cast<double*>(ctx->pipe_buf[b]);
+    double* d_dB = d_dA + (int64_t)n * n * chunk;
+    double* d_x0 = d_dB + (int64_t)n * m * chunk;
+    double* d_J = d_x0 + (int64_t)n * chunk;
+    double* d_rho = d_J + (int64_t)H * chunk;
+    double* d_ratio = d_rho + (int64_t)H * chunk;
+    int32_t* d_flags = reinterpret_cast<int32_t*>(d_ratio + (int64_t)H * chunk);
+    if (c >= 2) cudaStreamWaitEvent(s_in, ctx->tp_ev[2 + b], 0);      // slot inputs free once chunk c-2 was computed
+    rc = lq_check_cuda(ctx, cudaMemcpyAsync(d_dA, dA_h + s0 * n * n, (size_t)cs * n * n * 8, cudaMemcpyHostToDevice, s_in),
+                       "H2D dA");
+    if (rc) return rc;
+    cudaMemcpyAsync(d_dB, dB_h + s0 * n * m, (size_t)cs * n * m * 8, cudaMemcpyHostToDevice, s_in);
+    cudaMemcpyAsync(d_x0, x0_h + s0 * n, (size_t)cs * n * 8, cudaMemcpyHostToDevice, s_in);
+    cudaEventRecord(ev_in, s_in);
+    cudaStreamWaitEvent(s_cmp, ev_in, 0);
+    if (c >= 2) cudaStreamWaitEvent(s_cmp, ctx->tp_ev[4 + b], 0);     // slot outputs free once chunk c-2 was copied back
+    TiledEval t;
+    t.S = cs; t.dA = d_dA; t.dB = d_dB; t.x0 = d_x0; t.N_min = N_min; t.N_max = N_max;
+    t.J = d_J; t.rho = d_rho; t.ratio = d_ratio; t.Vn = nullptr; t.flags = d_flags; t.Pout = nullptr;
+    // [H][cs] tables inside the slot: the kernels index outputs with leading dimension S = cs
+    rc = lq_launch_tiled(ctx, t);
+    if (rc) return rc;
+    cudaEventRecord(ev_cmp, s_cmp);
+    cudaStreamWaitEvent(s_out, ev_cmp, 0);
+    const size_t w = (size_t)cs * 8, sp = (size_t)S * 8;
+    if (J_h) cudaMemcpy2DAsync(J_h + s0, sp, d_J, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
+    if (rho_h) cudaMemcpy2DAsync(rho_h + s0, sp, d_rho, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
+    if (ratio_h) cudaMemcpy2DAsync(ratio_h + s0, sp, d_ratio, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
+    if (flags_h)
+      cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)cs * 4, (size_t)cs * 4, (size_t)H,
+                        cudaMemcpyDeviceToHost, s_out);
+    cudaEventRecord(ev_out, s_out);
+  }
+  rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_out), "pipeline sync (D2H)");
+  if (rc) return rc;
+  rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_cmp), "pipeline sync (compute)");
+  if (rc) return rc;
+  return lq_check_cuda(ctx, cudaGetLastError(), "tiled host pipeline");
 }
 
 int lqmpc_get_prepared(lqmpc_ctx* ctx, double* out, int64_t capacity) {

@@ -39,6 +39,7 @@ struct lqmpc_ctx {
   cudaEvent_t pipe_done[2] = {nullptr, nullptr};
   void* pipe_buf[2] = {nullptr, nullptr};
   size_t pipe_bytes = 0;
+  cudaEvent_t tp_ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // tiled host pipeline: h2d/comp/d2h x 2 slots
 };
 
 struct EvalArgs {

@@ -47,6 +47,7 @@ ABI = {
     "lqmpc_set_problem_tiled": (_int, [_vp, _int, _int] + [_vp] * 5 + [_int]),
     "lqmpc_get_prepared_tiled": (_int, [_vp, _vp, _i64]),
     "lqmpc_eval_batch_tiled": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int] + [_vp] * 5),
+    "lqmpc_eval_batch_tiled_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64]),
     "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
     "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
     "lqmpc_bounds_fields": (_int, []),
@@ -230,6 +231,23 @@ class Engine:
                                              _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
                                              _ptr(out.get("V_N")), _ptr(out.get("flags")))
         self._check(rc, "lqmpc_eval_batch_tiled")
+        return out
+
+    def eval_batch_tiled_host(self, dA, dB, x0, N_min: int, N_max: int, out=None, chunk: int = 16384):
+        """eval_batch_tiled from/to HOST buffers (numpy arrays or CPU tensors [S][n*n] ..., ideally pinned), chunked
+        with copies overlapping the kernels. `out` may hold preallocated host tensors J/rho/ratio/flags [H][S]."""
+        torch = self.torch
+        S = x0.shape[0]
+        H = N_max - N_min + 1
+        if out is None:
+            out = {"J": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "rho": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "ratio": torch.empty((H, S), dtype=torch.float64).pin_memory(),
+                   "flags": torch.empty((H, S), dtype=torch.int32).pin_memory()}
+        rc = self.lib.lqmpc_eval_batch_tiled_host(self._h, S, _ptr(dA), _ptr(dB), _ptr(x0), N_min, N_max,
+                                                  _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
+                                                  _ptr(out.get("flags")), chunk)
+        self._check(rc, "lqmpc_eval_batch_tiled_host")
         return out
 
     def prepared(self):

@@ -535,6 +535,12 @@ def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
     assert np.array_equal(one["flags"].cpu().numpy()[0], g["flags"][2])
     empty = engine.eval_batch_tiled(np.zeros((0, n, n)), np.zeros((0, n, m)), np.zeros((0, n)), N, N)
     assert empty["J"].shape == (1, 0)
+    # host-buffer pipeline (3 streams, 2 slots), ragged chunks, nested horizons: identical to the device-resident call
+    import torch
+    h = [torch.from_numpy(np.ascontiguousarray(a)).pin_memory() for a in (dA, dB, x0)]
+    hp = engine.eval_batch_tiled_host(h[0], h[1], h[2], N - 2, N, chunk=64)
+    for k in ("J", "rho", "ratio", "flags"):
+        assert np.array_equal(hp[k].numpy(), g[k]), k
 
 
 # --------------------------------------------------------------------------------------------- sweep driver (cfg 2)
