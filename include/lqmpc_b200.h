@@ -193,6 +193,9 @@ int lqmpc_sample_error_grid(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, 
  * measured denominator of the FP64 roofline (MEASURED_PEAKS.json has none). Synchronises. */
 int lqmpc_fp64_peak(lqmpc_ctx* ctx, double* tflops_out);
 
+/* Same for the FP64 tensor cores (mma.sync.m8n8k4.f64 accumulator chains): the roofline denominator of K4. Synchronises. */
+int lqmpc_fp64_tensor_peak(lqmpc_ctx* ctx, double* tflops_out);
+
 /* Number of kernels this context has launched since creation (bench.py's `gpu_launches`). */
 int64_t lqmpc_launch_count(const lqmpc_ctx* ctx);
 

@@ -521,6 +521,12 @@ int lqmpc_column_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t 
   return lq_launch_moments(ctx, table, cols, S, ld, moments);
 }
 
+int lqmpc_fp64_tensor_peak(lqmpc_ctx* ctx, double* tflops_out) {
+  if (!ctx || !tflops_out) return LQMPC_EINVAL;
+  cudaSetDevice(ctx->device);
+  return lq_launch_dmma_peak(ctx, tflops_out);
+}
+
 int lqmpc_sample_error_grid(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int cols, int64_t N_sys,
                             int64_t j_first, int n_err, const double* levels_host, int64_t n_boundary, int norm_type,
                             double* out, int64_t* stats_host) {

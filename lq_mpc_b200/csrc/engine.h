@@ -126,6 +126,7 @@ int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes);
 int lq_launch_prepare(lqmpc_ctx* ctx);
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
+int lq_launch_dmma_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);
 int lq_launch_bounds(lqmpc_ctx* ctx, const BoundsArgs& a);
 int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats);

@@ -744,6 +744,53 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
 
 }  // namespace
 
+// ---- FP64 tensor-core peak: 8 independent m8n8k4 accumulator chains per warp (the K4 roofline denominator)
+namespace {
+__global__ void __launch_bounds__(256) dmma_peak_kernel(double* out, int iters, double a, double b) {
+  double c[8][2];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) { c[i][0] = threadIdx.x + i; c[i][1] = threadIdx.x - i; }
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dmma_m8n8k4(c[i][0], c[i][1], a, b);
+  }
+  double r = 0.0;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r += c[i][0] + c[i][1];
+  if (r == 123.456) out[0] = r;
+}
+}  // namespace
+
+int lq_launch_dmma_peak(lqmpc_ctx* ctx, double* tflops) {
+  int rc = lq_reserve_ws(ctx, 64);
+  if (rc) return rc;
+  int sms = 148;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  const int blocks = sms * 8, threads = 256, iters = 1 << 13;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = 0.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, ctx->stream);
+    dmma_peak_kernel<<<blocks, threads, 0, ctx->stream>>>(reinterpret_cast<double*>(ctx->ws), iters, 1e-3, 1e-3);
+    ctx->launches++;
+    cudaEventRecord(e1, ctx->stream);
+    rc = lq_check_cuda(ctx, cudaEventSynchronize(e1), "dmma peak sync");
+    if (rc) break;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, e0, e1);
+    // one m8n8k4 MMA = 8*8*4 FMAs = 512 flop per warp
+    const double fl = 512.0 * 8.0 * (double)iters * (double)blocks * (double)(threads / 32);
+    const double tf = fl / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *tflops = best;
+  return rc;
+}
+
 bool lq_tiled_supported(int n, int m) { return (n == 32 && m == 8) || (n == 16 && m == 4); }
 
 size_t lq_tiled_pb_doubles(int n, int m) { return (size_t)(4 * n * n + n * m + m * m); }

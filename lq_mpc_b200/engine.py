@@ -61,6 +61,7 @@ ABI = {
     "lqmpc_sample_error_grid": (_int, [_vp, ctypes.c_uint64, _int, _int, _int, _i64, _i64, _int, _vp, _i64, _int, _vp,
                                        _vp]),
     "lqmpc_fp64_peak": (_int, [_vp, _c_double_p]),
+    "lqmpc_fp64_tensor_peak": (_int, [_vp, _c_double_p]),
     "lqmpc_launch_count": (_i64, [_vp]),
 }
 
@@ -492,6 +493,11 @@ class Engine:
                                               None if st is None else st.ctypes.data)
         self._check(rc, "lqmpc_sample_error_grid")
         return (out, {"rejected": int(st[0]), "projected": int(st[1])}) if want_stats else out
+
+    def fp64_tensor_peak(self) -> float:
+        v = ctypes.c_double(0.0)
+        self._check(self.lib.lqmpc_fp64_tensor_peak(self._h, ctypes.byref(v)), "lqmpc_fp64_tensor_peak")
+        return float(v.value)
 
     def fp64_peak(self) -> float:
         v = ctypes.c_double(0.0)
