@@ -50,10 +50,10 @@ def merge_moments(parts):
     return finish(mx, mn, n, nb, mean, m2)
 
 
-def column_stats(engine, table, group=None):
-    """table: [cols][S_local] device tensor. One pass over the shard (K5 `lqmpc_column_moments`), ONE collective
-    (all-gather of 6 doubles per column), Chan merge in rank order. Returns dict of numpy arrays (max, min, mean, std,
-    count, n_nonfinite), identical on every rank."""
+def column_moments_device(engine, table, group=None):
+    """Asynchronous half of `column_stats`: K5 on this rank's shard plus the all-gather, everything enqueued on the
+    device; returns the [world][cols][6] DEVICE tensor of per-shard moments (no host synchronisation). Finish with
+    `merge_moments(t.cpu().numpy())` whenever the numbers are needed on the host."""
     import torch
     import torch.distributed as dist
     mom = engine.column_moments_raw(table)                      # device [cols][6]
@@ -61,10 +61,15 @@ def column_stats(engine, table, group=None):
         world = dist.get_world_size(group)
         allm = torch.empty((world,) + tuple(mom.shape), dtype=mom.dtype, device=mom.device)
         dist.all_gather_into_tensor(allm, mom, group=group)
-        parts = allm.cpu().numpy()
-    else:
-        parts = mom.cpu().numpy()[None]
-    return merge_moments(parts)
+        return allm
+    return mom[None]
+
+
+def column_stats(engine, table, group=None):
+    """table: [cols][S_local] device tensor. One pass over the shard (K5 `lqmpc_column_moments`), ONE collective
+    (all-gather of 6 doubles per column), Chan merge in rank order. Returns dict of numpy arrays (max, min, mean, std,
+    count, n_nonfinite), identical on every rank."""
+    return merge_moments(column_moments_device(engine, table, group).cpu().numpy())
 
 
 def column_stats_two_pass(engine, table, group=None):
