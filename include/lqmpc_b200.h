@@ -118,6 +118,13 @@ int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host
 int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int npts,
                           const double* pts, const double* x0, double* V, double* u0, double* M_V, int32_t* flags);
 
+/* Shared references for the following lqmpc_mpc_solve_batch / lqmpc_simulate_batch calls (utils_class.py:48-81:
+ * x_ref[:, i] is the reference of x_{i+1}, u_ref[:, i] of u_i; HOST pointers, row-major (n x n_cols), (m x n_cols),
+ * n_cols >= N of the calls that follow; either may be NULL = zeros). n_cols <= 0 or both NULL clears them (the state
+ * after lqmpc_set_problem). Non-zero references make the law affine: the exact solver then skips the Riccati fast
+ * path. The bound kernels (K3) and K1/K4 are regulation-only, as every caller in the reference is. Synchronises. */
+int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, const double* u_ref_host);
+
 /* K2b — batched LQ_MPC_Simulator.simulate (utils_class.py:245-285): T receding-horizon steps, the controller plans
  * with (A+dA_s, B+dB_s) and horizon N, the plant is the TRUE model; J_T as accumulated at utils_class.py:261,282-283.
  * Initial state: `x0_shared` device [n] (one state for all samples) or `x0` device [n][S].

@@ -113,6 +113,8 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
+  if (ctx->ref_x) cudaFree(ctx->ref_x);
+  if (ctx->ref_u) cudaFree(ctx->ref_u);
   if (ctx->tiled_pb) cudaFree(ctx->tiled_pb);
   if (ctx->tiled_zero) cudaFree(ctx->tiled_zero);
   for (int i = 0; i < 6; ++i)
@@ -149,6 +151,9 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   LQ_FOR_EACH_DIM(X)
 #undef X
   if (!found) return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
+  if (ctx->ref_x) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_x); ctx->ref_x = nullptr; }
+  if (ctx->ref_u) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_u); ctx->ref_u = nullptr; }
+  ctx->ref_ld = 0;
   ctx->n = n;
   ctx->m = m;
   ctx->N_opc = N_opc;
@@ -424,6 +429,34 @@ int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const d
     rc = lq_check_cuda(ctx, cudaStreamSynchronize(ctx->pipe_stream[b]), "pipeline sync");
     if (rc) return rc;
   }
+  return LQMPC_OK;
+}
+
+int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, const double* u_ref_host) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->ref_x) { cudaFree(ctx->ref_x); ctx->ref_x = nullptr; }
+  if (ctx->ref_u) { cudaFree(ctx->ref_u); ctx->ref_u = nullptr; }
+  ctx->ref_ld = 0;
+  if (n_cols <= 0 || (!x_ref_host && !u_ref_host)) return LQMPC_OK;     // cleared: zero references
+  const int n = ctx->n, m = ctx->m;
+  if (x_ref_host) {
+    int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->ref_x, (size_t)n * n_cols * sizeof(double)), "cudaMalloc x_ref");
+    if (rc) return rc;
+    rc = lq_check_cuda(ctx, cudaMemcpy(ctx->ref_x, x_ref_host, (size_t)n * n_cols * sizeof(double),
+                                       cudaMemcpyHostToDevice), "H2D x_ref");
+    if (rc) return rc;
+  }
+  if (u_ref_host) {
+    int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->ref_u, (size_t)m * n_cols * sizeof(double)), "cudaMalloc u_ref");
+    if (rc) return rc;
+    rc = lq_check_cuda(ctx, cudaMemcpy(ctx->ref_u, u_ref_host, (size_t)m * n_cols * sizeof(double),
+                                       cudaMemcpyHostToDevice), "H2D u_ref");
+    if (rc) return rc;
+  }
+  ctx->ref_ld = n_cols;
   return LQMPC_OK;
 }
 

@@ -25,6 +25,18 @@ struct WsView {
   LQ_HD double& operator[](int64_t e) const { return p[e * stride]; }
 };
 
+// Shared references of LQ_MPC_Controller.solve (utils_class.py:48-81): x_ref[:, i] is the reference of x_{i+1},
+// u_ref[:, i] of u_i (row-major, leading dimension ld >= N; only the first N columns are read). NULL = zeros, which is
+// what every caller in the reference passes; non-zero references make the law affine and disable the Riccati fast path.
+struct Refs {
+  const double* xr = nullptr;
+  const double* ur = nullptr;
+  int ld = 0;
+  LQ_HD bool any() const { return xr != nullptr || ur != nullptr; }
+  LQ_HD double x(int i, int k) const { return xr ? xr[i * ld + k] : 0.0; }
+  LQ_HD double u(int j, int k) const { return ur ? ur[j * ld + k] : 0.0; }
+};
+
 template <int n, int m>
 struct ClqrLayout {
   int N;
@@ -85,11 +97,16 @@ LQ_HD void step_model(const double* A, const double* B, const double* x, const d
 // Backward affine Riccati sweep for the working set (fixed, athi): stores K_k (m x n) and k_k (m).
 template <int n, int m>
 LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, uint64_t fixed, uint64_t athi,
-                         const WsView& ws) {
+                         const WsView& ws, const Refs& rf = Refs()) {
   const ClqrLayout<n, m> L(N);
+  // cost-to-go INCLUDING the state's own stage term: Phi_k(x) = x'S x + 2 s'x + const; Phi_N = (x - r_{N-1})'P(x - r_{N-1})
   double S[n * n], s[n];
   LQ_UNROLL for (int i = 0; i < n * n; ++i) S[i] = pb.Pt[i];
-  LQ_UNROLL for (int i = 0; i < n; ++i) s[i] = 0.0;
+  LQ_UNROLL for (int i = 0; i < n; ++i) {
+    double acc = 0.0;
+    LQ_UNROLL for (int j = 0; j < n; ++j) acc = fma(-pb.Pt[i * n + j], rf.x(j, N - 1), acc);
+    s[i] = acc;
+  }
   bool ok = true;
   for (int k = N - 1; k >= 0; --k) {
     double SB[n * m], G[m * m], Hx[m * (n + 1)];
@@ -109,6 +126,7 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, u
       }
       double acc = 0.0;
       LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Bh[r * m + i], s[r], acc);
+      LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(-pb.R[i * m + r], rf.u(r, k), acc);   // - R u_ref_k
       Hx[i * (n + 1) + n] = acc;
     }
     // clamp: substitute constants for the fixed components
@@ -159,9 +177,12 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, u
         t[i] = acc;
       }
       mm<m, m, n>(pb.R, K, RK);
-      mv<m, m>(pb.R, kv, Rk);
+      double kw[m];
+      LQ_UNROLL for (int j = 0; j < m; ++j) kw[j] = kv[j] - rf.u(j, k);
+      mv<m, m>(pb.R, kw, Rk);                              // R (k_k - u_ref_k)
       LQ_UNROLL for (int i = 0; i < n; ++i) {
         double acc = 0.0;
+        LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(-pb.Q[i * n + r], rf.x(r, k - 1), acc);   // - Q x_ref_{k-1}
         LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(K[r * n + i], Rk[r], acc);
         LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(Acl[r * n + i], t[r], acc);
         s[i] = acc;
@@ -178,38 +199,53 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, u
 // Exact constrained solve from state x0. Returns flags; writes u0[m] and V (= optimum + x0'Qx0).
 template <int n, int m>
 LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const double* x0, const WsView& ws,
-                     double* u0, double* V) {
+                     double* u0, double* V, const Refs& rf = Refs()) {
   const ClqrLayout<n, m> L(N);
   double x[n], xn[n], u[m];
-  // ---- 1. unconstrained plan; feasible => optimal
+  const bool trk = rf.any();
+  int flags = 0;
+  // ---- 1. unconstrained plan; feasible => optimal. With references the plan is affine: gains AND offsets come from
+  //         the affine sweep with an empty working set (stored where the constrained sweeps store theirs).
+  if (trk && !clqr_backward<n, m>(pb, pl, N, 0, 0, ws, rf)) flags |= FLAG_CHOL_FAIL;
+  const int64_t oK = trk ? L.oKc : L.oKu;
   bool feas = true;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
+  double cost_u = quad<n>(x0, pb.Q, x0);
   for (int k = 0; k < N; ++k) {
     double K[m * n];
-    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
     mv<m, n>(K, x, u);
     LQ_UNROLL for (int j = 0; j < m; ++j) {
+      if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
       if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) feas = false;
       if (k == 0) u0[j] = u[j];
     }
     if (!feas) break;
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
+    if (trk) {
+      double du[m], dx[n];
+      LQ_UNROLL for (int j = 0; j < m; ++j) du[j] = u[j] - rf.u(j, k);
+      LQ_UNROLL for (int i = 0; i < n; ++i) dx[i] = xn[i] - rf.x(i, k);
+      cost_u += quad<m>(du, pb.R, du);
+      cost_u += (k == N - 1) ? quad<n>(dx, pb.Pt, dx) : quad<n>(dx, pb.Q, dx);
+    }
     LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
   if (feas) {
-    *V = quad<n>(x0, pl.P0, x0);
-    return 0;
+    *V = trk ? cost_u : quad<n>(x0, pl.P0, x0);
+    return flags;
   }
-  int flags = FLAG_QP_ACTIVE;
+  flags |= FLAG_QP_ACTIVE;
   if (N * m > 64) return flags | FLAG_QP_MAXITER;   // working set is a 64-bit mask
   // ---- 2. feasible start: saturated rollout of the unconstrained gains; clipped components enter the working set
   uint64_t fixed = 0, athi = 0;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
   for (int k = 0; k < N; ++k) {
     double K[m * n];
-    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
     mv<m, n>(K, x, u);
     LQ_UNROLL for (int j = 0; j < m; ++j) {
+      if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
       const uint64_t bit = (uint64_t)1 << (k * m + j);
       if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed |= bit; athi |= bit; }
       else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed |= bit; }
@@ -222,7 +258,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   const int maxit = 8 * N * m + 32;
   bool done = false;
   for (int it = 0; it < maxit && !done; ++it) {
-    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws)) flags |= FLAG_CHOL_FAIL;
+    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf)) flags |= FLAG_CHOL_FAIL;
     // forward sweep: candidate z* (stored in zs), trajectory in xs, largest feasible step along z* - z
     double alpha = 1.0;
     int block = -1;
@@ -269,7 +305,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     double lam[n];
     {
       double xe[n];
-      LQ_UNROLL for (int i = 0; i < n; ++i) xe[i] = ws[L.oxs + (int64_t)N * n + i];
+      LQ_UNROLL for (int i = 0; i < n; ++i) xe[i] = ws[L.oxs + (int64_t)N * n + i] - rf.x(i, N - 1);
       mv<n, n>(pb.Pt, xe, lam);
       LQ_UNROLL for (int i = 0; i < n; ++i) lam[i] *= 2.0;
     }
@@ -277,7 +313,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     int rel = -1;
     for (int k = N - 1; k >= 0; --k) {
       double uk[m], g1[m], g2[m];
-      LQ_UNROLL for (int j = 0; j < m; ++j) uk[j] = ws[L.oz + (int64_t)k * m + j];
+      LQ_UNROLL for (int j = 0; j < m; ++j) uk[j] = ws[L.oz + (int64_t)k * m + j] - rf.u(j, k);
       mv<m, m>(pb.R, uk, g1);
       LQ_UNROLL for (int j = 0; j < m; ++j) {
         double acc = 0.0;
@@ -293,7 +329,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       }
       if (k > 0) {
         double xk[n], qx[n], atl[n];
-        LQ_UNROLL for (int i = 0; i < n; ++i) xk[i] = ws[L.oxs + (int64_t)k * n + i];
+        LQ_UNROLL for (int i = 0; i < n; ++i) xk[i] = ws[L.oxs + (int64_t)k * n + i] - rf.x(i, k - 1);
         mv<n, n>(pb.Q, xk, qx);
         LQ_UNROLL for (int i = 0; i < n; ++i) {
           double acc = 2.0 * qx[i];
@@ -316,8 +352,11 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       if (k == 0) u0[j] = u[j];
     }
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
-    cost += quad<m>(u, pb.R, u);
-    cost += (k == N - 1) ? quad<n>(xn, pb.Pt, xn) : quad<n>(xn, pb.Q, xn);
+    double du[m], dx[n];
+    LQ_UNROLL for (int j = 0; j < m; ++j) du[j] = u[j] - rf.u(j, k);
+    LQ_UNROLL for (int i = 0; i < n; ++i) dx[i] = xn[i] - rf.x(i, k);
+    cost += quad<m>(du, pb.R, du);
+    cost += (k == N - 1) ? quad<n>(dx, pb.Pt, dx) : quad<n>(dx, pb.Q, dx);
     LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
   }
   *V = cost;
@@ -328,7 +367,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
 // the plant is the TRUE model. Optional trajectories X [(T+1)*n], U [T*m] through strided views.
 template <int n, int m, class Traj>
 LQ_HD int simulate_sample(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, int T, const double* x0,
-                          const WsView& ws, double* J_T, int* n_active, Traj& traj) {
+                          const WsView& ws, double* J_T, int* n_active, Traj& traj, const Refs& rf = Refs()) {
   double x[n], xn[n], u[m];
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
   traj.state(0, x);
@@ -336,7 +375,7 @@ LQ_HD int simulate_sample(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, 
   int flags = 0, act = 0;
   for (int t = 0; t < T; ++t) {
     double V;
-    const int f = clqr_solve<n, m>(pb, pl, N, x, ws, u, &V);
+    const int f = clqr_solve<n, m>(pb, pl, N, x, ws, u, &V, rf);   // the same reference window every step (:269)
     flags |= f;
     act += (f & FLAG_QP_ACTIVE) ? 1 : 0;
     step_model<n, m>(pb.A, pb.B, x, u, xn);

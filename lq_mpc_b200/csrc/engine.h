@@ -31,6 +31,10 @@ struct lqmpc_ctx {
   bool has_tiled = false;
   void* tiled_pb = nullptr;
   void* tiled_zero = nullptr;   // n*n + n*m + n zero doubles (problem preparation runs the kernel on dA = dB = 0)
+  // shared references of the next mpc_solve / simulate calls (lqmpc_set_references); NULL = zeros
+  double* ref_x = nullptr;
+  double* ref_u = nullptr;
+  int ref_ld = 0;
   // scratch (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -75,6 +79,9 @@ struct MpcArgs {
   int32_t* flags;     // solve: [P][S]; simulate: [S]
   int32_t* n_active;  // [S]
   double* ws;         // filled by the launcher
+  const double* xr = nullptr;   // shared references (device, row-major [n][ref_ld] / [m][ref_ld]) or NULL = zeros
+  const double* ur = nullptr;
+  int ref_ld = 0;
 };
 
 struct BoundsArgs {

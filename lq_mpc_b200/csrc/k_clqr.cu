@@ -28,6 +28,8 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const __grid_constant__ 
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const lq::WsView ws{a.ws + tid, nthreads};
+  lq::Refs rf;
+  rf.xr = a.xr; rf.ur = a.ur; rf.ld = a.ref_ld;
   for (int64_t s = tid; s < a.S; s += nthreads) {
     lq::Plan<n, m> pl;
     load_plan<n, m>(a, pb, s, pl);
@@ -38,7 +40,7 @@ __global__ void __launch_bounds__(128) mpc_solve_kernel(const __grid_constant__ 
       double x0[n], u0[m], V;
 #pragma unroll
       for (int i = 0; i < n; ++i) x0[i] = a.pts ? a.pts[p * n + i] : a.x0[(int64_t)i * a.S + s];
-      const int f = pf | lq::clqr_solve<n, m>(pb, pl, a.N, x0, ws, u0, &V);
+      const int f = pf | lq::clqr_solve<n, m>(pb, pl, a.N, x0, ws, u0, &V, rf);
       mv = lq::dmax(mv, V);
       if (a.V) a.V[(int64_t)p * a.S + s] = V;
       if (a.u0) {
@@ -75,6 +77,8 @@ __global__ void __launch_bounds__(128) simulate_kernel(const __grid_constant__ l
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
   const lq::WsView ws{a.ws + tid, nthreads};
+  lq::Refs rf;
+  rf.xr = a.xr; rf.ur = a.ur; rf.ld = a.ref_ld;
   for (int64_t s = tid; s < a.S; s += nthreads) {
     lq::Plan<n, m> pl;
     load_plan<n, m>(a, pb, s, pl);
@@ -85,7 +89,7 @@ __global__ void __launch_bounds__(128) simulate_kernel(const __grid_constant__ l
     DevTraj<n, m> traj{a, s};
     double JT;
     int act;
-    const int f = pf | lq::simulate_sample<n, m>(pb, pl, a.N, a.T, x0, ws, &JT, &act, traj);
+    const int f = pf | lq::simulate_sample<n, m>(pb, pl, a.N, a.T, x0, ws, &JT, &act, traj, rf);
     if (a.J_T) a.J_T[s] = JT;
     if (a.flags) a.flags[s] = f;
     if (a.n_active) a.n_active[s] = act;
@@ -106,6 +110,8 @@ int launch_mpc_t(lqmpc_ctx* ctx, MpcArgs a, bool sim) {
   int rc = lq_reserve_ws(ctx, (size_t)(per * nthreads) * sizeof(double));
   if (rc) return rc;
   a.ws = reinterpret_cast<double*>(ctx->ws);
+  if (ctx->ref_ld >= a.N) { a.xr = ctx->ref_x; a.ur = ctx->ref_u; a.ref_ld = ctx->ref_ld; }
+  else if (ctx->ref_ld > 0) return lq_set_error(ctx, -1, "references hold fewer than N columns");
   if (sim)
     simulate_kernel<n, m><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a);
   else

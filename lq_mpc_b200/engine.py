@@ -48,6 +48,7 @@ ABI = {
     "lqmpc_get_prepared_tiled": (_int, [_vp, _vp, _i64]),
     "lqmpc_eval_batch_tiled": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int] + [_vp] * 5),
     "lqmpc_eval_batch_tiled_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64]),
+    "lqmpc_set_references": (_int, [_vp, _int, _vp, _vp]),
     "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
     "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
     "lqmpc_bounds_fields": (_int, []),
@@ -306,6 +307,39 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------------------------------------ K2
+    def set_references(self, x_ref=None, u_ref=None):
+        """Shared references of the following mpc_solve_batch / simulate_batch calls: x_ref (n, >=N), u_ref (m, >=N);
+        None / all-zero clears them (the reference's callers always pass zeros)."""
+        xr = None if x_ref is None else _np_f64(x_ref, (self.n, -1))
+        ur = None if u_ref is None else _np_f64(u_ref, (self.m, -1))
+        if xr is not None and not xr.any():
+            xr = None
+        if ur is not None and not ur.any():
+            ur = None
+        if xr is None and ur is None:
+            self._check(self.lib.lqmpc_set_references(self._h, 0, None, None), "lqmpc_set_references")
+            return self
+        cols = (xr if xr is not None else ur).shape[1]
+        if xr is not None and ur is not None and xr.shape[1] != ur.shape[1]:
+            cols = min(xr.shape[1], ur.shape[1])
+            xr, ur = np.ascontiguousarray(xr[:, :cols]), np.ascontiguousarray(ur[:, :cols])
+        self._check(self.lib.lqmpc_set_references(self._h, cols, _ptr(xr), _ptr(ur)), "lqmpc_set_references")
+        return self
+
+    def references(self, x_ref=None, u_ref=None):
+        """`with eng.references(x_ref, u_ref): ...` — set for the K2 calls inside, cleared on exit."""
+        eng = self
+
+        class _Scope:
+            def __enter__(self_inner):
+                eng.set_references(x_ref, u_ref)
+                return eng
+
+            def __exit__(self_inner, *exc):
+                eng.set_references(None, None)
+                return False
+        return _Scope()
+
     def _opt_dev(self, a):
         return None if a is None else self._dev(a)
 

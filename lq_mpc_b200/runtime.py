@@ -41,12 +41,6 @@ def box_from_F(F_u):
     return lo, hi
 
 
-def require_zero_refs(x_ref, u_ref):
-    """Every caller in the reference passes all-zero references; tracking terms are a `next` row."""
-    if (x_ref is not None and np.any(np.asarray(x_ref) != 0)) or (u_ref is not None and np.any(np.asarray(u_ref) != 0)):
-        raise NotImplementedError("non-zero x_ref / u_ref are not supported by the B200 engine yet")
-
-
 def problem_for(A, B, Q, R, P=None, F_u=None, N_opc=30, device=None) -> Engine:
     """Engine with (A, B, Q, R, P, box(F_u)) installed as the TRUE/nominal problem."""
     eng = get_engine(device)

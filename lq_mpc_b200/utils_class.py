@@ -3,7 +3,9 @@ dict keys; citations are into /root/reference/utils_class.py). Every numeric res
 single calls are S = 1 batches, the sweep drivers pack all (system, level) pairs of a table into one launch.
 
 Not carried over: the three Plotter_* classes (presentation, out of scope) — importing them raises a clear error.
-Unsupported inputs fail loudly instead of falling back: non-box F_u, non-zero references.
+Unsupported inputs fail loudly instead of falling back: non-box F_u; non-zero references are supported by the
+controller / simulator / M_V paths (K2) and rejected by the regulation-only bound drivers, as upstream's own callers
+only ever pass zeros there.
 """
 from __future__ import annotations
 
@@ -35,10 +37,10 @@ class LQ_MPC_Controller:
         self.A, self.B, self.Q, self.R, self.P, self.F_u = A, B, Q, R, P, F_u
 
     def solve(self, x0, x_ref, u_ref):
-        _rt.require_zero_refs(x_ref, u_ref)
         eng = _rt.problem_for(self.A, self.B, self.Q, self.R, self.P, self.F_u)
         x0 = np.asarray(x0, dtype=np.float64).reshape(1, -1)
-        out = eng.mpc_solve_batch(None, None, self.N, pts=x0, S=1, want=("V", "u0"))
+        with eng.references(x_ref, u_ref):        # utils_class.py:62-81; all-zero references = regulation
+            out = eng.mpc_solve_batch(None, None, self.N, pts=x0, S=1, want=("V", "u0"))
         return {'u_0': _cpu(out["u0"])[0, :, 0].copy(), 'V_N': float(_cpu(out["V"])[0, 0])}
 
 
@@ -53,15 +55,15 @@ class LQ_MPC_Simulator:
         self.X = np.zeros((np.asarray(A).shape[1], self.T + 1))
 
     def simulate(self, x0, A_true, B_true, x_ref, u_ref):
-        _rt.require_zero_refs(x_ref, u_ref)
         A_true = np.asarray(A_true, dtype=np.float64)
         n = A_true.shape[0]
         B_true = np.asarray(B_true, dtype=np.float64).reshape(n, -1)
         eng = _rt.problem_for(A_true, B_true, self.Q, self.R, self.P, self.F_u)
         dA = (np.asarray(self.A, dtype=np.float64) - A_true).reshape(-1, 1)
         dB = (np.asarray(self.B, dtype=np.float64).reshape(n, -1) - B_true).reshape(-1, 1)
-        out = eng.simulate_batch(dA, dB, self.N, self.T, x0_shared=np.asarray(x0, dtype=np.float64).reshape(n),
-                                 want=("J_T", "X", "U"))
+        with eng.references(x_ref, u_ref):        # the same reference window at every step (utils_class.py:269)
+            out = eng.simulate_batch(dA, dB, self.N, self.T, x0_shared=np.asarray(x0, dtype=np.float64).reshape(n),
+                                     want=("J_T", "X", "U"))
         self.X[:, :] = _cpu(out["X"])[:, :, 0].T
         self.U[:, :] = _cpu(out["U"])[:, :, 0].T
         return {'X': self.X, 'U': self.U, 'J_T': float(_cpu(out["J_T"])[0])}
@@ -118,9 +120,10 @@ class LQ_RDP_Behavior:
 
     def OL_energy_bound(self, N, N_points, ext_radius_max, x_ref, u_ref):
         """utils_class.py:439-466."""
-        _rt.require_zero_refs(x_ref, u_ref)
         x0_vec = circle_generator(N_points, ext_radius_max, self.epsilon, self.Q)
-        out = self._engine().mpc_solve_batch(None, None, int(N), pts=x0_vec.T, S=1, want=("M_V",))
+        eng = self._engine()
+        with eng.references(x_ref, u_ref):
+            out = eng.mpc_solve_batch(None, None, int(N), pts=x0_vec.T, S=1, want=("M_V",))
         return float(_cpu(out["M_V"])[0])
 
     def _bounds_over(self, N, e_vec, K, M_V, x, p):
@@ -161,8 +164,6 @@ class LQ_RDP_Behavior:
 
     def _surface(self, N, sim_info, sys_true, err_nominal, info_ref, M_V, p, points):
         """Shared body of data_generation_plane / _mesh for a (n, S) array of initial states: three launches."""
-        _rt.require_zero_refs(info_ref['x_ref'], info_ref['u_ref'])
-        _rt.require_zero_refs(info_ref['x_ref_long'], info_ref['u_ref_long'])
         e_A, e_B = err_nominal['e_A'], err_nominal['e_B']
         A_true = np.asarray(sys_true['A_true'], dtype=np.float64)
         n = A_true.shape[0]
@@ -179,10 +180,12 @@ class LQ_RDP_Behavior:
         alpha, beta = _cpu(b['alpha']), _cpu(b['beta'])
         # open-loop expert cost on the TRUE system and closed-loop cost of the estimated-model controller
         eng_t = self._engine(A_true, B_true)
-        V = _cpu(eng_t.mpc_solve_batch(None, None, int(sim_info['N_opc']), x0=pts, S=S, want=("V",))["V"])[0]
+        with eng_t.references(info_ref['x_ref_long'], info_ref['u_ref_long']):            # :591, :672
+            V = _cpu(eng_t.mpc_solve_batch(None, None, int(sim_info['N_opc']), x0=pts, S=S, want=("V",))["V"])[0]
         dA = np.repeat((np.asarray(self.A, dtype=np.float64) - A_true).reshape(-1, 1), S, axis=1)
         dB = np.repeat((np.asarray(self.B, dtype=np.float64).reshape(n, -1) - B_true).reshape(-1, 1), S, axis=1)
-        J = _cpu(eng_t.simulate_batch(dA, dB, int(N), int(sim_info['T_mpc']), x0=pts, want=("J_T",))["J_T"])
+        with eng_t.references(info_ref['x_ref'], info_ref['u_ref']):                      # :598, :679
+            J = _cpu(eng_t.simulate_batch(dA, dB, int(N), int(sim_info['T_mpc']), x0=pts, want=("J_T",))["J_T"])
         return J, factor * (alpha * V + beta), V
 
     def data_generation_plane(self, N, sim_info, sys_true, err_nominal, info_ref, M_V, p, N_points,
@@ -236,12 +239,13 @@ class LQ_RDP_Behavior_Multiple:
         K_lqr = _cpu(self.engine.dlqr_batch(S=1)["K"])[:, 0].reshape(np.asarray(self.B_true).shape[1], -1)
         self.epsilon_lqr = local_radius(self.F_u, -K_lqr, self.Q)             # utils_class.py:761-764
 
-    def _column_block(self, dA, dB, N, e, x0_vec, x_start, V_expert, p, strict_reference=True):
+    def _column_block(self, dA, dB, N, e, x0_vec, x_start, V_expert, p, strict_reference=True, refs=(None, None)):
         """All five quantities for S estimated models sharing one horizon N: three launches
         (ring solves -> M_V, closed-loop simulate -> J_T, bounds -> alpha, beta, xi, eta, bound)."""
         eng = self.engine
-        mv = eng.mpc_solve_batch(dA, dB, int(N), pts=x0_vec.T, want=("M_V",))["M_V"]      # utils_class.py:813-824
-        J = eng.simulate_batch(dA, dB, int(N), int(self.N_mpc), x0_shared=x_start, want=("J_T", "flags"))   # 828-833
+        with eng.references(*refs):
+            mv = eng.mpc_solve_batch(dA, dB, int(N), pts=x0_vec.T, want=("M_V",))["M_V"]  # utils_class.py:813-824
+            J = eng.simulate_batch(dA, dB, int(N), int(self.N_mpc), x0_shared=x_start, want=("J_T", "flags"))  # 828-833
         b = eng.bounds_batch(dA, dB, int(N), e, e, mv, x_start, p, V_expert, K=None,                       # 840-859
                              strict_reference=strict_reference)
         return {'alpha': b['alpha'], 'beta': b['beta'], 'xi': b['xi'], 'bound': b['bound'], 'J': J['J_T'],
@@ -249,21 +253,21 @@ class LQ_RDP_Behavior_Multiple:
 
     def data_generation(self, N_points: int, ext_radius_max: float, info_ref: dict, p: np.ndarray) -> dict:
         """utils_class.py:766-959. Returns the reference's 13 keys and writes data_lq_mpc_multipleSys.npz to cwd."""
-        for k in ('x_ref', 'u_ref', 'x_ref_long', 'u_ref_long'):
-            _rt.require_zero_refs(info_ref[k], None)
         self.engine = _rt.problem_for(self.A_true, self.B_true, self.Q, self.R, self.Q, self.F_u, N_opc=self.N_opc)
         x0_vec = circle_generator(N_points, ext_radius_max, self.epsilon_lqr, self.Q)
         x_start = x0_vec[:, 1].copy()                                                     # :783
-        V_expert = self.mpc_open.solve(x_start, None, None)['V_N']                        # :786
+        V_expert = self.mpc_open.solve(x_start, info_ref['x_ref_long'], info_ref['u_ref_long'])['V_N']   # :786
         self.engine = _rt.problem_for(self.A_true, self.B_true, self.Q, self.R, self.Q, self.F_u, N_opc=self.N_opc)
         n_err, N_sys = len(self.error_vec), self.N_sys
         eA, eB = self.error_A[:, :, :N_sys, :], self.error_B[:, :, :N_sys, :]
         # ---- error sweep: every (system j, level i) pair in one batch, s = j*n_err + i
         dA, dB = grids_to_soa(np.ascontiguousarray(eA), np.ascontiguousarray(eB))
         e_per = np.tile(self.error_vec, N_sys)
-        r = self._column_block(dA, dB, self.N_nominal, e_per, x0_vec, x_start, V_expert, p)
+        r = self._column_block(dA, dB, self.N_nominal, e_per, x0_vec, x_start, V_expert, p,
+                               refs=(info_ref['x_ref'], info_ref['u_ref']))                # :820, :832
         tab_e = {k: _cpu(r[k]).reshape(N_sys, n_err) for k in ('alpha', 'beta', 'xi', 'bound', 'J')}
-        # ---- horizon sweep: level index 4 is hard-coded in the reference (:880), scalar error = e_nominal (:872)
+        # ---- horizon sweep: level index 4 is hard-coded in the reference (:880), scalar error = e_nominal (:872);
+        #      its references are zeros built per horizon (:887-888), whatever info_ref holds
         dA4, dB4 = grids_to_soa(np.ascontiguousarray(eA), np.ascontiguousarray(eB), level=4)
         tab_h = {k: np.zeros([N_sys, len(self.horizon)]) for k in ('alpha', 'beta', 'xi', 'bound', 'J')}
         for i, N in enumerate(self.horizon):

@@ -188,4 +188,50 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    import sys as _sys
+    if "--tracking" not in _sys.argv:
+        main()
+
+
+def tracking_cases(uc, seed=11):
+    """Non-zero references (utils_class.py:62-81: (x_{i+1} - x_ref[:, i])' Q~ (.) + (u_i - u_ref[:, i])' R (.)) through
+    the untouched reference classes: open-loop solves and closed loops, saturated and not."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    for c in range(16):
+        n = 2 if c % 2 == 0 else 3
+        m = 1 if c % 3 else 2
+        N = int(rng.integers(2, 11))
+        T = int(rng.integers(3, 10))
+        A = rng.normal(size=(n, n))
+        A *= rng.uniform(0.6, 1.1) / np.max(np.abs(np.linalg.eigvals(A)))
+        B = rng.normal(size=(n, m))
+        q, r = rng.uniform(0.5, 3.0), rng.uniform(0.3, 2.0)
+        Q, R = q * np.eye(n), r * np.eye(m)
+        ub = rng.uniform(0.05, 0.5)
+        F_u = np.vstack((np.eye(m) / ub, -np.eye(m) / ub))
+        x0 = rng.normal(size=n) * rng.uniform(0.05, 0.6)
+        dA = rng.uniform(-0.02, 0.02, size=(n, n))
+        dB = rng.uniform(-0.02, 0.02, size=(n, m))
+        xr = rng.normal(size=(n, N + 2)) * rng.uniform(0.0, 0.4)        # wider than N: only the first N columns count
+        ur = rng.normal(size=(m, N + 2)) * rng.uniform(0.0, 0.3)
+        sol = uc.LQ_MPC_Controller(N, A + dA, B + dB, Q, R, Q, F_u).solve(x0, xr, ur)
+        sim = uc.LQ_MPC_Simulator(T, N, A + dA, B + dB, Q, R, Q, F_u).simulate(x0, A, B, xr, ur)
+        cases.append({'n': n, 'm': m, 'N': N, 'T': T, 'A': _l(A), 'B': _l(B), 'dA': _l(dA), 'dB': _l(dB), 'q': q,
+                      'r': r, 'ub': ub, 'x0': _l(x0), 'x_ref': _l(xr), 'u_ref': _l(ur), 'u_0': _l(sol['u_0']),
+                      'V_N': float(sol['V_N']), 'J_T': float(sim['J_T']), 'X': _l(sim['X']), 'U': _l(sim['U'])})
+    return cases
+
+
+def main_tracking():
+    """Adds tests/golden/ref_tracking_cases.json without touching the other fixtures."""
+    u, uc = ro.load()
+    with open(os.path.join(GOLD, "ref_tracking_cases.json"), "w") as f:
+        json.dump(tracking_cases(uc), f, indent=0)
+    print("tracking fixtures written")
+
+
+if __name__ == "__main__":
+    import sys as _sys
+    if "--tracking" in _sys.argv:
+        main_tracking()

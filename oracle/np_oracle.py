@@ -102,9 +102,10 @@ def sl_syn_Gamma(N, A, B):
     return out
 
 
-def condensed_qp(N, A, B, Q, R, P_term, x0):
-    """H, g, c0 with objective z'Hz + 2g'z + c0 for z = vec(u_0..u_{N-1}) (time-major), zero references
-    (utils_class.py:59-75: stage cost Q on x_1..x_{N-1}, P on x_N, R on every u_k)."""
+def condensed_qp(N, A, B, Q, R, P_term, x0, x_ref=None, u_ref=None):
+    """H, g, c0 with objective z'Hz + 2g'z + c0 for z = vec(u_0..u_{N-1}) (time-major)
+    (utils_class.py:59-75: stage cost Q on x_1..x_{N-1}, P on x_N, R on every u_k; x_ref[:, i] is the reference of
+    x_{i+1}, u_ref[:, i] of u_i — only the first N columns are read)."""
     n, m = B.shape
     Gam = sl_syn_Gamma(N, A, B)[n:]            # rows for x_1..x_N
     Phi = sl_syn_Phi(N, A)[n:]
@@ -112,8 +113,14 @@ def condensed_qp(N, A, B, Q, R, P_term, x0):
     Rb = sla.block_diag(*([R] * N))
     H = Rb + Gam.T @ W @ Gam
     f = Phi @ x0
+    if x_ref is not None:
+        f = f - np.asarray(x_ref, dtype=float)[:, :N].T.reshape(-1)
     g = Gam.T @ W @ f
     c0 = f @ W @ f
+    if u_ref is not None:
+        w = np.asarray(u_ref, dtype=float)[:, :N].T.reshape(-1)
+        g = g - Rb @ w
+        c0 = c0 + w @ Rb @ w
     return 0.5 * (H + H.T), g, float(c0)
 
 
@@ -128,8 +135,9 @@ def box_qp(H, g, lo, hi):
     return res.x
 
 
-def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None):
-    """LQ_MPC_Controller.solve (utils_class.py:48-91) with zero references. Returns (u_0, V_N, active).
+def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_ref=None, u_ref=None):
+    """LQ_MPC_Controller.solve (utils_class.py:48-91). Returns (u_0, V_N, active). Non-zero references always take
+    the dense condensed QP (the law is affine then).
 
     exact_fast: if the unconstrained (Riccati) open-loop plan is feasible it IS the QP minimiser (KKT with zero
     multipliers), so the dense QP is only assembled when some planned input leaves the box."""
@@ -137,7 +145,9 @@ def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None):
     x0 = np.asarray(x0, dtype=float)
     lo = np.full(m, -np.inf) if lo is None else np.asarray(lo, dtype=float)
     hi = np.full(m, np.inf) if hi is None else np.asarray(hi, dtype=float)
-    if exact_fast:
+    tracking = (x_ref is not None and np.any(np.asarray(x_ref) != 0)) or \
+        (u_ref is not None and np.any(np.asarray(u_ref) != 0))
+    if exact_fast and not tracking:
         K, P = riccati(A, B, Q, R, P_term, N) if _ric is None else _ric
         x = x0
         feas = True
@@ -149,14 +159,15 @@ def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None):
             x = A @ x + B @ u
         if feas:
             return K[0] @ x0, float(x0 @ P[0] @ x0), False
-    H, g, c0 = condensed_qp(N, A, B, Q, R, P_term, x0)
+    H, g, c0 = condensed_qp(N, A, B, Q, R, P_term, x0, x_ref, u_ref)
     z = box_qp(H, g, np.tile(lo, N), np.tile(hi, N))
     V = float(z @ H @ z + 2 * g @ z + c0 + x0 @ Q @ x0)
-    return z[:m].copy(), V, True
+    active = bool(np.any(z <= np.tile(lo, N)) or np.any(z >= np.tile(hi, N))) if tracking else True
+    return z[:m].copy(), V, active
 
 
 # ----------------------------------------------------------------------------------------------- a2: simulator
-def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=True):
+def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=True, x_ref=None, u_ref=None):
     """LQ_MPC_Simulator.simulate (utils_class.py:245-285): controller plans with (A,B), plant is (A_true,B_true).
     J_T = x0'Qx0 + sum_t (x_{t+1}'Q x_{t+1} + u_t'R u_t)."""
     n, m = B.shape
@@ -167,7 +178,7 @@ def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=Tr
     n_active = 0
     ric = riccati(A, B, Q, R, P_term, N) if exact_fast else None
     for t in range(T):
-        u, _, act = mpc_solve(N, A, B, Q, R, P_term, lo, hi, X[:, t], exact_fast, ric)
+        u, _, act = mpc_solve(N, A, B, Q, R, P_term, lo, hi, X[:, t], exact_fast, ric, x_ref, u_ref)
         n_active += int(act)
         U[:, t] = u
         xn = A_true @ X[:, t] + B_true @ u

@@ -30,6 +30,22 @@ def known():
 
 
 @pytest.fixture(scope="session")
+def tracking():
+    """Non-zero-reference solves / closed loops of the untouched reference (oracle/make_golden.py --tracking)."""
+    with open(os.path.join(GOLD, "ref_tracking_cases.json")) as f:
+        return json.load(f)
+
+
+def tracking_case(c):
+    """Arrays of one tests/golden/ref_tracking_cases.json entry."""
+    n, m = c["n"], c["m"]
+    d = {k: np.array(c[k]) for k in ("A", "B", "dA", "dB", "x0", "x_ref", "u_ref", "u_0", "X", "U")}
+    d.update(n=n, m=m, N=c["N"], T=c["T"], Q=c["q"] * np.eye(n), R=c["r"] * np.eye(m), lo=-c["ub"] * np.ones(m),
+             hi=c["ub"] * np.ones(m), F_u=np.vstack((np.eye(m), -np.eye(m))) / c["ub"], V_N=c["V_N"], J_T=c["J_T"])
+    return d
+
+
+@pytest.fixture(scope="session")
 def golden_norm2():
     return dict(np.load(os.path.join(GOLD, "ref_norm2_subset.npz")))
 

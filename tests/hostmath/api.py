@@ -67,8 +67,20 @@ def eval_batch(A, B, Q, R, Pt, N_opc, dA_soa, dB_soa, x0_soa, Nmin, Nmax, T):
     return o
 
 
-def mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None):
-    """mode 0: open-loop solves; mode 1: closed-loop simulate."""
+def mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None, x_ref=None, u_ref=None):
+    """mode 0: open-loop solves; mode 1: closed-loop simulate. x_ref (n, >=N) / u_ref (m, >=N): shared references."""
+    xr, ur = _c(x_ref), _c(u_ref)
+    if xr is not None or ur is not None:
+        ld = (xr if xr is not None else ur).shape[1]
+        assert (xr is None or xr.shape[1] == ld) and (ur is None or ur.shape[1] == ld) and ld >= N
+        lib().hm_set_refs(_p(xr), _p(ur), ld)
+    try:
+        return _mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T, pts, x0_soa)
+    finally:
+        lib().hm_set_refs(None, None, 0)
+
+
+def _mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None):
     n, m = B.shape
     S = 1 if dA_soa is None else dA_soa.shape[-1]
     if dA_soa is None and x0_soa is not None:

@@ -13,6 +13,8 @@
 
 namespace {
 
+lq::Refs g_refs;   // set by hm_set_refs (test fixture state)
+
 template <int n, int m>
 void fill_problem(lq::Problem<n, m>& pb, const double* A, const double* B, const double* Q, const double* R,
                   const double* P, const double* lo, const double* hi, int N_opc) {
@@ -104,7 +106,7 @@ int mpc_t(int mode, const double* A, const double* B, const double* Q, const dou
       for (int p = 0; p < Pn; ++p) {
         double xx[n], uu[m], v;
         for (int i = 0; i < n; ++i) xx[i] = pts ? pts[p * n + i] : x0[i * S + s];
-        const int f = pf | lq::clqr_solve<n, m>(pb, pl, N, xx, ws, uu, &v);
+        const int f = pf | lq::clqr_solve<n, m>(pb, pl, N, xx, ws, uu, &v, g_refs);
         if (v > mvv) mvv = v;
         if (V) V[(int64_t)p * S + s] = v;
         if (u0) for (int j = 0; j < m; ++j) u0[((int64_t)p * m + j) * S + s] = uu[j];
@@ -116,7 +118,7 @@ int mpc_t(int mode, const double* A, const double* B, const double* Q, const dou
       int act;
       for (int i = 0; i < n; ++i) xx[i] = pts ? pts[i] : x0[i * S + s];
       HostTraj traj{n, m, S, s, X, U};
-      const int f = pf | lq::simulate_sample<n, m>(pb, pl, N, T, xx, ws, &jt, &act, traj);
+      const int f = pf | lq::simulate_sample<n, m>(pb, pl, N, T, xx, ws, &jt, &act, traj, g_refs);
       if (J_T) J_T[s] = jt;
       if (flags) flags[s] = f;
       if (n_active) n_active[s] = act;
@@ -215,6 +217,13 @@ int hm_mpc(int mode, int n, int m, const double* A, const double* B, const doubl
   HM_FOR_EACH_DIM(X_)
 #undef X_
   return -1;
+}
+
+// references shared by every following hm_mpc call: x_ref (n x ld), u_ref (m x ld) row-major; NULLs clear them
+void hm_set_refs(const double* x_ref, const double* u_ref, int ld) {
+  g_refs.xr = x_ref;
+  g_refs.ur = u_ref;
+  g_refs.ld = ld;
 }
 
 int hm_bounds_fields(void) { return (int)lq::BF_COUNT; }

@@ -177,6 +177,56 @@ def test_random_api_cases(known):
     assert n_raise > 0
 
 
+def test_tracking_references(engine, tracking):
+    """Non-zero x_ref / u_ref (utils_class.py:62-81): drop-in classes vs the untouched reference's answers, a batch
+    through the C ABI vs the oracle's dense QP, and the state really clears (regulation answers come back)."""
+    import torch
+    from oracle import np_oracle as o
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_MPC_Simulator
+    from tests.conftest import tracking_case
+    for c in map(tracking_case, tracking):
+        Ah, Bh = c["A"] + c["dA"], c["B"] + c["dB"]
+        sol = LQ_MPC_Controller(c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["F_u"]).solve(c["x0"], c["x_ref"], c["u_ref"])
+        assert abs(sol["V_N"] - c["V_N"]) < TOL * abs(c["V_N"]) and np.max(np.abs(sol["u_0"] - c["u_0"])) < 1e-10
+        sim = LQ_MPC_Simulator(c["T"], c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["F_u"]).simulate(
+            c["x0"], c["A"], c["B"], c["x_ref"], c["u_ref"])
+        assert abs(sim["J_T"] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"] - c["U"])) < 1e-10 and np.max(np.abs(sim["X"] - c["X"])) < 1e-10
+    rng = np.random.default_rng(5)
+    n, m, N, S = 4, 2, 6, 257
+    A = rng.normal(size=(n, n)); A *= 0.9 / np.max(np.abs(np.linalg.eigvals(A)))
+    B = rng.normal(size=(n, m)); Q = np.eye(n); R = 0.5 * np.eye(m)
+    lo, hi = -0.3 * np.ones(m), 0.3 * np.ones(m)
+    engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+    dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
+    x0 = rng.normal(size=(n, S)) * 0.5
+    base = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+    for xr, ur in ((rng.normal(size=(n, N)) * 0.3, None), (None, rng.normal(size=(m, N)) * 0.2),
+                   (rng.normal(size=(n, N + 3)) * 0.3, rng.normal(size=(m, N + 3)) * 0.2)):
+        with engine.references(xr, ur):
+            got = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+            sim = engine.simulate_batch(dA, dB, N, 5, x0=x0, want=("J_T", "U"))
+        V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
+        J, U = sim["J_T"].cpu().numpy(), sim["U"].cpu().numpy()
+        assert not np.any(fl & ~2)
+        n_act = 0
+        for s in range(0, S, 4):
+            Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+            u_o, V_o, act = o.mpc_solve(N, Ah, Bh, Q, R, Q, lo, hi, x0[:, s], x_ref=xr, u_ref=ur)
+            n_act += int(act)
+            assert abs(V[0, s] - V_o) < TOL * abs(V_o) and np.max(np.abs(u0[0, :, s] - u_o)) < 1e-9
+            assert bool(fl[0, s] & 2) == act
+            if s % 32 == 0:
+                so = o.simulate(5, N, Ah, Bh, Q, R, Q, lo, hi, x0[:, s], A, B, x_ref=xr, u_ref=ur)
+                assert abs(J[s] - so["J_T"]) < TOL * abs(so["J_T"]) and np.max(np.abs(U[:, :, s].T - so["U"])) < 1e-9
+        assert 0 < n_act < len(range(0, S, 4))
+    with pytest.raises(Exception):
+        with engine.references(np.ones((n, N - 1)), None):              # fewer than N columns
+            engine.mpc_solve_batch(dA, dB, N, x0=x0)
+    again = engine.mpc_solve_batch(dA, dB, N, x0=x0)                     # cleared: regulation answers, bit for bit
+    assert torch.equal(again["V"], base["V"]) and torch.equal(again["u0"], base["u0"])
+
+
 def test_clqr_stress_vs_dense_qp(engine):
     """Heavily saturated random problems: batched K2 vs the dense Cholesky+BVLS oracle (per problem: one engine
     problem, 48 initial states)."""

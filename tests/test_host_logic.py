@@ -53,9 +53,6 @@ def test_input_set_constants_and_box_parsing(known):
         rt.box_from_F(np.array([[1.0, 1.0]]))
     with pytest.raises(ValueError):
         U.bar_u_solve(np.array([[10.0]]))                 # unbounded below (Gurobi would report unbounded)
-    with pytest.raises(NotImplementedError):
-        rt.require_zero_refs(np.ones((2, 3)), None)
-    rt.require_zero_refs(np.zeros((2, 3)), np.zeros((1, 3)))
 
 
 def test_circle_generator_vs_reference_answers(known):

@@ -118,6 +118,40 @@ def test_k2_math_mpc_test_and_random_api(known):
         assert np.max(np.abs(sim["U"][:, :, 0].T - np.array(c["U"]))) < 1e-10
 
 
+def test_k2_math_tracking_references(tracking):
+    """The affine (non-zero reference) branch of the exact solver vs the untouched reference's answers, then a batch
+    of random references vs the oracle's dense QP (saturated and unsaturated mixed)."""
+    from tests.conftest import tracking_case
+    for c in map(tracking_case, tracking):
+        n = c["n"]
+        a = (c["A"], c["B"], c["Q"], c["R"], c["Q"], c["lo"], c["hi"], c["dA"].reshape(-1, 1), c["dB"].reshape(-1, 1))
+        sol = hm.mpc(0, *a, c["N"], x0_soa=c["x0"].reshape(n, 1), x_ref=c["x_ref"], u_ref=c["u_ref"])
+        assert abs(sol["V"][0, 0] - c["V_N"]) < TOL * abs(c["V_N"])
+        assert np.max(np.abs(sol["u0"][0, :, 0] - c["u_0"])) < 1e-10
+        sim = hm.mpc(1, *a, c["N"], T=c["T"], x0_soa=c["x0"].reshape(n, 1), x_ref=c["x_ref"], u_ref=c["u_ref"])
+        assert abs(sim["J_T"][0] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"][:, :, 0].T - c["U"])) < 1e-10
+        assert np.max(np.abs(sim["X"][:, :, 0].T - c["X"])) < 1e-10
+    rng = np.random.default_rng(5)
+    n, m, N, S = 4, 2, 6, 64
+    A = rng.normal(size=(n, n)); A *= 0.9 / np.max(np.abs(np.linalg.eigvals(A)))
+    B = rng.normal(size=(n, m)); Q = np.eye(n); R = 0.5 * np.eye(m)
+    lo, hi = -0.3 * np.ones(m), 0.3 * np.ones(m)
+    dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
+    x0 = rng.normal(size=(n, S)) * 0.5
+    for xr, ur in ((rng.normal(size=(n, N)) * 0.3, None), (None, rng.normal(size=(m, N)) * 0.2),
+                   (rng.normal(size=(n, N + 3)) * 0.3, rng.normal(size=(m, N + 3)) * 0.2)):
+        sol = hm.mpc(0, A, B, Q, R, Q, lo, hi, dA, dB, N, x0_soa=x0, x_ref=xr, u_ref=ur)
+        n_act = 0
+        for s in range(S):
+            u0, V, act = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi,
+                                     x0[:, s], x_ref=xr, u_ref=ur)
+            n_act += int(act)
+            assert abs(sol["V"][0, s] - V) < TOL * abs(V) and np.max(np.abs(sol["u0"][0, :, s] - u0)) < 1e-9
+            assert bool(sol["flags"][0, s] & 2) == act
+        assert 0 < n_act < S
+
+
 def _golden_inputs(golden, rows):
     eA = np.ascontiguousarray(golden["error_A_f"][:, :, rows, :]).reshape(4, -1)
     eB = np.ascontiguousarray(golden["error_B_f"][:, :, rows, :]).reshape(2, -1)

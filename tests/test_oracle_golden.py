@@ -127,6 +127,24 @@ def test_oracle_random_api_cases(known):
     assert n_raise > 0
 
 
+def test_oracle_tracking_references(tracking):
+    """Non-zero x_ref / u_ref (utils_class.py:62-81) — 16 solves + closed loops of the untouched reference, saturated
+    and not; the reference window is wider than N (only its first N columns count)."""
+    from tests.conftest import tracking_case
+    n_act = 0
+    for c in map(tracking_case, tracking):
+        Ah, Bh = c["A"] + c["dA"], c["B"] + c["dB"]
+        u0, V, act = o.mpc_solve(c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["lo"], c["hi"], c["x0"],
+                                 x_ref=c["x_ref"], u_ref=c["u_ref"])
+        n_act += int(act)
+        assert abs(V - c["V_N"]) < TOL * abs(c["V_N"]) and np.max(np.abs(u0 - c["u_0"])) < 1e-10
+        sim = o.simulate(c["T"], c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["lo"], c["hi"], c["x0"], c["A"], c["B"],
+                         x_ref=c["x_ref"], u_ref=c["u_ref"])
+        assert abs(sim["J_T"] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"] - c["U"])) < 1e-10 and np.max(np.abs(sim["X"] - c["X"])) < 1e-10
+    assert 0 < n_act < len(tracking)
+
+
 # ------------------------------------------------------------------------------------------- analytic cross-checks
 def test_riccati_equals_condensed_qp_when_unconstrained():
     """utils_class.py:59-91 unconstrained == Riccati: u_0 = K_0 x0, V_N = x0' P_0 x0."""
