@@ -8,14 +8,19 @@
 //     TMA engine (cp.async.bulk + mbarrier complete_tx); A^, P and the n x n temporaries live in shared memory
 //     (leading dimension n+4: the MMA fragment footprints hit the 32 banks with the minimum 2 wavefronts); every
 //     matrix product — n x n x n and the skinny n x 8 ones alike — is a set of warp-level FP64 tensor-core MMAs
-//     (mma.sync m8n8k4.f64 -> DMMA; a DFMA evaluation of the same fragments is kept for A/B timing); the 8 x 8
-//     Cholesky runs on one warp, the triangular solves one row/column per thread. Lyapunov doubling accumulates M'(S M) straight into S from the
-//     GEMM epilogue. Writes J_raw = x0' S x0, V_expert(x0), optional V_N, flags and the closed-loop matrix A_cl.
-//   * k4b `tiled_rho_kernel<n>`: ONE WARP PER SAMPLE: Householder -> Hessenberg and the Francis double-shift QR
-//     iteration run warp-synchronously on a shared-memory copy of A_cl (lane = row or column of the 3-row/3-column
-//     reflector updates), scalars replicated across lanes. Finishes J = +inf / UNSTABLE when rho >= 1 and the ratio.
-// Two kernels because the QR iteration is latency-bound and sequential: as many independent warps per SM as fit
-// hide it, whereas inside k4a it would idle three quarters of every CTA.
+//     (mma.sync m8n8k4.f64 -> DMMA; a DFMA evaluation of the same fragments is kept for A/B timing).
+//     The Riccati step is arranged so that the serial 8 x 8 Cholesky chain runs on ONE warp while the other three keep
+//     the tensor pipe busy:   P+ = Q + A^'P A^ - W W',  W = Z L^-T,  Z = A^'(P B^),  G = R + B^'P B^ = L L'
+//     — only W depends on the factorisation; X = P A^ and T = Q + A^'X (lower blocks, mirrored: P stays exactly
+//     symmetric) do not. The Cholesky is replicated in the registers of every lane of the chain warp (no shuffles,
+//     no shared-memory round trips on the serial stretch); the chain warp rotates with blockIdx so the co-resident
+//     CTAs load all four SM sub-partitions. Lyapunov doubling accumulates M'(S M) straight into S from the GEMM
+//     epilogue. The spectral radius comes from the SAME squarings carried on with exact power-of-two rescaling:
+//     rho = lim ||A_cl^(2^k)||^(1/2^k), 40 squarings, accepted when the k = 34 and k = 40 estimates agree to 5e-10
+//     (then the error is ~1e-11 or better); anything else is left to k4b.
+//   * k4b `tiled_rho_kernel<n>`: ONE WARP PER PENDING SAMPLE: Householder -> Hessenberg and the Francis double-shift
+//     QR iteration run warp-synchronously on a shared-memory copy of A_cl (lane = row or column of the 3-row/3-column
+//     reflector updates), scalars replicated across lanes. Only samples k4a did not accept (LQMPC_K4_RHO=qr: all).
 #include <stdlib.h>
 
 #include "engine.h"
@@ -169,6 +174,9 @@ __device__ __forceinline__ void gemm_nn(const double* __restrict__ A, const doub
 }
 
 // ------------------------------------------------------------------------------------------------ k4a
+constexpr int kRhoK1 = 34, kRhoK2 = 40;          // squarings behind the two spectral-radius estimates
+constexpr int kFlagRhoPending = 1 << 30;          // internal: k4b still owes this entry its QR iteration
+
 struct TiledArgs {
   int64_t S;
   const double* dA;      // [S][n*n]  (array of matrices: one sample contiguous)
@@ -176,12 +184,16 @@ struct TiledArgs {
   const double* x0;      // [S][n]
   const double* pb;      // device: A | B | Q | R | Pt | Pexp
   int N_min, N_max;
-  double* Jraw;          // [H][S]
+  double* Jraw;          // [H][S]   scratch: x0' S x0 of the entries left to k4b
   double* vexp;          // [S]
   double* Vn;            // [H][S] or NULL
   int32_t* flags;        // [H][S]
-  double* Acl;           // [H][S][n*n]
+  double* Acl;           // [H][S][n*n]  closed-loop matrices of the entries left to k4b
   double* Pout;          // [n*n] or NULL: final cost-to-go of sample 0 (problem preparation: the expert matrix)
+  double* J;             // [H][S] outputs finished here when the squaring estimate is accepted (any may be NULL)
+  double* rho;
+  double* ratio;
+  int rho_qr;            // 1: leave every spectral radius to k4b
 };
 
 template <int n, int m>
@@ -193,37 +205,57 @@ struct PbOff {
 template <int n, int m>
 struct K4Smem {
   static constexpr int LD = n + 4, NN = n * LD, LS = 12, M8 = 8;
-  static constexpr int oBh = 0, oPB = oBh + n * LS, oY = oPB + n * LS, oKg = oY + n * LS, oRK = oKg + M8 * LD,
-                       oG = oRK + M8 * LD, oRs = oG + M8 * LS, oLi = oRs + M8 * LS, oxs = oLi + M8, ored = oxs + n,
-                       obar = ored + 2 * (kT / 32), total = obar + 2;
+  static constexpr int oBh = 0, oPB = oBh + n * LS, oZ = oPB + n * LS, oKg = oZ + n * LS, oRK = oKg + M8 * LD,
+                       oG = oRK + M8 * LD, oRs = oG + M8 * LS, oxs = oRs + M8 * LS, ored = oxs + n,
+                       obar = ored + 4 * (kT / 32), total = obar + 2;
   static_assert(M8 * LD >= n * m, "dB lands dense in the RK area");
-  static_assert((oxs % 2) == 0 && (oRK % 2) == 0, "TMA destinations must be 16-byte aligned");
+  static_assert((oxs % 2) == 0 && (oRK % 2) == 0 && (oG % 2) == 0, "TMA destinations / 16-byte loads must be aligned");
 };
 
-template <int n, int m, bool DM>
-__global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const int nbig) {
+// 1/sqrt(x) for normal x > 0: hardware seed (MUFU.RSQ64H) + two Newton steps, no slow path (callers flag x <= 0).
+__device__ __forceinline__ double fast_rsqrt(double x) {
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double h = 0.5 * x;
+  double e = fma(-h * y, y, 0.5);
+  y = fma(y, e, y);
+  e = fma(-h * y, y, 0.5);
+  return fma(y, e, y);
+}
+
+// named barrier 1: the three worker warps signal "Z is in shared memory", the chain warp waits for it
+__device__ __forceinline__ void z_ready_arrive() {
+  __threadfence_block();
+  asm volatile("bar.arrive 1, %0;" ::"r"(kT) : "memory");
+}
+__device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"r"(kT) : "memory"); }
+
+// MB = CTAs per SM the register allocation is held to (5 -> <= 102 registers; shared memory fits 5 single-horizon CTAs)
+template <int n, int m, bool DM, int MB>
+__global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, const int nbig) {
   using L = K4Smem<n, m>;
   using O = PbOff<n, m>;
-  constexpr int LD = L::LD, NN = L::NN, LS = L::LS, M8 = L::M8, NW = n / 8;
+  constexpr int LD = L::LD, NN = L::NN, LS = L::LS, M8 = L::M8, NW = n / 8, T = n / 16, HB = n / 2;
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sm = reinterpret_cast<double*>(smem_raw);
   double* big[5];
   for (int i = 0; i < 5; ++i) big[i] = sm + (i < nbig ? i : nbig - 1) * NN;
   double* sk = sm + nbig * NN;
   double* Bh = sk + L::oBh;             // n x 8 (ld 12), columns >= m are zero
-  double* PB = sk + L::oPB;             // n x 8
-  double* Y = sk + L::oY;               // n x 8
+  double* PB = sk + L::oPB;             // n x 8: P B^, later W = Z L^-T
+  double* Z = sk + L::oZ;               // n x 8: A^' (P B^)
   double* Kg = sk + L::oKg;             // 8 x n (ld LD), rows >= m are zero
-  double* RK = sk + L::oRK;             // 8 x n; also the TMA landing zone of dB and the Y'A^ temporary
-  double* G = sk + L::oG;               // 8 x 8 (ld 12): Cholesky factor in the lower triangle
+  double* RK = sk + L::oRK;             // 8 x n; also the TMA landing zone of dB
+  double* G = sk + L::oG;               // 8 x 8 (ld 12)
   double* Rs = sk + L::oRs;             // 8 x 8 (ld 12): R padded with the identity
-  double* Li = sk + L::oLi;             // reciprocals of diag(L)
   double* xs = sk + L::oxs;             // n
-  double* red = sk + L::ored;
+  double* red = sk + L::ored;           // 4 * (kT/32): two slots for block_sum/block_max2, two for the squarings
   uint64_t* bar = reinterpret_cast<uint64_t*>(sk + L::obar);
   int* cflag = reinterpret_cast<int*>(bar + 1);
 
-  const int tid = threadIdx.x, w = tid >> 5;
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int cw = blockIdx.x & 3;                       // chain warp of this CTA (rotates over the SM sub-partitions)
+  const int widx = (w - cw - 1) & 3;                   // 0..2 for the workers, 3 for the chain warp
   const bool nested = (a.N_min != a.N_max);
   double* Ah = big[0];
   double* P = big[1];
@@ -278,101 +310,115 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
     if (tid == 0 && a.vexp) a.vexp[s] = ve;
 
     for (int k = 1; k <= a.N_max; ++k) {
-      // ---- P B^  (n x 8): warp w < n/8 owns row tile w
+      const bool emit = (k >= a.N_min);
+      const bool advance = (k < a.N_max || a.Vn || a.Pout);       // the cost-to-go of this step is still needed
+      // ---- phase A (all warps): P B^ (n x 8; warp w < n/8 owns row tile w) and X = P A^ (quadrants)
       if (w < NW) {
         double c[1][1][2];
         warp_mma<1, 1, DM>(n, 8 * w, 0, [&](int i, int q) { return P[i * LD + q]; },
                            [&](int q, int j) { return Bh[q * LS + j]; }, c);
         warp_mma_store<1, 1>(8 * w, 0, c, [&](int i, int j, double v) { PB[i * LS + j] = v; });
       }
+      if (advance) gemm_nn<n, false, DM>(P, Ah, [&](int i, int j, double v) { X[i * LD + j] = v; });
       __syncthreads();
-      // ---- warp 0: G = R + B^' (P B^) (8 x 8), then its Cholesky G = L L' (lane i owns row i of the trailing update)
-      if (w == 0) {
-        double c[1][1][2];
-        warp_mma<1, 1, DM>(n, 0, 0, [&](int i, int q) { return Bh[q * LS + i]; },
-                           [&](int q, int j) { return PB[q * LS + j]; }, c);
-        warp_mma_store<1, 1>(0, 0, c, [&](int i, int j, double v) { G[i * LS + j] = Rs[i * LS + j] + v; });
+      // ---- phase B: the chain warp factorises G while the workers form Z and the part of P+ that does not need it
+      if (w == cw) {
+        {
+          double c[1][1][2];
+          warp_mma<1, 1, DM>(n, 0, 0, [&](int i, int q) { return Bh[q * LS + i]; },
+                             [&](int q, int j) { return PB[q * LS + j]; }, c);
+          warp_mma_store<1, 1>(0, 0, c, [&](int i, int j, double v) { G[i * LS + j] = Rs[i * LS + j] + v; });
+        }
         __syncwarp();
-        // Cholesky in registers: lane i (< 8) holds row i of G; column j is broadcast with shuffles (no shared-memory
-        // round trips on this serial stretch of the step — it was 42 % of the stall samples of the first version).
-        const int i = tid & 7;                            // lanes >= 8 mirror rows 0..7 (keeps the shuffles uniform)
-        double grow[M8];
+        // Cholesky G = L L' replicated in the registers of every lane (broadcast loads; fully unrolled, no shuffles):
+        // lo[i][j] holds L(i, j) for i > j, the reciprocal of the diagonal sits in li[].
+        double lo[M8][M8], li[M8];
 #pragma unroll
-        for (int j = 0; j < M8; ++j) grow[j] = G[i * LS + j];
+        for (int i = 0; i < M8; ++i) {
+#pragma unroll
+          for (int j = 0; j <= i; j += 2) {
+            const double2 v2 = *reinterpret_cast<const double2*>(G + i * LS + j);
+            lo[i][j] = v2.x;
+            if (j + 1 <= i) lo[i][j + 1] = v2.y;
+          }
+        }
         bool bad = false;
 #pragma unroll
         for (int j = 0; j < M8; ++j) {
-          const double d = __shfl_sync(0xffffffffu, grow[j], j);
+          const double d = lo[j][j];
           bad = bad || !(d > 0.0);
-          const double inv = rsqrt(d);
-          const double lij = (i == j) ? d * inv : grow[j] * inv;    // L(i, j) for i >= j
-          grow[j] = lij;
-          if (tid == j) Li[j] = inv;
+          const double inv = fast_rsqrt(d);
+          li[j] = inv;
 #pragma unroll
-          for (int cc = j + 1; cc < M8; ++cc) {
-            const double lcj = __shfl_sync(0xffffffffu, lij, cc);
-            if (i >= cc) grow[cc] = fma(-lij, lcj, grow[cc]);
+          for (int i = j + 1; i < M8; ++i) lo[i][j] *= inv;
+#pragma unroll
+          for (int i = j + 1; i < M8; ++i)
+#pragma unroll
+            for (int cc = j + 1; cc <= i; ++cc) lo[i][cc] = fma(-lo[i][j], lo[cc][j], lo[i][cc]);
+        }
+        if (bad && lane == 0) atomicOr(cflag, (int)lq::FLAG_CHOL_FAIL);
+        z_ready_wait();
+        // W = Z L^-T, one row per lane; at an emitting step the gain K = -L^-T W' follows, one column per lane
+        if (lane < n) {
+          double wv[M8];
+#pragma unroll
+          for (int j = 0; j < M8; j += 2) {
+            const double2 v2 = *reinterpret_cast<const double2*>(Z + lane * LS + j);
+            wv[j] = v2.x; wv[j + 1] = v2.y;
+          }
+#pragma unroll
+          for (int j = 0; j < M8; ++j) {
+            double sacc = wv[j];
+#pragma unroll
+            for (int cc = 0; cc < j; ++cc) sacc = fma(-wv[cc], lo[j][cc], sacc);
+            wv[j] = sacc * li[j];
+          }
+#pragma unroll
+          for (int j = 0; j < M8; j += 2)
+            *reinterpret_cast<double2*>(PB + lane * LS + j) = make_double2(wv[j], wv[j + 1]);
+          if (emit) {
+#pragma unroll
+            for (int i = M8 - 1; i >= 0; --i) {
+              double sacc = wv[i];
+#pragma unroll
+              for (int cc = i + 1; cc < M8; ++cc) sacc = fma(-lo[cc][i], wv[cc], sacc);
+              wv[i] = sacc * li[i];
+              Kg[i * LD + lane] = -wv[i];
+            }
           }
         }
-        if (bad && tid == 0) atomicOr(cflag, (int)lq::FLAG_CHOL_FAIL);
-        if (tid < M8) {
-#pragma unroll
-          for (int j = 0; j < M8; ++j) G[i * LS + j] = grow[j];     // lower triangle = L (upper entries unused)
-        }
-      }
-      __syncthreads();
-      // ---- Y = (P B^) L^-T : one thread per row
-      if (tid < n) {
-        double y[M8];
-#pragma unroll
-        for (int j = 0; j < M8; ++j) {
-          double sacc = PB[tid * LS + j];
-#pragma unroll
-          for (int cc = 0; cc < j; ++cc) sacc = fma(-y[cc], G[j * LS + cc], sacc);
-          y[j] = sacc * Li[j];
-        }
-#pragma unroll
-        for (int j = 0; j < M8; ++j) Y[tid * LS + j] = y[j];
-      }
-      __syncthreads();
-      const bool emit = (k >= a.N_min);
-      // ---- gain of horizon k: K = -L^-T (Y' A^)   (8 x n): warp w < n/8 owns column tile w, then a column per thread
-      if (emit) {
-        if (w < NW) {
+      } else {
+        // Z = A^' (P B^): row tiles over the workers
+        for (int t = widx; t < NW; t += 3) {
           double c[1][1][2];
-          warp_mma<1, 1, DM>(n, 0, 8 * w, [&](int i, int q) { return Y[q * LS + i]; },
-                             [&](int q, int j) { return Ah[q * LD + j]; }, c);
-          warp_mma_store<1, 1>(0, 8 * w, c, [&](int i, int j, double v) { RK[i * LD + j] = v; });
+          warp_mma<1, 1, DM>(n, 8 * t, 0, [&](int i, int q) { return Ah[q * LD + i]; },
+                             [&](int q, int j) { return PB[q * LS + j]; }, c);
+          warp_mma_store<1, 1>(8 * t, 0, c, [&](int i, int j, double v) { Z[i * LS + j] = v; });
         }
-        __syncthreads();
-        if (tid < n) {
-          double z[M8];
-#pragma unroll
-          for (int i = M8 - 1; i >= 0; --i) {
-            double sacc = RK[i * LD + tid];
-#pragma unroll
-            for (int cc = i + 1; cc < M8; ++cc) sacc = fma(-G[cc * LS + i], z[cc], sacc);
-            z[i] = sacc * Li[i];
-          }
-#pragma unroll
-          for (int i = 0; i < M8; ++i) Kg[i * LD + tid] = -z[i];
+        z_ready_arrive();
+        // T = Q + A^' X: the three lower (n/2)-blocks, one per worker, mirrored into the upper triangle
+        if (advance) {
+          const int bi = (widx + 1) >> 1, bj = widx >> 1;            // (0,0), (1,0), (1,1)
+          double c[T][T][2];
+          warp_mma<T, T, DM>(n, bi * HB, bj * HB, [&](int i, int q) { return Ah[q * LD + i]; },
+                             [&](int q, int j) { return X[q * LD + j]; }, c);
+          warp_mma_store<T, T>(bi * HB, bj * HB, c, [&](int i, int j, double v) {
+            if (i >= j) {
+              const double t = __ldg(gQ + i * n + j) + v;
+              P[i * LD + j] = t;
+              P[j * LD + i] = t;
+            }
+          });
         }
-      }
-      // ---- P <- P - Y Y'
-      {
-        constexpr int T = n / 16;
-        const int r0 = (w >> 1) * (n / 2), c0 = (w & 1) * (n / 2);
-        double c[T][T][2];
-        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return Y[i * LS + q]; },
-                           [&](int q, int j) { return Y[j * LS + q]; }, c);
-        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { P[i * LD + j] -= v; });
       }
       __syncthreads();
-      if (k < a.N_max || a.Vn || a.Pout) {
-        // ---- X = M A^ ; P+ = Q + A^' X
-        gemm_nn<n, false, DM>(P, Ah, [&](int i, int j, double v) { X[i * LD + j] = v; });
-        __syncthreads();
-        gemm_nn<n, true, DM>(Ah, X, [&](int i, int j, double v) { P[i * LD + j] = __ldg(gQ + i * n + j) + v; });
+      // ---- phase D (all warps): P+ = T - W W'
+      if (advance) {
+        const int r0 = (w >> 1) * HB, c0 = (w & 1) * HB;
+        double c[T][T][2];
+        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return PB[i * LS + q]; },
+                           [&](int q, int j) { return PB[j * LS + q]; }, c);
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { P[i * LD + j] -= v; });
         __syncthreads();
         if (a.Pout && s == 0 && k == a.N_max) {            // problem preparation: the horizon-N cost-to-go itself
           for (int e = tid; e < n * n; e += kT) a.Pout[e] = P[(e / n) * LD + e % n];
@@ -387,7 +433,7 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
         vn = block_sum(vn, red);
         if (tid == 0) a.Vn[o] = vn;
       }
-      // ---- closed loop on the TRUE plant: R K (8 x n), then A_cl = A + B K -> Mb (and global), W = Q + K' R K -> Sb
+      // ---- closed loop on the TRUE plant: R K (8 x n), then A_cl = A + B K -> Mb, W = Q + K' R K -> Sb
       if (w < NW) {
         double c[1][1][2];
         warp_mma<1, 1, DM>(M8, 0, 8 * w, [&](int i, int q) { return Rs[i * LS + q]; },
@@ -396,24 +442,18 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
       }
       __syncthreads();
       {
-        constexpr int T = n / 16;
-        const int r0 = (w >> 1) * (n / 2), c0 = (w & 1) * (n / 2);
+        const int r0 = (w >> 1) * HB, c0 = (w & 1) * HB;
         double c[T][T][2];
         warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return (q < m) ? __ldg(gB + i * m + q) : 0.0; },
                            [&](int q, int j) { return Kg[q * LD + j]; }, c);
-        double* gout = a.Acl + o * (int64_t)(n * n);
-        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) {
-          const double acl = __ldg(gA + i * n + j) + v;
-          Mb[i * LD + j] = acl;
-          gout[i * n + j] = acl;
-        });
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { Mb[i * LD + j] = __ldg(gA + i * n + j) + v; });
         warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return Kg[q * LD + i]; },
                            [&](int q, int j) { return RK[q * LD + j]; }, c);
         warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { Sb[i * LD + j] = __ldg(gQ + i * n + j) + v; });
       }
       __syncthreads();
       // ---- Lyapunov squared doubling: S += M' (S M), M <- M^2
-      int lflag = lq::FLAG_LYAP_NOCONV;
+      int lflag = lq::FLAG_LYAP_NOCONV, nsq = 64;
       double* Mc = Mb;
       double* Xc = X;
       for (int it = 0; it < 64; ++it) {
@@ -429,9 +469,10 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
         block_max2(tmax, smax, red);                       // (contains the barriers ordering Sb / Xc reuse)
         if (!(tmax > 1e-18 * smax)) {
           lflag = (tmax == tmax && smax == smax) ? 0 : (int)lq::FLAG_NONFINITE;
+          nsq = it;
           break;
         }
-        if (!(smax < 1e300)) { lflag = lq::FLAG_NONFINITE; break; }   // diverging (unstable loop): k4b decides
+        if (!(smax < 1e300)) { lflag = lq::FLAG_NONFINITE; nsq = it; break; }   // diverging (unstable loop)
         gemm_nn<n, false, DM>(Mc, Mc, [&](int i, int j, double v) { Xc[i * LD + j] = v; });
         __syncthreads();
         double* t = Mc; Mc = Xc; Xc = t;
@@ -439,9 +480,84 @@ __global__ void __launch_bounds__(kT) tiled_eval_kernel(const TiledArgs a, const
       double J = 0.0;
       for (int e = tid; e < n * n; e += kT) J = fma(xs[e / n] * Sb[(e / n) * LD + e % n], xs[e % n], J);
       J = block_sum(J, red);
-      if (tid == 0) {
-        a.Jraw[o] = J;
-        a.flags[o] = lflag | *cflag;
+      // ---- spectral radius: keep squaring M = A_cl^(2^nsq) with exact power-of-two rescaling,
+      //      log2 rho ~ sum_j 2^-j e_j + 2^-k log2 max|N_k|  (N_k the stored, rescaled power; e_j its exponent)
+      double rho = 0.0;
+      bool accepted = false;
+      if (!a.rho_qr && nsq < kRhoK1) {
+        double mx = 0.0, dummy = 0.0;
+        int badv = 0;
+        for (int e = tid; e < n * n; e += kT) {
+          const double v = fabs(Mc[(e / n) * LD + e % n]);
+          mx = fmax(mx, v);
+          badv |= !(v <= 1.79e308);
+        }
+        block_max2(mx, dummy, red);
+        double lacc = 0.0, wgt = __hiloint2double((1023 - nsq) << 20, 0), est1 = 0.0;
+        bool fail = __syncthreads_or(badv) != 0, zero = false;
+        double* rq = red + 2 * (kT / 32);
+        int kk = nsq;
+        for (; kk < kRhoK2 && !fail; ++kk) {
+          if (kk == kRhoK1) est1 = fma(lacc, 0.6931471805599453, wgt * log(mx));
+          if (!(mx > 0.0)) { zero = true; break; }           // a vanishing power: nilpotent, rho = 0
+          const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+          if (e < -500 || e > 500) { fail = true; break; }
+          const double s2 = __hiloint2double((1023 - 2 * e) << 20, 0);
+          double lm = 0.0;
+          gemm_nn<n, false, DM>(Mc, Mc, [&](int i, int j, double v) {
+            const double sv = v * s2;
+            Xc[i * LD + j] = sv;
+            lm = fmax(lm, fabs(sv));
+            badv |= !(fabs(sv) <= 1.79e308);
+          });
+          lacc = fma(wgt, (double)e, lacc);
+          wgt *= 0.5;
+          lm = warp_max(lm);
+          double* slot = rq + (kk & 1) * (kT / 32);
+          if (lane == 0) slot[w] = lm;
+          if (__syncthreads_or(badv)) { fail = true; break; }
+          mx = slot[0];
+#pragma unroll
+          for (int q = 1; q < kT / 32; ++q) mx = fmax(mx, slot[q]);
+          double* t = Mc; Mc = Xc; Xc = t;
+        }
+        if (!fail) {
+          if (zero) {
+            accepted = true;
+          } else {
+            const double est2 = fma(lacc, 0.6931471805599453, wgt * log(mx));
+            rho = exp(est2);
+            accepted = fabs(rho - exp(est1)) <= 5e-10 * rho;
+          }
+        }
+      }
+      if (accepted) {
+        if (tid == 0) {
+          int fl = lflag | *cflag;
+          double Jo = J;
+          if (!(rho < 1.0)) {
+            fl = (fl & ~(lq::FLAG_LYAP_NOCONV | lq::FLAG_NONFINITE)) | lq::FLAG_UNSTABLE;
+            Jo = HUGE_VAL;
+          } else if (!(fabs(Jo) <= 1.79e308)) {
+            fl |= lq::FLAG_NONFINITE;
+          }
+          if (a.J) a.J[o] = Jo;
+          if (a.rho) a.rho[o] = rho;
+          if (a.ratio) a.ratio[o] = Jo / ve;
+          a.flags[o] = fl;
+        }
+      } else {
+        // left to k4b: hand over A_cl = A + B K (rebuilt from the gain, the doubling consumed the shared-memory copy)
+        const int r0 = (w >> 1) * HB, c0 = (w & 1) * HB;
+        double c[T][T][2];
+        warp_mma<T, T, DM>(M8, r0, c0, [&](int i, int q) { return (q < m) ? __ldg(gB + i * m + q) : 0.0; },
+                           [&](int q, int j) { return Kg[q * LD + j]; }, c);
+        double* gout = a.Acl + o * (int64_t)(n * n);
+        warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { gout[i * n + j] = __ldg(gA + i * n + j) + v; });
+        if (tid == 0) {
+          a.Jraw[o] = J;
+          a.flags[o] = lflag | *cflag | kFlagRhoPending;
+        }
       }
       __syncthreads();
     }
@@ -642,6 +758,7 @@ __global__ void __launch_bounds__(kT) tiled_rho_kernel(const RhoArgs a) {
   double* v = am + n * LDA;
   const int64_t wid = (int64_t)blockIdx.x * (kT / 32) + wib, nw = (int64_t)gridDim.x * (kT / 32);
   for (int64_t e = wid; e < a.total; e += nw) {
+    if (!(a.flags[e] & kFlagRhoPending)) continue;          // k4a finished this entry (warp-uniform)
     const double* src = a.Acl + e * (int64_t)(n * n);
     for (int q = lane; q < n * n; q += 32) am[(q / n) * LDA + q % n] = src[q];
     __syncwarp();
@@ -649,7 +766,7 @@ __global__ void __launch_bounds__(kT) tiled_rho_kernel(const RhoArgs a) {
     const double rho = warp_spectral_radius<n>(am, v, &ok);
     __syncwarp();
     if (lane == 0) {
-      int fl = a.flags[e];
+      int fl = a.flags[e] & ~kFlagRhoPending;
       if (!ok) fl |= lq::FLAG_EIG_NOCONV;
       double J = a.Jraw[e];
       if (!(rho < 1.0)) {
@@ -680,18 +797,29 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
   const size_t smem = k4a_smem_bytes<n, m>(nbig);
   // FP64 tensor-core variant of the n x n x n products (n = 32): default decided by measurement;
   // LQMPC_K4_DMMA=0/1 overrides it for A/B runs.
+  // spectral radius: repeated squaring inside k4a with the QR kernel as fallback (default), LQMPC_K4_RHO=qr: QR for all
+  const char* rhov = getenv("LQMPC_K4_RHO");
+  const int rho_qr = (rhov && rhov[0] == 'q') ? 1 : 0;
+  auto r_J = [](const TiledEval& tt, int64_t s0) { return tt.J ? tt.J + s0 : nullptr; };
+  auto r_rho = [](const TiledEval& tt, int64_t s0) { return tt.rho ? tt.rho + s0 : nullptr; };
+  auto r_ratio = [](const TiledEval& tt, int64_t s0) { return tt.ratio ? tt.ratio + s0 : nullptr; };
   const char* dmv = getenv("LQMPC_K4_DMMA");
   const bool use_dmma = dmv ? atoi(dmv) != 0 : LQ_K4_DMMA_DEFAULT;
-  auto kern = use_dmma ? tiled_eval_kernel<n, m, true> : tiled_eval_kernel<n, m, false>;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[H > 1]) {
-    cudaFuncSetAttribute(tiled_eval_kernel<n, m, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)k4a_smem_bytes<n, m>(5));
-    cudaFuncSetAttribute(tiled_eval_kernel<n, m, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                         (int)k4a_smem_bytes<n, m>(5));
+  // register budget: 5 CTAs/SM (<= 102 registers, what the single-horizon shared-memory plan admits) unless
+  // LQMPC_K4_OCC=4 asks for the 128-register build
+  const char* occv = getenv("LQMPC_K4_OCC");
+  const bool occ5 = occv ? atoi(occv) >= 5 : true;
+  using KernT = void (*)(const TiledArgs, const int);
+  KernT kerns[4] = {tiled_eval_kernel<n, m, false, 4>, tiled_eval_kernel<n, m, true, 4>,
+                    tiled_eval_kernel<n, m, false, 5>, tiled_eval_kernel<n, m, true, 5>};
+  KernT kern = kerns[(occ5 ? 2 : 0) + (use_dmma ? 1 : 0)];
+  static bool attr_done = false;
+  if (!attr_done) {
+    for (KernT kf : kerns)
+      cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes<n, m>(5));
     cudaFuncSetAttribute(tiled_rho_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((kT / 32) * (n * (n + 1) + 32) * sizeof(double)));
-    attr_done[H > 1] = true;
+    attr_done = true;
   }
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT, smem);
@@ -720,6 +848,8 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
     a.N_min = t.N_min; a.N_max = t.N_max;
     a.Jraw = jraw; a.vexp = vexp; a.Vn = t.Vn ? t.Vn + s0 : nullptr; a.flags = t.flags ? t.flags + s0 : fscratch; a.Acl = acl;
     a.Pout = t.Pout;
+    a.J = r_J(t, s0); a.rho = r_rho(t, s0); a.ratio = r_ratio(t, s0);
+    a.rho_qr = rho_qr;
     int64_t blocks = (int64_t)sms * per_sm;
     if (blocks > cs) blocks = cs;
     kern<<<(unsigned)blocks, kT, smem, ctx->stream>>>(a, nbig);

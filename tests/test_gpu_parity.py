@@ -196,7 +196,7 @@ def test_tracking_references(engine, tracking):
     n, m, N, S = 4, 2, 6, 257
     A = rng.normal(size=(n, n)); A *= 0.9 / np.max(np.abs(np.linalg.eigvals(A)))
     B = rng.normal(size=(n, m)); Q = np.eye(n); R = 0.5 * np.eye(m)
-    lo, hi = -0.3 * np.ones(m), 0.3 * np.ones(m)
+    lo, hi = -0.55 * np.ones(m), 0.55 * np.ones(m)
     engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
     dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
     x0 = rng.normal(size=(n, S)) * 0.5
@@ -647,6 +647,6 @@ def test_errors_are_loud(engine):
     with pytest.raises(NotImplementedError):
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
                           np.array([[1.0, 1.0]])).solve(np.ones(2), None, None)     # non-box F_u (m = 2 row)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(EngineError):                                                  # reference window shorter than N
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
-                          np.array([[10.0], [-10.0]])).solve(np.ones(2), np.ones((2, 3)), np.zeros((1, 3)))
+                          np.array([[10.0], [-10.0]])).solve(np.ones(2), np.ones((2, 2)), np.zeros((1, 2)))
