@@ -13,14 +13,14 @@
 //     the tensor pipe busy:   P+ = Q + A^'P A^ - W W',  W = Z L^-T,  Z = A^'(P B^),  G = R + B^'P B^ = L L'
 //     — only W depends on the factorisation; X = P A^ and T = Q + A^'X (lower blocks, mirrored: P stays exactly
 //     symmetric) do not. The Cholesky is replicated in the registers of every lane of the chain warp (no shuffles,
-//     no shared-memory round trips on the serial stretch); the chain warp rotates with blockIdx so the co-resident
-//     CTAs load all four SM sub-partitions. Lyapunov doubling accumulates M'(S M) straight into S from the GEMM
+//     no shared-memory round trips on the serial stretch). Lyapunov doubling accumulates M'(S M) straight into S from the GEMM
 //     epilogue. The spectral radius comes from the SAME squarings carried on with exact power-of-two rescaling:
 //     rho = lim ||A_cl^(2^k)||^(1/2^k), 40 squarings, accepted when the k = 34 and k = 40 estimates agree to 5e-10
 //     (then the error is ~1e-11 or better); anything else is left to k4b.
 //   * k4b `tiled_rho_kernel<n>`: ONE WARP PER PENDING SAMPLE: Householder -> Hessenberg and the Francis double-shift
 //     QR iteration run warp-synchronously on a shared-memory copy of A_cl (lane = row or column of the 3-row/3-column
 //     reflector updates), scalars replicated across lanes. Only samples k4a did not accept (LQMPC_K4_RHO=qr: all).
+#include <stdio.h>
 #include <stdlib.h>
 
 #include "engine.h"
@@ -92,6 +92,26 @@ __device__ __forceinline__ void block_max2(double& a, double& b, double* red) {
   double ta = red[0], tb = red[kT / 32];
 #pragma unroll
   for (int w = 1; w < kT / 32; ++w) { ta = fmax(ta, red[w]); tb = fmax(tb, red[kT / 32 + w]); }
+  a = ta; b = tb;
+}
+
+// Magnitude reductions on the INTEGER path: for finite doubles the order of |v| is the order of the sign-stripped bit
+// pattern, its high word alone fixes the binary exponent (all the rescaling and the convergence tests need), and a NaN
+// or Inf sorts above every finite value, so it surfaces in the maximum. One redux.sync per warp, one barrier per block
+// — an FP64 fmax/shuffle chain here would queue behind the other CTAs' tensor-core MMAs on the shared FP64 pipe
+// (profile r01k4d: 20 % of k4a's stall samples sat in that chain).
+__device__ __forceinline__ unsigned hi_abs(double v) { return (unsigned)__double2hiint(v) & 0x7fffffffu; }
+__device__ __forceinline__ double from_hi(unsigned h) { return __hiloint2double((int)h, 0); }
+__device__ __forceinline__ bool hi_nonfinite(unsigned h) { return (h >> 20) == 0x7ffu; }
+// `slot`: 2 * kT/32 unsigned, not touched by a reduction less than one barrier old (callers alternate two groups)
+__device__ __forceinline__ void block_max2_u32(unsigned& a, unsigned& b, unsigned* slot) {
+  a = __reduce_max_sync(0xffffffffu, a);
+  b = __reduce_max_sync(0xffffffffu, b);
+  if ((threadIdx.x & 31) == 0) { slot[threadIdx.x >> 5] = a; slot[kT / 32 + (threadIdx.x >> 5)] = b; }
+  __syncthreads();
+  unsigned ta = slot[0], tb = slot[kT / 32];
+#pragma unroll
+  for (int w = 1; w < kT / 32; ++w) { ta = max(ta, slot[w]); tb = max(tb, slot[kT / 32 + w]); }
   a = ta; b = tb;
 }
 
@@ -231,6 +251,15 @@ __device__ __forceinline__ void z_ready_arrive() {
 __device__ __forceinline__ void z_ready_wait() { asm volatile("bar.sync 1, %0;" ::"r"(kT) : "memory"); }
 
 // MB = CTAs per SM the register allocation is held to (5 -> <= 102 registers; shared memory fits 5 single-horizon CTAs)
+#ifdef LQ_K4_PROFILE
+// development build only: cycles per warp and phase (0 stage, 1 phase A, 2 phase B, 3 phase D, 4 closed loop,
+// 5 Lyapunov, 6 squarings, 7 hand-over / finish), accumulated in shared memory and added to a global table at exit
+#define K4_PROF(idx) do { if (lane == 0) { const long long t_ = clock64(); sprof[w * 8 + (idx)] += t_ - tlast; tlast = t_; } } while (0)
+__device__ unsigned long long g_k4_prof[4 * 8];
+#else
+#define K4_PROF(idx) do { } while (0)
+#endif
+
 template <int n, int m, bool DM, int MB>
 __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, const int nbig) {
   using L = K4Smem<n, m>;
@@ -254,7 +283,12 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
   int* cflag = reinterpret_cast<int*>(bar + 1);
 
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
-  const int cw = blockIdx.x & 3;                       // chain warp of this CTA (rotates over the SM sub-partitions)
+#ifdef LQ_K4_PROFILE
+  __shared__ unsigned long long sprof[4 * 8];
+  if (tid < 32) sprof[tid] = 0;
+  long long tlast = clock64();
+#endif
+  const int cw = blockIdx.x & 3;                       // chain warp of this CTA
   const int widx = (w - cw - 1) & 3;                   // 0..2 for the workers, 3 for the chain warp
   const bool nested = (a.N_min != a.N_max);
   double* Ah = big[0];
@@ -309,6 +343,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
     ve = block_sum(ve, red);
     if (tid == 0 && a.vexp) a.vexp[s] = ve;
 
+    K4_PROF(0);
     for (int k = 1; k <= a.N_max; ++k) {
       const bool emit = (k >= a.N_min);
       const bool advance = (k < a.N_max || a.Vn || a.Pout);       // the cost-to-go of this step is still needed
@@ -321,6 +356,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
       }
       if (advance) gemm_nn<n, false, DM>(P, Ah, [&](int i, int j, double v) { X[i * LD + j] = v; });
       __syncthreads();
+      K4_PROF(1);
       // ---- phase B: the chain warp factorises G while the workers form Z and the part of P+ that does not need it
       if (w == cw) {
         {
@@ -411,6 +447,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           });
         }
       }
+      K4_PROF(2);
       __syncthreads();
       // ---- phase D (all warps): P+ = T - W W'
       if (advance) {
@@ -424,6 +461,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           for (int e = tid; e < n * n; e += kT) a.Pout[e] = P[(e / n) * LD + e % n];
         }
       }
+      K4_PROF(3);
       if (!emit) continue;
       const int h = k - a.N_min;
       const int64_t o = (int64_t)h * a.S + s;
@@ -452,26 +490,27 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
         warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) { Sb[i * LD + j] = __ldg(gQ + i * n + j) + v; });
       }
       __syncthreads();
+      K4_PROF(4);
       // ---- Lyapunov squared doubling: S += M' (S M), M <- M^2
       int lflag = lq::FLAG_LYAP_NOCONV, nsq = 64;
       double* Mc = Mb;
       double* Xc = X;
+      unsigned* ru = reinterpret_cast<unsigned*>(red + 2 * (kT / 32));     // two groups of 2 * kT/32 unsigned
+      int rp = 0;
       for (int it = 0; it < 64; ++it) {
         gemm_nn<n, false, DM>(Sb, Mc, [&](int i, int j, double v) { Xc[i * LD + j] = v; });
         __syncthreads();
-        double tmax = 0.0, smax = 0.0;
+        unsigned thi = 0, shi = 0;
         gemm_nn<n, true, DM>(Mc, Xc, [&](int i, int j, double v) {
           const double nv = Sb[i * LD + j] + v;
           Sb[i * LD + j] = nv;
-          tmax = fmax(tmax, fabs(v));
-          smax = fmax(smax, fabs(nv));
+          thi = max(thi, hi_abs(v));
+          shi = max(shi, hi_abs(nv));
         });
-        block_max2(tmax, smax, red);                       // (contains the barriers ordering Sb / Xc reuse)
-        if (!(tmax > 1e-18 * smax)) {
-          lflag = (tmax == tmax && smax == smax) ? 0 : (int)lq::FLAG_NONFINITE;
-          nsq = it;
-          break;
-        }
+        block_max2_u32(thi, shi, ru + (rp++ & 1) * (2 * (kT / 32)));     // (its barrier orders the Sb / Xc reuse)
+        const double tmax = from_hi(thi), smax = from_hi(shi);            // magnitudes to 2^-20: ample for the tests
+        if (hi_nonfinite(thi) || hi_nonfinite(shi)) { lflag = lq::FLAG_NONFINITE; nsq = it; break; }
+        if (!(tmax > 1e-18 * smax)) { lflag = 0; nsq = it; break; }
         if (!(smax < 1e300)) { lflag = lq::FLAG_NONFINITE; nsq = it; break; }   // diverging (unstable loop)
         gemm_nn<n, false, DM>(Mc, Mc, [&](int i, int j, double v) { Xc[i * LD + j] = v; });
         __syncthreads();
@@ -480,57 +519,68 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
       double J = 0.0;
       for (int e = tid; e < n * n; e += kT) J = fma(xs[e / n] * Sb[(e / n) * LD + e % n], xs[e % n], J);
       J = block_sum(J, red);
+      K4_PROF(5);
       // ---- spectral radius: keep squaring M = A_cl^(2^nsq) with exact power-of-two rescaling,
       //      log2 rho ~ sum_j 2^-j e_j + 2^-k log2 max|N_k|  (N_k the stored, rescaled power; e_j its exponent)
       double rho = 0.0;
       bool accepted = false;
       if (!a.rho_qr && nsq < kRhoK1) {
-        double mx = 0.0, dummy = 0.0;
-        int badv = 0;
-        for (int e = tid; e < n * n; e += kT) {
-          const double v = fabs(Mc[(e / n) * LD + e % n]);
-          mx = fmax(mx, v);
-          badv |= !(v <= 1.79e308);
-        }
-        block_max2(mx, dummy, red);
+        // max |N| to full precision (only the two estimates need the mantissa)
+        auto absmax = [&](const double* Mm) {
+          double mx = 0.0, dummy = 0.0;
+          for (int e = tid; e < n * n; e += kT) mx = fmax(mx, fabs(Mm[(e / n) * LD + e % n]));
+          block_max2(mx, dummy, red);
+          return mx;
+        };
+        unsigned mh = 0, dm = 0;
+        for (int e = tid; e < n * n; e += kT) mh = max(mh, hi_abs(Mc[(e / n) * LD + e % n]));
+        block_max2_u32(mh, dm, ru + (rp++ & 1) * (2 * (kT / 32)));
         double lacc = 0.0, wgt = __hiloint2double((1023 - nsq) << 20, 0), est1 = 0.0;
-        bool fail = __syncthreads_or(badv) != 0, zero = false;
-        double* rq = red + 2 * (kT / 32);
+        bool fail = false, zero = false;
         int kk = nsq;
-        for (; kk < kRhoK2 && !fail; ++kk) {
-          if (kk == kRhoK1) est1 = fma(lacc, 0.6931471805599453, wgt * log(mx));
-          if (!(mx > 0.0)) { zero = true; break; }           // a vanishing power: nilpotent, rho = 0
-          const int e = ((__double2hiint(mx) >> 20) & 0x7ff) - 1023;
+        for (; kk < kRhoK2; ++kk) {
+          if (hi_nonfinite(mh)) { fail = true; break; }
+          if ((mh >> 20) == 0) {                             // a vanishing power: A_cl^(2^kk) = 0 (or subnormal).
+            zero = (kk <= 6);                                // Nilpotent (rho = 0) if that early; later it is underflow
+            fail = !zero;                                    // of the entries that carry rho (huge Jordan blocks) -> QR
+            break;
+          }
+          if (kk == kRhoK1) est1 = fma(lacc, 0.6931471805599453, wgt * log(absmax(Mc)));
+          const int e = (int)(mh >> 20) - 1023;
           if (e < -500 || e > 500) { fail = true; break; }
+          // (2^-e N)^2 with the scale applied to the LEFT operand on load: the stored power keeps its full dynamic
+          // range (a product of two unnormalised operands would underflow the small entries that carry rho)
           const double s2 = __hiloint2double((1023 - 2 * e) << 20, 0);
-          double lm = 0.0;
-          gemm_nn<n, false, DM>(Mc, Mc, [&](int i, int j, double v) {
-            const double sv = v * s2;
-            Xc[i * LD + j] = sv;
-            lm = fmax(lm, fabs(sv));
-            badv |= !(fabs(sv) <= 1.79e308);
-          });
+          unsigned lh = 0;
+          {
+            const int r0 = (w >> 1) * HB, c0 = (w & 1) * HB;
+            double c[T][T][2];
+            warp_mma<T, T, DM>(n, r0, c0, [&](int i, int q) { return Mc[i * LD + q] * s2; },
+                               [&](int q, int j) { return Mc[q * LD + j]; }, c);
+            warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) {
+              Xc[i * LD + j] = v;
+              lh = max(lh, hi_abs(v));
+            });
+          }
           lacc = fma(wgt, (double)e, lacc);
           wgt *= 0.5;
-          lm = warp_max(lm);
-          double* slot = rq + (kk & 1) * (kT / 32);
-          if (lane == 0) slot[w] = lm;
-          if (__syncthreads_or(badv)) { fail = true; break; }
-          mx = slot[0];
-#pragma unroll
-          for (int q = 1; q < kT / 32; ++q) mx = fmax(mx, slot[q]);
+          block_max2_u32(lh, dm, ru + (rp++ & 1) * (2 * (kT / 32)));
+          mh = lh;
           double* t = Mc; Mc = Xc; Xc = t;
         }
         if (!fail) {
           if (zero) {
             accepted = true;
+          } else if (hi_nonfinite(mh) || (mh >> 20) == 0) {
+            fail = true;
           } else {
-            const double est2 = fma(lacc, 0.6931471805599453, wgt * log(mx));
+            const double est2 = fma(lacc, 0.6931471805599453, wgt * log(absmax(Mc)));
             rho = exp(est2);
             accepted = fabs(rho - exp(est1)) <= 5e-10 * rho;
           }
         }
       }
+      K4_PROF(6);
       if (accepted) {
         if (tid == 0) {
           int fl = lflag | *cflag;
@@ -560,9 +610,14 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
         }
       }
       __syncthreads();
+      K4_PROF(7);
     }
     __syncthreads();
   }
+#ifdef LQ_K4_PROFILE
+  __syncthreads();
+  if (tid < 32) atomicAdd(&g_k4_prof[tid], sprof[tid]);
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ k4b
@@ -865,6 +920,20 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
     const int64_t wantb = (r.total + kT / 32 - 1) / (kT / 32);
     if (rblocks > wantb) rblocks = wantb;
     tiled_rho_kernel<n><<<(unsigned)rblocks, kT, rsmem, ctx->stream>>>(r);
+#ifdef LQ_K4_PROFILE
+    if (cs > 1000) {
+      unsigned long long hp[32];
+      cudaStreamSynchronize(ctx->stream);
+      cudaMemcpyFromSymbol(hp, g_k4_prof, sizeof(hp));
+      unsigned long long z[32] = {0};
+      cudaMemcpyToSymbol(g_k4_prof, z, sizeof(z));
+      for (int ww = 0; ww < 4; ++ww) {
+        fprintf(stderr, "k4prof warp %d (cycles per sample):", ww);
+        for (int q = 0; q < 8; ++q) fprintf(stderr, " %9.0f", (double)hp[ww * 8 + q] / (double)cs);
+        fprintf(stderr, "\n");
+      }
+    }
+#endif
     ctx->launches += 2;
     rc = lq_check_cuda(ctx, cudaGetLastError(), "tiled kernels launch");
     if (rc) return rc;

@@ -593,6 +593,42 @@ def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
         assert np.array_equal(hp[k].numpy(), g[k]), k
 
 
+def test_k4_spectral_radius_by_squaring_and_qr_fallback(engine, monkeypatch):
+    """k4a's spectral radius (rescaled repeated squaring, accepted when two depths agree) vs the QR kernel on the same
+    batch, and the cases squaring must NOT decide alone: a 16 x 16 Jordan block (estimates at the two depths disagree
+    -> handed to the QR kernel, which is exact on a triangular matrix) and a nilpotent plant (rho = 0 exactly).
+    B = 0 makes the closed loop equal to the plant, so A_cl is under the test's control."""
+    from oracle import np_batched as nb
+    n, m, N = 32, 8, 6
+    rng = np.random.default_rng(3)
+    S = 37
+    x0 = rng.normal(size=(S, n))
+    zA, zB = np.zeros((S, n, n)), np.zeros((S, n, m))
+    for kind in ("jordan", "nilpotent"):
+        sup = np.zeros(n - 1)
+        sup[:15] = 0.3
+        A = (0.7 * np.eye(n) + np.diag(sup, 1)) if kind == "jordan" else np.diag(0.5 * np.ones(n - 1), 1)
+        B, Q, R = np.zeros((n, m)), np.eye(n), np.eye(m)
+        engine.set_problem_tiled(A, B, Q, R, Q, 30)
+        Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+        ref = nb.eval_batch(A, B, Q, R, Q, Pexp, zA, zB, x0, N, N)
+        got = engine.eval_batch_tiled(zA, zB, x0, N, N)
+        rho = got["rho"].cpu().numpy()[0]
+        want = 0.7 if kind == "jordan" else 0.0
+        assert np.max(np.abs(rho - want)) < 1e-13, kind
+        assert relerr(got["J"].cpu().numpy(), ref["J"]) < TOL and not np.any(got["flags"].cpu().numpy())
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    engine.set_problem_tiled(A, B, Q, R, Q, 30)
+    dA, dB, x0 = nb.synth_samples(n, m, 600, seed=4, e=0.05)
+    monkeypatch.setenv("LQMPC_K4_RHO", "qr")
+    qr = engine.eval_batch_tiled(dA, dB, x0, 30, 30)
+    monkeypatch.setenv("LQMPC_K4_RHO", "sq")
+    sq = engine.eval_batch_tiled(dA, dB, x0, 30, 30)
+    assert relerr(sq["rho"].cpu().numpy(), qr["rho"].cpu().numpy()) < 1e-10
+    assert np.array_equal(sq["flags"].cpu().numpy(), qr["flags"].cpu().numpy())
+    assert np.array_equal(sq["J"].cpu().numpy(), qr["J"].cpu().numpy())
+
+
 # --------------------------------------------------------------------------------------------- sweep driver (cfg 2)
 def test_error_horizon_sweep_vs_golden_and_oracle(engine, golden, example):
     """Full error-level x horizon grid (lq_mpc_b200/sweep.py): column N=7 is the shipped error table, row level 4
