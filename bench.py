@@ -33,7 +33,7 @@ SEED_PROBLEM, SEED_SAMPLES = 0, 1
 WORKLOADS = {
     "cfg-synth-4-2-10": dict(n=4, m=2, N=10, S=12_500_000, e=0.01, tiled=False, kernel="eval_kernel<4,2>"),
     "cfg-synth-32-8-30": dict(n=32, m=8, N=30, S=125_000, e=1e-3, tiled=True,
-                              kernel="tiled_eval_kernel<32,8> + tiled_rho_kernel<32>"),
+                              kernel="tiled_eval_kernel<32,8> (+ tiled_rho_kernel<32> for entries it hands over)"),
 }
 
 
