@@ -125,6 +125,14 @@ int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const dou
  * path. The bound kernels (K3) and K1/K4 are regulation-only, as every caller in the reference is. Synchronises. */
 int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, const double* u_ref_host);
 
+/* General input polytope F_u u <= 1 (utils_class.py:23,81: F_u is an arbitrary p x m matrix; rows with several
+ * non-zeros couple the inputs) for the following lqmpc_mpc_solve_batch / lqmpc_simulate_batch / lqmpc_bounds_batch
+ * calls: HOST pointer, row-major (p x m), p <= 12, N * p <= 128 per solve. p <= 0 or NULL clears it (back to the box of
+ * lqmpc_set_problem, the state after lqmpc_set_problem). The origin must be interior (it is: the right-hand side is 1).
+ * With a polytope installed lqmpc_bounds_batch takes local_radius (utils.py:548-564) over these rows and needs bar_u /
+ * bar_d_u (utils.py:592-650: maxima of convex functions, attained at vertices) from the caller. Synchronises. */
+int lqmpc_set_input_polytope(lqmpc_ctx* ctx, int p, const double* F_u_host);
+
 /* K2b — batched LQ_MPC_Simulator.simulate (utils_class.py:245-285): T receding-horizon steps, the controller plans
  * with (A+dA_s, B+dB_s) and horizon N, the plant is the TRUE model; J_T as accumulated at utils_class.py:261,282-283.
  * Initial state: `x0_shared` device [n] (one state for all samples) or `x0` device [n][S].

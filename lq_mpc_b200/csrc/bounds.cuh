@@ -234,6 +234,8 @@ struct BoundsScalars {
   int strict_reference;    // literal kron ordering of utils.py:317-318 (only matters when Q, R are not scalar)
   int has_gram = 0;        // extreme eigenvalues of Gamma'Gamma supplied by gram_extremes_kernel (Q = qI, R = rI only)
   double cmin = 0.0, cmax = 0.0;
+  const double* polyF = nullptr;   // general input polytope rows [p][m] (then bar_u / bar_d_u must be supplied), or NULL
+  int polyP = 0;
 };
 
 // Gamma[(t, r), (j, s)] for t = 0..N, j = 0..N-1 from the stored G_d = A^d B.
@@ -268,12 +270,25 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
   out[BF_NORM_A] = fA; out[BF_NORM_B] = fB; out[BF_NORM_K] = nK;
   const double maxQ = pb.maxQ, minQ = pb.minQ, maxR = pb.maxR, minR = pb.minR;
   const double ratioQ = maxQ / minQ;
-  // ---------------- local_radius (utils.py:548-564) for the box rows
+  // ---------------- local_radius (utils.py:548-564): max_i ||(F_u K)_i||^2 in the Q^-1 metric — box rows, or the
+  //                  rows of a general polytope
   double amax = 0.0;
-  LQ_UNROLL for (int j = 0; j < m; ++j) {
-    const double kq = quad<n>(K + j * n, pb.Qinv, K + j * n);
-    if (pb.ulo[j] > -1e300) amax = dmax(amax, kq / (pb.ulo[j] * pb.ulo[j]));
-    if (pb.uhi[j] < 1e300) amax = dmax(amax, kq / (pb.uhi[j] * pb.uhi[j]));
+  if (sc.polyP > 0) {
+    for (int i = 0; i < sc.polyP; ++i) {
+      double fk[n];
+      LQ_UNROLL for (int c = 0; c < n; ++c) {
+        double acc = 0.0;
+        LQ_UNROLL for (int j = 0; j < m; ++j) acc = fma(sc.polyF[i * m + j], K[j * n + c], acc);
+        fk[c] = acc;
+      }
+      amax = dmax(amax, quad<n>(fk, pb.Qinv, fk));
+    }
+  } else {
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      const double kq = quad<n>(K + j * n, pb.Qinv, K + j * n);
+      if (pb.ulo[j] > -1e300) amax = dmax(amax, kq / (pb.ulo[j] * pb.ulo[j]));
+      if (pb.uhi[j] < 1e300) amax = dmax(amax, kq / (pb.uhi[j] * pb.uhi[j]));
+    }
   }
   const double eps_K = 1.0 / amax;
   out[BF_EPSILON_K] = eps_K;

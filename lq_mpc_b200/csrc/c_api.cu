@@ -7,6 +7,7 @@
 #include "../../include/lqmpc_b200.h"
 #include "engine.h"
 #include "bounds.cuh"
+#include "pclqr.cuh"
 
 int lq_set_error(lqmpc_ctx* ctx, int code, const char* what) {
   if (ctx) ctx->err = what ? what : "";
@@ -115,6 +116,7 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
   if (ctx->ref_x) cudaFree(ctx->ref_x);
   if (ctx->ref_u) cudaFree(ctx->ref_u);
+  if (ctx->poly_dev) cudaFree(ctx->poly_dev);
   if (ctx->tiled_pb) cudaFree(ctx->tiled_pb);
   if (ctx->tiled_zero) cudaFree(ctx->tiled_zero);
   for (int i = 0; i < 6; ++i)
@@ -154,6 +156,8 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   if (ctx->ref_x) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_x); ctx->ref_x = nullptr; }
   if (ctx->ref_u) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_u); ctx->ref_u = nullptr; }
   ctx->ref_ld = 0;
+  if (ctx->poly_dev) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->poly_dev); ctx->poly_dev = nullptr; }
+  ctx->poly_p = 0;
   ctx->n = n;
   ctx->m = m;
   ctx->N_opc = N_opc;
@@ -460,6 +464,26 @@ int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, c
   return LQMPC_OK;
 }
 
+int lqmpc_set_input_polytope(lqmpc_ctx* ctx, int p, const double* F_host) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  if (ctx->poly_dev) { cudaFree(ctx->poly_dev); ctx->poly_dev = nullptr; }
+  ctx->poly_p = 0;
+  if (p <= 0 || !F_host) return LQMPC_OK;                              // cleared: the box of lqmpc_set_problem
+  if (p > lq::kPolyMaxRows) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: at most 12 rows");
+  const size_t bytes = (size_t)p * ctx->m * sizeof(double);
+  for (int e = 0; e < p * ctx->m; ++e)
+    if (!(fabs(F_host[e]) <= 1.79e308)) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: non-finite entry");
+  int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->poly_dev, bytes), "cudaMalloc F_u");
+  if (rc) return rc;
+  rc = lq_check_cuda(ctx, cudaMemcpy(ctx->poly_dev, F_host, bytes, cudaMemcpyHostToDevice), "H2D F_u");
+  if (rc) return rc;
+  ctx->poly_p = p;
+  return LQMPC_OK;
+}
+
 int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int npts,
                           const double* pts, const double* x0, double* V, double* u0, double* M_V, int32_t* flags) {
   if (!ctx) return LQMPC_EINVAL;
@@ -514,6 +538,11 @@ int lqmpc_bounds_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double
   a.V_expert = V_expert; a.bar_u = bar_u; a.bar_d_u = bar_d_u; a.strict = strict_reference;
   a.alpha = alpha; a.beta = beta; a.xi = xi; a.eta = eta; a.bound = bound; a.detail = detail; a.K_out = K_out;
   a.P_out = P_out; a.flags = flags;
+  if (ctx->poly_p > 0) {
+    if (bar_u < 0.0 || bar_d_u < 0.0)
+      return lq_set_error(ctx, LQMPC_EINVAL, "with an input polytope installed bar_u / bar_d_u must be supplied (>= 0)");
+    a.polyF = ctx->poly_dev; a.polyP = ctx->poly_p;
+  }
   return lq_launch_bounds(ctx, a);
 }
 

@@ -35,6 +35,9 @@ struct lqmpc_ctx {
   double* ref_x = nullptr;
   double* ref_u = nullptr;
   int ref_ld = 0;
+  // general input polytope F_u u <= 1 (lqmpc_set_input_polytope): device copy of the p x m rows; p = 0 -> the box
+  double* poly_dev = nullptr;
+  int poly_p = 0;
   // scratch (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
@@ -82,6 +85,8 @@ struct MpcArgs {
   const double* xr = nullptr;   // shared references (device, row-major [n][ref_ld] / [m][ref_ld]) or NULL = zeros
   const double* ur = nullptr;
   int ref_ld = 0;
+  const double* polyF = nullptr;   // filled by the polytope launcher (device, row-major [p][m])
+  int polyP = 0;
 };
 
 struct BoundsArgs {
@@ -109,6 +114,8 @@ struct BoundsArgs {
   int32_t* flags;
   double* ws;
   const double* gtri = nullptr;   // [2 N m][S] tridiagonal form of Gamma'Gamma from gram_extremes_kernel, or NULL
+  const double* polyF = nullptr;  // general input polytope rows (device, [p][m]) for local_radius, or NULL -> the box
+  int polyP = 0;
 };
 
 struct TiledEval {
@@ -135,6 +142,7 @@ int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_dmma_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);
+int lq_launch_mpc_poly(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);
 int lq_launch_bounds(lqmpc_ctx* ctx, const BoundsArgs& a);
 int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats);
 int lq_launch_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* out);

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(128) bounds_kernel(const __grid_constant__ lq:
     sc.V_expert = a.V_expert;
     sc.bar_u = a.bar_u; sc.bar_d_u = a.bar_d_u;
     sc.strict_reference = a.strict;
+    sc.polyF = a.polyF; sc.polyP = a.polyP;
     if (a.gtri) {   // tridiagonal form of Gamma'Gamma precomputed by the warp kernel: only the Sturm bisection is left
       const int k = a.N * m;
       const lq::WsView tv{const_cast<double*>(a.gtri) + s, a.S};

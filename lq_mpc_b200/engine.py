@@ -49,6 +49,7 @@ ABI = {
     "lqmpc_eval_batch_tiled": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int] + [_vp] * 5),
     "lqmpc_eval_batch_tiled_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _vp, _vp, _vp, _vp, _i64]),
     "lqmpc_set_references": (_int, [_vp, _int, _vp, _vp]),
+    "lqmpc_set_input_polytope": (_int, [_vp, _int, _vp]),
     "lqmpc_mpc_solve_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 6),
     "lqmpc_simulate_batch": (_int, [_vp, _i64, _vp, _vp, _int, _int] + [_vp] * 7),
     "lqmpc_bounds_fields": (_int, []),
@@ -185,6 +186,7 @@ class Engine:
         rc = self.lib.lqmpc_set_problem(self._h, n, m, _ptr(A), _ptr(B), _ptr(Q), _ptr(R), _ptr(P), _ptr(lo),
                                         _ptr(hi), int(N_opc))
         self._check(rc, "lqmpc_set_problem")
+        self._poly_bar = None                       # lqmpc_set_problem clears an installed input polytope
         self.n, self.m = n, m
         self.A, self.B, self.Q, self.R, self.P = A, B, Q, R, P
         self.u_lo, self.u_hi = lo, hi
@@ -326,6 +328,22 @@ class Engine:
         self._check(self.lib.lqmpc_set_references(self._h, cols, _ptr(xr), _ptr(ur)), "lqmpc_set_references")
         return self
 
+    def set_input_polytope(self, F_u=None, bar_u: float = -1.0, bar_d_u: float = -1.0):
+        """General input polytope F_u u <= 1 (p x m) for the following K2 / K3 calls; None clears it (box of
+        set_problem). set_problem also clears it. bar_u / bar_d_u (utils.py:592-650, vertex maxima) become the defaults
+        of bounds_batch while the polytope is installed."""
+        self._poly_bar = None
+        if F_u is None:
+            self._check(self.lib.lqmpc_set_input_polytope(self._h, 0, None), "lqmpc_set_input_polytope")
+            return self
+        F = _np_f64(F_u)
+        if F.ndim != 2 or F.shape[1] != self.m:
+            raise EngineError("F_u must be (p, m) with m = %d input columns, got %r" % (self.m, F.shape))
+        self._check(self.lib.lqmpc_set_input_polytope(self._h, F.shape[0], _ptr(F)), "lqmpc_set_input_polytope")
+        if bar_u >= 0.0 and bar_d_u >= 0.0:
+            self._poly_bar = (float(bar_u), float(bar_d_u))
+        return self
+
     def references(self, x_ref=None, u_ref=None):
         """`with eng.references(x_ref, u_ref): ...` — set for the K2 calls inside, cleared on exit."""
         eng = self
@@ -442,6 +460,8 @@ class Engine:
         K_out = torch.empty((m * n, S), dtype=torch.float64, device=self.device) if want_K else None
         P_out = torch.empty((n * n, S), dtype=torch.float64, device=self.device) if want_P else None
         p3 = _np_f64(p, (3,))
+        if getattr(self, "_poly_bar", None) is not None and (bar_u < 0.0 or bar_d_u < 0.0):
+            bar_u, bar_d_u = self._poly_bar
         rc = self.lib.lqmpc_bounds_batch(self._h, S, _ptr(dA), _ptr(dB), int(N), _ptr(eA_d), _ptr(eB_d), eA_s, eB_s,
                                          _ptr(MV_d), MV_s, _ptr(x_sh), _ptr(x_ps), _ptr(K_ps), _ptr(K_sh), _ptr(p3),
                                          float(V_expert), float(bar_u), float(bar_d_u), int(bool(strict_reference)),

@@ -5,7 +5,7 @@ import os
 
 import numpy as np
 
-from .engine import Engine
+from .engine import Engine, EngineError
 
 _engines = {}
 
@@ -32,7 +32,8 @@ def box_from_F(F_u):
     for row in F_u:
         nz = np.flatnonzero(row)
         if len(nz) != 1:
-            raise NotImplementedError("lq_mpc_b200 supports box-shaped F_u (one non-zero per row) only")
+            raise NotImplementedError("not a box: this row of F_u couples several inputs (general polytopes go "
+                                      "through Engine.set_input_polytope / runtime.problem_for)")
         j = nz[0]
         if row[j] > 0:
             hi[j] = min(hi[j], 1.0 / row[j])
@@ -41,13 +42,54 @@ def box_from_F(F_u):
     return lo, hi
 
 
+def is_box(F_u) -> bool:
+    """Every row of F_u has exactly one non-zero (the only shape the reference's own scripts build)."""
+    F_u = np.atleast_2d(np.asarray(F_u, dtype=np.float64))
+    return all(len(np.flatnonzero(row)) == 1 for row in F_u)
+
+
+def polytope_vertices(F_u):
+    """Vertices of {u : F_u u <= 1}: feasible intersections of m rows (m <= 4, p <= 12: at most 495 candidates).
+    Host-side and once per problem, like the Gurobi models it stands in for (utils.py:592-650)."""
+    import itertools
+    F = np.atleast_2d(np.asarray(F_u, dtype=np.float64))
+    p, m = F.shape
+    out = []
+    for rows in itertools.combinations(range(p), m):
+        Fs = F[list(rows)]
+        if abs(np.linalg.det(Fs)) < 1e-12 * np.prod(np.linalg.norm(Fs, axis=1)):
+            continue
+        v = np.linalg.solve(Fs, np.ones(m))
+        if np.all(F @ v <= 1 + 1e-9):
+            out.append(v)
+    if not out:
+        raise ValueError("input set is unbounded or empty")
+    # a bounded polytope: every direction is blocked by some row (checked on the vertex set's recession: any row
+    # combination with no vertex would have raised above; an unbounded set with vertices is caught here)
+    V = np.array(out)
+    for d in np.vstack((np.eye(m), -np.eye(m))):
+        if not np.any(F @ d > 1e-12):
+            raise ValueError("input set is unbounded")
+    return V
+
+
 def problem_for(A, B, Q, R, P=None, F_u=None, N_opc=30, device=None) -> Engine:
-    """Engine with (A, B, Q, R, P, box(F_u)) installed as the TRUE/nominal problem."""
+    """Engine with (A, B, Q, R, P, F_u) installed as the TRUE/nominal problem: a box-shaped F_u goes into the problem
+    itself, a general polytope is installed behind it (lqmpc_set_input_polytope)."""
     eng = get_engine(device)
     lo = hi = None
-    if F_u is not None:
+    general = F_u is not None and not is_box(F_u)
+    if F_u is not None and not general:
         lo, hi = box_from_F(F_u)
     eng.set_problem(np.asarray(A, dtype=np.float64), np.asarray(B, dtype=np.float64),
                     np.asarray(Q, dtype=np.float64), np.asarray(R, dtype=np.float64),
                     None if P is None else np.asarray(P, dtype=np.float64), lo, hi, N_opc)
+    if general:
+        if np.atleast_2d(np.asarray(F_u)).shape[1] != eng.m:
+            raise EngineError("F_u has %d columns, the plant has %d inputs"
+                              % (np.atleast_2d(np.asarray(F_u)).shape[1], eng.m))
+        V = polytope_vertices(F_u)
+        bar_u = float(np.max(np.sum(V * V, axis=1)))
+        D = V[:, None, :] - V[None, :, :]
+        eng.set_input_polytope(F_u, bar_u=bar_u, bar_d_u=float(np.max(np.sum(D * D, axis=2))))
     return eng

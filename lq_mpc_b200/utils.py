@@ -195,13 +195,21 @@ def _vertices(F_u):
 
 
 def bar_u_solve(F_u):
-    """utils.py:592-619 (Gurobi non-convex QP) — for a box the maximum of ||u||^2 sits at a vertex."""
+    """utils.py:592-619 (Gurobi non-convex QP) — the maximum of the convex ||u||^2 over a polytope sits at a vertex:
+    closed form for a box, vertex enumeration otherwise."""
+    if not _rt.is_box(F_u):
+        V = _rt.polytope_vertices(F_u)
+        return float(np.max(np.sum(V * V, axis=1)))
     lo, hi = _vertices(F_u)
     return float(np.sum(np.maximum(lo * lo, hi * hi)))
 
 
 def bar_d_u_solve(F_u):
-    """utils.py:622-650."""
+    """utils.py:622-650 — max ||u1 - u2||^2 over the polytope x itself: a pair of vertices."""
+    if not _rt.is_box(F_u):
+        V = _rt.polytope_vertices(F_u)
+        D = V[:, None, :] - V[None, :, :]
+        return float(np.max(np.sum(D * D, axis=2)))
     lo, hi = _vertices(F_u)
     return float(np.sum((hi - lo) ** 2))
 

@@ -3,9 +3,9 @@ dict keys; citations are into /root/reference/utils_class.py). Every numeric res
 single calls are S = 1 batches, the sweep drivers pack all (system, level) pairs of a table into one launch.
 
 Not carried over: the three Plotter_* classes (presentation, out of scope) — importing them raises a clear error.
-Unsupported inputs fail loudly instead of falling back: non-box F_u; non-zero references are supported by the
-controller / simulator / M_V paths (K2) and rejected by the regulation-only bound drivers, as upstream's own callers
-only ever pass zeros there.
+Both box-shaped and general polytopic F_u are supported (the latter up to 12 rows and N * rows <= 128, beyond which the
+solve is flagged, not approximated); non-zero references are supported by the controller / simulator / M_V paths (K2);
+the bound formulas have no reference terms upstream either.
 """
 from __future__ import annotations
 

@@ -189,7 +189,7 @@ def main():
 
 if __name__ == "__main__":
     import sys as _sys
-    if "--tracking" not in _sys.argv:
+    if "--tracking" not in _sys.argv and "--polytope" not in _sys.argv:
         main()
 
 
@@ -223,6 +223,54 @@ def tracking_cases(uc, seed=11):
     return cases
 
 
+def polytope_cases(u, uc, seed=23):
+    """General input polytopes F_u (rows coupling several inputs, utils_class.py:81) through the untouched reference
+    classes: open-loop solves, closed loops, bar_u / bar_d_u (vertex maxima) and energy_bound; m = 2 and 3.
+    (energy_decreasing cannot be pinned here: the reference's `A + B * K`, utils.py:356, raises for m > 1.)"""
+    rng = np.random.default_rng(seed)
+    cases = []
+    shapes = [(2, 2, 3), (2, 2, 5), (3, 2, 4), (3, 2, 6), (2, 2, 8), (3, 3, 4), (3, 3, 7), (2, 2, 4)]
+    for c in range(16):
+        n, m, p = shapes[c % len(shapes)]
+        N = int(rng.integers(2, min(10, 128 // p) + 1))
+        T = int(rng.integers(3, 9))
+        A = rng.normal(size=(n, n))
+        A *= rng.uniform(0.6, 1.15) / np.max(np.abs(np.linalg.eigvals(A)))
+        B = rng.normal(size=(n, m))
+        q, r = rng.uniform(0.5, 3.0), rng.uniform(0.3, 2.0)
+        Q, R = q * np.eye(n), r * np.eye(m)
+        while True:                                   # bounded polytope around the origin: unit normals / support
+            D = rng.normal(size=(p, m))
+            D /= np.linalg.norm(D, axis=1, keepdims=True)
+            probe = rng.normal(size=(4000, m))
+            probe /= np.linalg.norm(probe, axis=1, keepdims=True)
+            if np.min(np.max(probe @ D.T, axis=1)) > 0.1:
+                break
+        F_u = D / rng.uniform(0.1, 0.45, size=(p, 1))
+        x0 = rng.normal(size=n) * rng.uniform(0.3, 1.5)
+        dA = rng.uniform(-0.02, 0.02, size=(n, n))
+        dB = rng.uniform(-0.02, 0.02, size=(n, m))
+        zx, zu = np.zeros((n, N)), np.zeros((m, N))
+        sol = uc.LQ_MPC_Controller(N, A + dA, B + dB, Q, R, Q, F_u).solve(x0, zx, zu)
+        sim = uc.LQ_MPC_Simulator(T, N, A + dA, B + dB, Q, R, Q, F_u).simulate(x0, A, B, zx, zu)
+        e = float(rng.uniform(1e-3, 1e-2))
+        bnd = uc.LQ_RDP_Calculator(A + dA, B + dB, Q, R, F_u).energy_bound(N, e, e, x0, np.array([0.1, 1, 0.6]))
+        cases.append({'n': n, 'm': m, 'p': p, 'N': N, 'T': T, 'A': _l(A), 'B': _l(B), 'dA': _l(dA), 'dB': _l(dB),
+                      'q': q, 'r': r, 'F_u': _l(F_u), 'x0': _l(x0), 'u_0': _l(sol['u_0']), 'V_N': float(sol['V_N']),
+                      'J_T': float(sim['J_T']), 'X': _l(sim['X']), 'U': _l(sim['U']), 'e': e,
+                      'bar_u': float(u.bar_u_solve(F_u)), 'bar_d_u': float(u.bar_d_u_solve(F_u)),
+                      'alpha': float(bnd['alpha']), 'beta': float(bnd['beta'])})
+    return cases
+
+
+def main_polytope():
+    """Adds tests/golden/ref_polytope_cases.json without touching the other fixtures."""
+    u, uc = ro.load()
+    with open(os.path.join(GOLD, "ref_polytope_cases.json"), "w") as f:
+        json.dump(polytope_cases(u, uc), f, indent=0)
+    print("polytope fixtures written")
+
+
 def main_tracking():
     """Adds tests/golden/ref_tracking_cases.json without touching the other fixtures."""
     u, uc = ro.load()
@@ -235,3 +283,5 @@ if __name__ == "__main__":
     import sys as _sys
     if "--tracking" in _sys.argv:
         main_tracking()
+    if "--polytope" in _sys.argv:
+        main_polytope()

@@ -135,9 +135,10 @@ def box_qp(H, g, lo, hi):
     return res.x
 
 
-def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_ref=None, u_ref=None):
+def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_ref=None, u_ref=None, F_u=None):
     """LQ_MPC_Controller.solve (utils_class.py:48-91). Returns (u_0, V_N, active). Non-zero references always take
-    the dense condensed QP (the law is affine then).
+    the dense condensed QP (the law is affine then). F_u (p, m): general input polytope F_u u_k <= 1
+    (utils_class.py:81) instead of the box lo / hi — dense active-set QP of oracle/qp_dense.py.
 
     exact_fast: if the unconstrained (Riccati) open-loop plan is feasible it IS the QP minimiser (KKT with zero
     multipliers), so the dense QP is only assembled when some planned input leaves the box."""
@@ -147,7 +148,7 @@ def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_r
     hi = np.full(m, np.inf) if hi is None else np.asarray(hi, dtype=float)
     tracking = (x_ref is not None and np.any(np.asarray(x_ref) != 0)) or \
         (u_ref is not None and np.any(np.asarray(u_ref) != 0))
-    if exact_fast and not tracking:
+    if exact_fast and not tracking and F_u is None:
         K, P = riccati(A, B, Q, R, P_term, N) if _ric is None else _ric
         x = x0
         feas = True
@@ -160,6 +161,12 @@ def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_r
         if feas:
             return K[0] @ x0, float(x0 @ P[0] @ x0), False
     H, g, c0 = condensed_qp(N, A, B, Q, R, P_term, x0, x_ref, u_ref)
+    if F_u is not None:
+        from .qp_dense import ineq_qp
+        F_u = np.atleast_2d(np.asarray(F_u, dtype=float))
+        z, Wact = ineq_qp(H, g, np.kron(np.eye(N), F_u), np.ones(N * F_u.shape[0]))
+        V = float(z @ H @ z + 2 * g @ z + c0 + x0 @ Q @ x0)
+        return z[:m].copy(), V, len(Wact) > 0
     z = box_qp(H, g, np.tile(lo, N), np.tile(hi, N))
     V = float(z @ H @ z + 2 * g @ z + c0 + x0 @ Q @ x0)
     active = bool(np.any(z <= np.tile(lo, N)) or np.any(z >= np.tile(hi, N))) if tracking else True
@@ -167,7 +174,8 @@ def mpc_solve(N, A, B, Q, R, P_term, lo, hi, x0, exact_fast=True, _ric=None, x_r
 
 
 # ----------------------------------------------------------------------------------------------- a2: simulator
-def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=True, x_ref=None, u_ref=None):
+def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=True, x_ref=None, u_ref=None,
+             F_u=None):
     """LQ_MPC_Simulator.simulate (utils_class.py:245-285): controller plans with (A,B), plant is (A_true,B_true).
     J_T = x0'Qx0 + sum_t (x_{t+1}'Q x_{t+1} + u_t'R u_t)."""
     n, m = B.shape
@@ -177,8 +185,10 @@ def simulate(T, N, A, B, Q, R, P_term, lo, hi, x0, A_true, B_true, exact_fast=Tr
     cost = float(X[:, 0] @ Q @ X[:, 0])
     n_active = 0
     ric = riccati(A, B, Q, R, P_term, N) if exact_fast else None
+    if F_u is not None:
+        exact_fast = False
     for t in range(T):
-        u, _, act = mpc_solve(N, A, B, Q, R, P_term, lo, hi, X[:, t], exact_fast, ric, x_ref, u_ref)
+        u, _, act = mpc_solve(N, A, B, Q, R, P_term, lo, hi, X[:, t], exact_fast, ric, x_ref, u_ref, F_u)
         n_active += int(act)
         U[:, t] = u
         xn = A_true @ X[:, t] + B_true @ u
@@ -290,9 +300,18 @@ def fc_ec_E(N, e_A, e_B, A, B, Q, R, x, bu_max, bdu_max, strict_reference=True):
             'norm_Gamma': nG, 'theta_u': th['theta_u'], 'theta_x_u': th['theta_x_u']}
 
 
-def energy_bound(A, B, Q, R, lo, hi, N, e_A, e_B, x, p, strict_reference=True):
-    """LQ_RDP_Calculator.energy_bound (utils_class.py:308-342)."""
-    E = fc_ec_E(N, e_A, e_B, A, B, Q, R, x, bar_u(lo, hi), bar_d_u(lo, hi), strict_reference)
+def bar_u_poly(F_u):
+    """utils.py:592-650 for a general polytope: the maxima of ||u||^2 and ||u1 - u2||^2 sit at vertices."""
+    from .qp_dense import polytope_vertices
+    V = polytope_vertices(F_u)
+    D = V[:, None, :] - V[None, :, :]
+    return float(np.max(np.sum(V * V, axis=1))), float(np.max(np.sum(D * D, axis=2)))
+
+
+def energy_bound(A, B, Q, R, lo, hi, N, e_A, e_B, x, p, strict_reference=True, F_u=None):
+    """LQ_RDP_Calculator.energy_bound (utils_class.py:308-342). F_u: general polytope instead of the box lo / hi."""
+    bu, bdu = (bar_u(lo, hi), bar_d_u(lo, hi)) if F_u is None else bar_u_poly(F_u)
+    E = fc_ec_E(N, e_A, e_B, A, B, Q, R, x, bu, bdu, strict_reference)
     p = np.asarray(p, dtype=float)
     q = 1.0 / p
     sp, su, spu = math.sqrt(E['E_psi']), math.sqrt(E['E_u']), math.sqrt(E['E_psi_u'])
@@ -359,9 +378,15 @@ def fc_ec_h(e_A, e_B, Q, R):
     return e_A ** 2 / my_eigen(Q)['min'] + e_B ** 2 / my_eigen(R)['min']
 
 
-def energy_decreasing(A, B, Q, R, lo, hi, N, e_A, e_B, K, M_V):
-    """LQ_RDP_Calculator.energy_decreasing (utils_class.py:344-373). K in the u = +Kx convention."""
-    eps = local_radius(lo, hi, K, Q)
+def energy_decreasing(A, B, Q, R, lo, hi, N, e_A, e_B, K, M_V, F_u=None):
+    """LQ_RDP_Calculator.energy_decreasing (utils_class.py:344-373). K in the u = +Kx convention. F_u: general
+    polytope rows for local_radius (utils.py:548-564) instead of the box lo / hi."""
+    if F_u is None:
+        eps = local_radius(lo, hi, K, Q)
+    else:
+        Mx = np.atleast_2d(F_u) @ np.atleast_2d(K)
+        Qi = np.linalg.inv(Q)
+        eps = 1.0 / max(float(r @ Qi @ r) for r in Mx)
     st = ex_stability_lq(A, B, Q, R, K)
     bd = ex_stability_bounds(st['gamma'], eps, M_V)
     oe = fc_omega_eta(N, A, B, Q, R, K, bd['L_V'], bd['N_0'])

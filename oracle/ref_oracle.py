@@ -48,16 +48,27 @@ def _box_from_F(F_u):
     return lo, hi
 
 
+def _is_box(F_u):
+    return all(len(np.flatnonzero(r)) == 1 for r in np.atleast_2d(np.asarray(F_u, dtype=float)))
+
+
 def bar_u_vertex(F_u):
-    """max ||u||^2 over the box (replaces the Gurobi model of utils.py:592-619)."""
+    """max ||u||^2 over the box / polytope (replaces the Gurobi model of utils.py:592-619)."""
+    if not _is_box(F_u):
+        from .qp_dense import polytope_vertices
+        return float(max(np.dot(v, v) for v in polytope_vertices(F_u)))
     lo, hi = _box_from_F(F_u)
     return float(max(np.dot(v, v) for v in itertools.product(*zip(lo, hi))))
 
 
 def bar_d_u_vertex(F_u):
     """max ||u1-u2||^2 over box x box (replaces the Gurobi model of utils.py:622-650)."""
-    lo, hi = _box_from_F(F_u)
-    verts = [np.array(v) for v in itertools.product(*zip(lo, hi))]
+    if not _is_box(F_u):
+        from .qp_dense import polytope_vertices
+        verts = list(polytope_vertices(F_u))
+    else:
+        lo, hi = _box_from_F(F_u)
+        verts = [np.array(v) for v in itertools.product(*zip(lo, hi))]
     return float(max(np.dot(v - w, v - w) for v in verts for w in verts))
 
 

@@ -5,8 +5,9 @@ constraints of the form  F @ u[:, i] <= 1.
 cvxpy (un-pinned, absent here) would canonicalise the same convex QP and hand it to OSQP/Clarabel; the
 minimiser of a strictly convex QP is unique, so this shim assembles the dense QP
     min_z  z'Hz + 2 g'z + c0   s.t.  lo <= z <= hi       (z time-major: z[i*m:(i+1)*m] = u[:, i])
-and solves it EXACTLY (Cholesky + BVLS active set, tol 1e-15).  Only box constraints are supported (rows of F
-with a single non-zero), which is the only kind the reference ever builds (F_u = [[10],[-10]] / +-10*I).
+and solves it EXACTLY (Cholesky + BVLS active set, tol 1e-15) when every constraint row has a single non-zero — the
+only kind the reference's own scripts build (F_u = [[10],[-10]] / +-10*I). Rows with several non-zeros (a general
+input polytope) go to the dense primal active-set solver of oracle/qp_dense.py instead.
 """
 import numpy as np
 import scipy.linalg as sla
@@ -106,6 +107,16 @@ class Problem:
             c0 += aff.c @ P @ aff.c
         lo = np.full(nz, -np.inf)
         hi = np.full(nz, np.inf)
+        if any(np.count_nonzero(aff.M[r]) > 1 for _, aff, _ in self.cons for r in range(aff.M.shape[0])):
+            from oracle.qp_dense import ineq_qp
+            C = np.vstack([aff.M for _, aff, _ in self.cons])
+            d = np.concatenate([np.broadcast_to(np.asarray(rhs, dtype=float).ravel(), (aff.M.shape[0],)) - aff.c
+                                for _, aff, rhs in self.cons])
+            H = 0.5 * (H + H.T)
+            z, _ = ineq_qp(H, g, C, d)
+            var._z = z
+            self.obj.value = float(z @ H @ z + 2 * g @ z + c0)
+            return self.obj.value
         for kind, aff, rhs in self.cons:
             assert kind == "le"
             rhs = np.broadcast_to(np.asarray(rhs, dtype=float).ravel(), (aff.M.shape[0],))

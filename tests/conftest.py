@@ -46,6 +46,32 @@ def tracking_case(c):
 
 
 @pytest.fixture(scope="session")
+def polytope():
+    """General-polytope F_u solves / closed loops / bounds of the untouched reference (make_golden.py --polytope)."""
+    with open(os.path.join(GOLD, "ref_polytope_cases.json")) as f:
+        return json.load(f)
+
+
+def polytope_case(c):
+    n, m = c["n"], c["m"]
+    d = {k: np.array(c[k]) for k in ("A", "B", "dA", "dB", "x0", "F_u", "u_0", "X", "U")}
+    d.update(n=n, m=m, p=c["p"], N=c["N"], T=c["T"], Q=c["q"] * np.eye(n), R=c["r"] * np.eye(m), e=c["e"],
+             **{k: c[k] for k in ("V_N", "J_T", "bar_u", "bar_d_u", "alpha", "beta")})
+    return d
+
+
+def random_polytope(rng, m, p, lo=0.1, hi=0.45):
+    """Bounded polytope {u : F u <= 1} around the origin: p unit normals that positively span R^m / support distances."""
+    while True:
+        D = rng.normal(size=(p, m))
+        D /= np.linalg.norm(D, axis=1, keepdims=True)
+        probe = rng.normal(size=(4000, m))
+        probe /= np.linalg.norm(probe, axis=1, keepdims=True)
+        if np.min(np.max(probe @ D.T, axis=1)) > 0.1:
+            return D / rng.uniform(lo, hi, size=(p, 1))
+
+
+@pytest.fixture(scope="session")
 def golden_norm2():
     return dict(np.load(os.path.join(GOLD, "ref_norm2_subset.npz")))
 

@@ -67,9 +67,14 @@ def eval_batch(A, B, Q, R, Pt, N_opc, dA_soa, dB_soa, x0_soa, Nmin, Nmax, T):
     return o
 
 
-def mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None, x_ref=None, u_ref=None):
-    """mode 0: open-loop solves; mode 1: closed-loop simulate. x_ref (n, >=N) / u_ref (m, >=N): shared references."""
+def mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None, x_ref=None, u_ref=None,
+        F_u=None):
+    """mode 0: open-loop solves; mode 1: closed-loop simulate. x_ref (n, >=N) / u_ref (m, >=N): shared references.
+    F_u (p, m): general input polytope F_u u <= 1 (then lo / hi are ignored by the solver)."""
     xr, ur = _c(x_ref), _c(u_ref)
+    Fp = _c(F_u)
+    if Fp is not None:
+        lib().hm_set_poly(_p(Fp), Fp.shape[0])
     if xr is not None or ur is not None:
         ld = (xr if xr is not None else ur).shape[1]
         assert (xr is None or xr.shape[1] == ld) and (ur is None or ur.shape[1] == ld) and ld >= N
@@ -78,6 +83,7 @@ def mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=N
         return _mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T, pts, x0_soa)
     finally:
         lib().hm_set_refs(None, None, 0)
+        lib().hm_set_poly(None, 0)
 
 
 def _mpc(mode, A, B, Q, R, Pt, lo, hi, dA_soa, dB_soa, N, T=0, pts=None, x0_soa=None):

@@ -7,6 +7,7 @@
 #include <vector>
 
 #include "../../lq_mpc_b200/csrc/bounds.cuh"
+#include "../../lq_mpc_b200/csrc/pclqr.cuh"
 #include "../../lq_mpc_b200/csrc/sampler.cuh"
 
 #define HM_FOR_EACH_DIM(X) X(1, 1) X(2, 1) X(2, 2) X(3, 1) X(3, 2) X(3, 3) X(4, 1) X(4, 2) X(4, 4) X(6, 2) X(8, 2)
@@ -14,6 +15,7 @@
 namespace {
 
 lq::Refs g_refs;   // set by hm_set_refs (test fixture state)
+lq::Poly g_poly;   // set by hm_set_poly: general input polytope F_u u <= 1 (p = 0: the box of lo/hi)
 
 template <int n, int m>
 void fill_problem(lq::Problem<n, m>& pb, const double* A, const double* B, const double* Q, const double* R,
@@ -106,7 +108,8 @@ int mpc_t(int mode, const double* A, const double* B, const double* Q, const dou
       for (int p = 0; p < Pn; ++p) {
         double xx[n], uu[m], v;
         for (int i = 0; i < n; ++i) xx[i] = pts ? pts[p * n + i] : x0[i * S + s];
-        const int f = pf | lq::clqr_solve<n, m>(pb, pl, N, xx, ws, uu, &v, g_refs);
+        const int f = pf | (g_poly.p > 0 ? lq::pclqr_solve<n, m>(pb, pl, N, xx, g_poly, ws, uu, &v, g_refs)
+                                         : lq::clqr_solve<n, m>(pb, pl, N, xx, ws, uu, &v, g_refs));
         if (v > mvv) mvv = v;
         if (V) V[(int64_t)p * S + s] = v;
         if (u0) for (int j = 0; j < m; ++j) u0[((int64_t)p * m + j) * S + s] = uu[j];
@@ -118,7 +121,9 @@ int mpc_t(int mode, const double* A, const double* B, const double* Q, const dou
       int act;
       for (int i = 0; i < n; ++i) xx[i] = pts ? pts[i] : x0[i * S + s];
       HostTraj traj{n, m, S, s, X, U};
-      const int f = pf | lq::simulate_sample<n, m>(pb, pl, N, T, xx, ws, &jt, &act, traj, g_refs);
+      const int f = pf | (g_poly.p > 0
+                              ? lq::psimulate_sample<n, m>(pb, pl, N, T, xx, g_poly, ws, &jt, &act, traj, g_refs)
+                              : lq::simulate_sample<n, m>(pb, pl, N, T, xx, ws, &jt, &act, traj, g_refs));
       if (J_T) J_T[s] = jt;
       if (flags) flags[s] = f;
       if (n_active) n_active[s] = act;
@@ -224,6 +229,12 @@ void hm_set_refs(const double* x_ref, const double* u_ref, int ld) {
   g_refs.xr = x_ref;
   g_refs.ur = u_ref;
   g_refs.ld = ld;
+}
+
+// general input polytope for every following hm_mpc call: F (p x m) row-major; p = 0 clears it
+void hm_set_poly(const double* F, int p) {
+  g_poly.F = F;
+  g_poly.p = p;
 }
 
 int hm_bounds_fields(void) { return (int)lq::BF_COUNT; }

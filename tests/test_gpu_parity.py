@@ -227,6 +227,109 @@ def test_tracking_references(engine, tracking):
     assert torch.equal(again["V"], base["V"]) and torch.equal(again["u0"], base["u0"])
 
 
+def test_general_input_polytope(engine, polytope):
+    """F_u with rows that couple the inputs (utils_class.py:81): the drop-in classes vs the untouched
+    reference's answers (solve, simulate, energy_bound), a batch through the C ABI vs the dense active-set oracle, the
+    bound kernel's local_radius over polytope rows vs the oracle, a box handed over as a polytope vs the box kernels,
+    and the limits (rows, working-set size) failing loudly."""
+    import torch
+    from oracle import np_oracle as o
+    from lq_mpc_b200.engine import EngineError
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_MPC_Simulator, LQ_RDP_Calculator
+    from tests.conftest import polytope_case, random_polytope
+    n_act = 0
+    for c in map(polytope_case, polytope):
+        Ah, Bh = c["A"] + c["dA"], c["B"] + c["dB"]
+        zx, zu = np.zeros((c["n"], c["N"])), np.zeros((c["m"], c["N"]))
+        sol = LQ_MPC_Controller(c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["F_u"]).solve(c["x0"], zx, zu)
+        assert abs(sol["V_N"] - c["V_N"]) < TOL * abs(c["V_N"]) and np.max(np.abs(sol["u_0"] - c["u_0"])) < 1e-10
+        sim = LQ_MPC_Simulator(c["T"], c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], c["F_u"]).simulate(
+            c["x0"], c["A"], c["B"], zx, zu)
+        assert abs(sim["J_T"] - c["J_T"]) < TOL * abs(c["J_T"]) and np.max(np.abs(sim["U"] - c["U"])) < 1e-10
+        n_act += int(np.max(c["F_u"] @ sim["U"]) > 1 - 1e-9)
+        bnd = LQ_RDP_Calculator(Ah, Bh, c["Q"], c["R"], c["F_u"]).energy_bound(c["N"], c["e"], c["e"], c["x0"],
+                                                                             np.array([0.1, 1, 0.6]))
+        assert abs(bnd["alpha"] - c["alpha"]) < TOL * c["alpha"] and abs(bnd["beta"] - c["beta"]) < TOL * c["beta"]
+    assert 4 <= n_act < len(polytope)
+    rng = np.random.default_rng(9)
+    for n, m, p in [(2, 2, 5), (4, 2, 8), (3, 3, 7), (4, 4, 9), (8, 2, 6)]:
+        N = int(rng.integers(3, min(12, 128 // p) + 1))
+        A = rng.normal(size=(n, n)); A *= 1.1 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+        Q, R = rng.uniform(0.5, 3) * np.eye(n), rng.uniform(0.1, 2) * np.eye(m)
+        F = random_polytope(rng, m, p, 0.15, 0.45)
+        engine.set_problem(A, B, Q, R, Q, None, None, 10)
+        engine.set_input_polytope(F)
+        S = 257
+        x0 = rng.normal(size=(n, S)) * rng.uniform(0.3, 1.2)
+        dA = rng.uniform(-0.02, 0.02, size=(n * n, S)); dB = rng.uniform(-0.02, 0.02, size=(n * m, S))
+        got = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+        sim = engine.simulate_batch(dA, dB, N, 5, x0=x0, want=("J_T", "U", "flags"))
+        V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
+        J, Us = sim["J_T"].cpu().numpy(), sim["U"].cpu().numpy()
+        assert not np.any(fl & ~2) and not np.any(sim["flags"].cpu().numpy() & ~2)
+        na = 0
+        for s in range(0, S, 8):
+            Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+            u_o, V_o, act = o.mpc_solve(N, Ah, Bh, Q, R, Q, None, None, x0[:, s], F_u=F)
+            na += int(act)
+            assert abs(V[0, s] - V_o) < TOL * abs(V_o) and np.max(np.abs(u0[0, :, s] - u_o)) < 1e-9
+            assert bool(fl[0, s] & 2) == act
+            if s % 64 == 0:
+                so = o.simulate(5, N, Ah, Bh, Q, R, Q, None, None, x0[:, s], A, B, F_u=F)
+                assert abs(J[s] - so["J_T"]) < TOL * abs(so["J_T"]) and np.max(np.abs(Us[:, :, s].T - so["U"])) < 1e-9
+        assert na > 3
+    # K3 over polytope rows (local_radius) + supplied vertex constants vs the oracle, on well-damped plants (the
+    # bound formulas need rho(A + BK) + 0.4 < 1, utils.py:358)
+    for n, m, p in [(2, 2, 5), (3, 2, 6), (2, 1, 2)]:
+        N = 7
+        A = rng.normal(size=(n, n)); A *= 0.45 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+        Q, R = 2.0 * np.eye(n), np.eye(m)
+        F = random_polytope(rng, m, p, 0.15, 0.45) if m > 1 else np.array([[4.0], [-5.0]])
+        x = rng.normal(size=n) * 0.2
+        engine.set_problem(A, B, Q, R, Q, None, None, 10)
+        if m > 1:
+            engine.set_input_polytope(F)
+        else:
+            engine.set_problem(A, B, Q, R, Q, [-0.2], [0.25], 10)
+        K = -o.dlqr(A, B, Q, R)[0]
+        bu, bdu = o.bar_u_poly(F) if m > 1 else (o.bar_u(np.array([-0.2]), np.array([0.25])),
+                                                 o.bar_d_u(np.array([-0.2]), np.array([0.25])))
+        if m > 1:
+            with pytest.raises(EngineError):
+                engine.bounds_batch(None, None, N, 5e-3, 5e-3, 0.3, x, (0.1, 1, 0.6), 0.2, K=K, S=1)
+        b = engine.bounds_batch(None, None, N, 5e-3, 5e-3, 0.3, x, (0.1, 1, 0.6), 0.2, K=K, S=1, bar_u=bu, bar_d_u=bdu)
+        lo_hi = (None, None) if m > 1 else (np.array([-0.2]), np.array([0.25]))
+        Fo = F if m > 1 else None
+        try:
+            dec = o.energy_decreasing(A, B, Q, R, *lo_hi, N, 5e-3, 5e-3, K, 0.3, F_u=Fo)
+        except ValueError:                                   # math domain error in the reference's formulas
+            assert int(b["flags"].cpu()[0]) & 512
+            continue
+        assert int(b["flags"].cpu()[0]) & ~32 == 0
+        bnd = o.energy_bound(A, B, Q, R, *lo_hi, N, 5e-3, 5e-3, x, (0.1, 1, 0.6), F_u=Fo)
+        for key, want in (("epsilon_K", dec["epsilon_K"]), ("xi", dec["xi"]), ("eta", dec["eta"]),
+                          ("alpha", bnd["alpha"]), ("beta", bnd["beta"])):
+            assert abs(float(b[key].cpu()[0]) - want) < TOL * abs(want), key
+    # a box handed over as a polytope: same answers as the box kernels; clearing restores them bit for bit
+    n, m, N, S = 4, 2, 6, 300
+    A = rng.normal(size=(n, n)); A *= 1.1 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+    lo, hi = -np.array([0.2, 0.35]), np.array([0.3, 0.25])
+    x0 = rng.normal(size=(n, S)); dA = rng.uniform(-.02, .02, size=(n * n, S)); dB = rng.uniform(-.02, .02, size=(n * m, S))
+    engine.set_problem(A, B, np.eye(n), np.eye(m), np.eye(n), lo, hi, 10)
+    box = engine.simulate_batch(dA, dB, N, 8, x0=x0, want=("J_T", "U", "flags"))
+    engine.set_input_polytope(np.vstack((np.diag(1 / hi), np.diag(1 / lo))))
+    pol = engine.simulate_batch(dA, dB, N, 8, x0=x0, want=("J_T", "U", "flags"))
+    assert relerr(pol["J_T"].cpu().numpy(), box["J_T"].cpu().numpy()) < 1e-12
+    assert torch.equal(pol["flags"], box["flags"]) and bool((box["flags"] & 2).any())
+    with pytest.raises(EngineError):
+        engine.set_input_polytope(np.ones((13, m)))                      # more than 12 rows
+    too_long = engine.mpc_solve_batch(dA[:, :8], dB[:, :8], 40, x0=5 * x0[:, :8])   # N * p = 160 > 128
+    assert bool((too_long["flags"] & 4).all())
+    engine.set_input_polytope(None)
+    again = engine.simulate_batch(dA, dB, N, 8, x0=x0, want=("J_T", "U", "flags"))
+    assert torch.equal(again["J_T"], box["J_T"]) and torch.equal(again["U"], box["U"])
+
+
 def test_clqr_stress_vs_dense_qp(engine):
     """Heavily saturated random problems: batched K2 vs the dense Cholesky+BVLS oracle (per problem: one engine
     problem, 48 initial states)."""
@@ -680,9 +783,9 @@ def test_errors_are_loud(engine):
     from lq_mpc_b200.utils_class import LQ_MPC_Controller
     with pytest.raises(EngineError):
         engine.set_problem(np.eye(5), np.ones((5, 1)), np.eye(5), np.eye(1))        # (5,1) is not compiled
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(EngineError):
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
-                          np.array([[1.0, 1.0]])).solve(np.ones(2), None, None)     # non-box F_u (m = 2 row)
+                          np.array([[1.0, 1.0]])).solve(np.ones(2), None, None)     # F_u with 2 columns, B with 1
     with pytest.raises(EngineError):                                                  # reference window shorter than N
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
                           np.array([[10.0], [-10.0]])).solve(np.ones(2), np.ones((2, 2)), np.zeros((1, 2)))

@@ -51,8 +51,25 @@ def test_input_set_constants_and_box_parsing(known):
     assert abs(U.bar_d_u_solve(F2) - (1.5 ** 2 + 0.45 ** 2)) < 1e-15
     with pytest.raises(NotImplementedError):
         rt.box_from_F(np.array([[1.0, 1.0]]))
+    # general polytopes: vertex enumeration stands in for the two Gurobi models (utils.py:592-650)
+    tri = np.array([[1, 1], [-1, 1], [0, -2.0]])
+    assert not rt.is_box(tri) and rt.is_box(F2)
+    V = rt.polytope_vertices(tri)
+    assert sorted(map(tuple, np.round(V, 12))) == [(-1.5, -0.5), (0.0, 1.0), (1.5, -0.5)]
+    assert abs(U.bar_u_solve(tri) - 2.5) < 1e-15 and abs(U.bar_d_u_solve(tri) - 9.0) < 1e-15
+    with pytest.raises(ValueError):
+        rt.polytope_vertices(np.array([[1.0, 1.0], [-1.0, 1.0]]))        # a cone: unbounded
     with pytest.raises(ValueError):
         U.bar_u_solve(np.array([[10.0]]))                 # unbounded below (Gurobi would report unbounded)
+
+
+def test_vertex_constants_vs_reference_answers(polytope):
+    """bar_u_solve / bar_d_u_solve on general polytopes vs the untouched reference (Gurobi models replaced by vertex
+    enumeration in the oracle's shim; both are maxima of convex functions over the same vertex set)."""
+    for c in polytope:
+        F = np.array(c["F_u"])
+        assert abs(U.bar_u_solve(F) - c["bar_u"]) < 1e-12 * c["bar_u"]
+        assert abs(U.bar_d_u_solve(F) - c["bar_d_u"]) < 1e-12 * c["bar_d_u"]
 
 
 def test_circle_generator_vs_reference_answers(known):

@@ -152,6 +152,70 @@ def test_k2_math_tracking_references(tracking):
         assert 0 < n_act < S
 
 
+def test_k2_math_general_polytope(polytope):
+    """pclqr.cuh (stage-wise projected Riccati sweeps) vs the untouched reference's answers, vs the dense active-set
+    oracle on random polytopes (m = 1..4, up to 9 rows), bit-level agreement with the box solver when the polytope IS
+    a box, and a degenerate polytope (duplicate + redundant rows, three rows through one vertex) with references."""
+    from tests.conftest import polytope_case, random_polytope
+    for c in map(polytope_case, polytope):
+        n = c["n"]
+        a = (c["A"], c["B"], c["Q"], c["R"], c["Q"], None, None, c["dA"].reshape(-1, 1), c["dB"].reshape(-1, 1))
+        sol = hm.mpc(0, *a, c["N"], x0_soa=c["x0"].reshape(n, 1), F_u=c["F_u"])
+        assert abs(sol["V"][0, 0] - c["V_N"]) < TOL * abs(c["V_N"])
+        assert np.max(np.abs(sol["u0"][0, :, 0] - c["u_0"])) < 1e-10
+        sim = hm.mpc(1, *a, c["N"], T=c["T"], x0_soa=c["x0"].reshape(n, 1), F_u=c["F_u"])
+        assert abs(sim["J_T"][0] - c["J_T"]) < TOL * abs(c["J_T"])
+        assert np.max(np.abs(sim["U"][:, :, 0].T - c["U"])) < 1e-10 and not (sim["flags"][0, 0] & ~2)
+    rng = np.random.default_rng(7)
+    n_act = tot = 0
+    for n, m, p in [(2, 1, 2), (2, 2, 3), (2, 2, 5), (3, 2, 6), (4, 2, 8), (3, 3, 6), (4, 4, 8), (3, 3, 9)]:
+        for rep in range(2):
+            N = int(rng.integers(2, min(12, 128 // p) + 1))
+            A = rng.normal(size=(n, n)); A *= rng.uniform(0.6, 1.2) / np.max(np.abs(np.linalg.eigvals(A)))
+            B = rng.normal(size=(n, m)); Q = rng.uniform(0.5, 3) * np.eye(n); R = rng.uniform(0.1, 2) * np.eye(m)
+            if rep:
+                Mq, Mr = rng.normal(size=(n, n)), rng.normal(size=(m, m))
+                Q, R = Mq @ Mq.T + 0.3 * np.eye(n), Mr @ Mr.T + 0.2 * np.eye(m)
+            F = random_polytope(rng, m, p, 0.15, 0.45)
+            S = 12
+            x0 = rng.normal(size=(n, S)) * rng.uniform(0.2, 1.5)
+            dA = rng.uniform(-0.03, 0.03, size=(n * n, S)); dB = rng.uniform(-0.03, 0.03, size=(n * m, S))
+            sol = hm.mpc(0, A, B, Q, R, Q, None, None, dA, dB, N, x0_soa=x0, F_u=F)
+            assert not np.any(sol["flags"] & ~2)
+            for s in range(S):
+                u, V, act = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, None, None,
+                                        x0[:, s], F_u=F)
+                assert abs(sol["V"][0, s] - V) < TOL * abs(V) and np.max(np.abs(sol["u0"][0, :, s] - u)) < 1e-9
+                n_act += int(act); tot += 1
+    assert tot // 4 < n_act < tot
+    for n, m in [(2, 1), (3, 2), (4, 2), (3, 3)]:                       # a box handed over as a polytope
+        N = 6
+        A = rng.normal(size=(n, n)); A *= 1.1 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+        Q, R = np.eye(n), 0.5 * np.eye(m)
+        lo, hi = -rng.uniform(0.1, 0.4, m), rng.uniform(0.1, 0.4, m)
+        F = np.vstack((np.diag(1 / hi), np.diag(1 / lo)))
+        S = 24
+        x0 = rng.normal(size=(n, S)); dA = rng.uniform(-.02, .02, size=(n * n, S)); dB = rng.uniform(-.02, .02, size=(n * m, S))
+        a = hm.mpc(1, A, B, Q, R, Q, lo, hi, dA, dB, N, T=8, x0_soa=x0)
+        b = hm.mpc(1, A, B, Q, R, Q, None, None, dA, dB, N, T=8, x0_soa=x0, F_u=F)
+        assert relerr(b["J_T"], a["J_T"]) < 1e-12 and np.max(np.abs(a["U"] - b["U"])) < 1e-12
+        assert np.array_equal(a["flags"], b["flags"]) and np.any(a["flags"] & 2)
+    F = np.array([[1, 0], [0, 1], [-1, 0], [0, -1], [0.5, 0.5], [1, 0], [0.25, 0.25]]) / 0.3
+    n, m, N, S = 3, 2, 7, 24
+    A = rng.normal(size=(n, n)); A *= 1.15 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+    Q, R = 2 * np.eye(n), np.eye(m)
+    x0 = rng.normal(size=(n, S)) * 1.5
+    z = np.zeros
+    xr, ur = rng.normal(size=(n, N)) * 0.2, rng.normal(size=(m, N)) * 0.1
+    for refs in ((None, None), (xr, ur)):
+        sol = hm.mpc(0, A, B, Q, R, Q, None, None, z((n * n, S)), z((n * m, S)), N, x0_soa=x0, F_u=F, x_ref=refs[0],
+                     u_ref=refs[1])
+        assert not np.any(sol["flags"] & ~2)
+        for s in range(S):
+            u, V, _ = o.mpc_solve(N, A, B, Q, R, Q, None, None, x0[:, s], F_u=F, x_ref=refs[0], u_ref=refs[1])
+            assert abs(sol["V"][0, s] - V) < TOL * abs(V) and np.max(np.abs(sol["u0"][0, :, s] - u)) < 1e-9
+
+
 def _golden_inputs(golden, rows):
     eA = np.ascontiguousarray(golden["error_A_f"][:, :, rows, :]).reshape(4, -1)
     eB = np.ascontiguousarray(golden["error_B_f"][:, :, rows, :]).reshape(2, -1)

@@ -145,6 +145,51 @@ def test_oracle_tracking_references(tracking):
     assert 0 < n_act < len(tracking)
 
 
+def test_dense_inequality_qp_oracle():
+    """oracle/qp_dense.py (general polytopes): equals the exact box solver on boxes and SLSQP (loosely) otherwise."""
+    from scipy.optimize import minimize
+    from oracle.qp_dense import ineq_qp, polytope_vertices
+    rng = np.random.default_rng(0)
+    for _ in range(40):
+        nz = int(rng.integers(2, 12))
+        M = rng.normal(size=(nz, nz)); H = M @ M.T + 0.1 * np.eye(nz); g = rng.normal(size=nz) * 3
+        lo, hi = -rng.uniform(0.1, 1, nz), rng.uniform(0.1, 1, nz)
+        z, _ = ineq_qp(H, g, np.vstack((np.diag(1 / hi), np.diag(1 / lo))), np.ones(2 * nz))
+        assert np.max(np.abs(z - o.box_qp(H, g, lo, hi))) < 1e-10
+    for _ in range(10):
+        nz = 6
+        M = rng.normal(size=(nz, nz)); H = M @ M.T + 0.1 * np.eye(nz); g = rng.normal(size=nz) * 3
+        C = rng.normal(size=(14, nz)); d = np.ones(14)
+        z, W = ineq_qp(H, g, C, d)
+        r = minimize(lambda x: x @ H @ x + 2 * g @ x, np.zeros(nz), jac=lambda x: 2 * H @ x + 2 * g, method="SLSQP",
+                     constraints=[{"type": "ineq", "fun": lambda x: d - C @ x, "jac": lambda x: -C}],
+                     options={"ftol": 1e-14, "maxiter": 500})
+        assert np.max(np.abs(z - r.x)) < 1e-5 and np.all(C @ z <= 1 + 1e-10)
+    V = polytope_vertices(np.array([[1, 1], [-1, 1], [0, -2.0]]))
+    assert sorted(map(tuple, np.round(V, 12))) == [(-1.5, -0.5), (0.0, 1.0), (1.5, -0.5)]
+
+
+def test_oracle_general_polytope_cases(polytope):
+    """General F_u (rows coupling the inputs, utils_class.py:81): 16 solves / closed loops / energy_bound calls of the
+    untouched reference (its QPs solved by the dense active-set shim), half of them constraint-active."""
+    from tests.conftest import polytope_case
+    n_act = 0
+    for c in map(polytope_case, polytope):
+        Ah, Bh = c["A"] + c["dA"], c["B"] + c["dB"]
+        u0, V, act = o.mpc_solve(c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], None, None, c["x0"], F_u=c["F_u"])
+        assert abs(V - c["V_N"]) < TOL * abs(c["V_N"]) and np.max(np.abs(u0 - c["u_0"])) < 1e-10
+        sim = o.simulate(c["T"], c["N"], Ah, Bh, c["Q"], c["R"], c["Q"], None, None, c["x0"], c["A"], c["B"],
+                         F_u=c["F_u"])
+        n_act += sim["n_active"] > 0
+        assert abs(sim["J_T"] - c["J_T"]) < TOL * abs(c["J_T"]) and np.max(np.abs(sim["U"] - c["U"])) < 1e-10
+        bu, bdu = o.bar_u_poly(c["F_u"])
+        assert abs(bu - c["bar_u"]) < 1e-12 * bu and abs(bdu - c["bar_d_u"]) < 1e-12 * bdu
+        bnd = o.energy_bound(Ah, Bh, c["Q"], c["R"], None, None, c["N"], c["e"], c["e"], c["x0"], [0.1, 1, 0.6],
+                             F_u=c["F_u"])
+        assert abs(bnd["alpha"] - c["alpha"]) < TOL * c["alpha"] and abs(bnd["beta"] - c["beta"]) < TOL * c["beta"]
+    assert 4 <= n_act < len(polytope)
+
+
 # ------------------------------------------------------------------------------------------- analytic cross-checks
 def test_riccati_equals_condensed_qp_when_unconstrained():
     """utils_class.py:59-91 unconstrained == Riccati: u_0 = K_0 x0, V_N = x0' P_0 x0."""
