@@ -106,6 +106,10 @@ class ClockSampler:
 # ---------------------------------------------------------------------------------------------------- CPU arm
 def _cpu_worker(args):
     os.environ["OMP_NUM_THREADS"] = "1"
+    try:                                    # the GPU arm may have bound its process to one NUMA node: the CPU arm
+        os.sched_setaffinity(0, range(os.cpu_count() or 1))            # gets every core of the box
+    except OSError:
+        pass
     first, count, (n, m, N, e) = args
     import numpy as np  # noqa
     from oracle import np_batched as nb
@@ -193,6 +197,8 @@ def run_ours(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
     torch.cuda.set_device(local)
+    from lq_mpc_b200.runtime import bind_to_gpu_numa
+    numa_cpus = bind_to_gpu_numa(local)          # pinned host shards below are then first-touched on the GPU's node
     eng = Engine(local)
     A, B, Q, R = sp.synth_problem(N_DIM, M_DIM, seed=SEED_PROBLEM)
     tiled = WL["tiled"]
@@ -326,6 +332,8 @@ def run_ours(args):
             "e2e": {"value": evals / e2e_s, "unit": "evals/s",
                     "h2d_bytes_per_step": int(S * (n * n + n * m + n) * 8),
                     "d2h_bytes_per_step": int(S * (3 * 8 + 4)), "matches_device_path": same,
+                    "host_numa_binding": ("process pinned to the %d cores NVML reports local to its GPU" % len(numa_cpus))
+                    if numa_cpus else "none (NVML affinity unavailable)",
                     "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)" if not tiled
                     else "lqmpc_eval_batch_tiled_host (pinned host array-of-matrices in, J/rho/ratio/flags tables out)"},
             "gpu_launches": int(launches),

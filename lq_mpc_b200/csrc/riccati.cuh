@@ -96,21 +96,22 @@ LQ_HD bool lyapunov_doubling(const double* Acl, const double* W, double* S) {
   (void)zero;
   for (int it = 0; it < 64; ++it) {
     mm<n, n, n>(S, M, SM);
-    double tmax = 0.0, smax = 0.0;
+    uint32_t thi = 0, shi = 0;                         // max |increment|, max |S| as exponent words (abs_hi)
     LQ_UNROLL for (int i = 0; i < n; ++i)
       LQ_UNROLL for (int j = i; j < n; ++j) {
         double acc = 0.0;
         LQ_UNROLL for (int k = 0; k < n; ++k) acc = fma(M[k * n + i], SM[k * n + j], acc);
         T[i * n + j] = acc;
-        tmax = dmax(tmax, fabs(acc));
+        thi = umax32(thi, abs_hi(acc));
       }
     LQ_UNROLL for (int i = 0; i < n; ++i)
       LQ_UNROLL for (int j = i; j < n; ++j) {
         const double v = S[i * n + j] + T[i * n + j];
         S[i * n + j] = v; S[j * n + i] = v;
-        smax = dmax(smax, fabs(v));
+        shi = umax32(shi, abs_hi(v));
       }
-    if (!(tmax > 1e-18 * smax)) return tmax == tmax;   // converged (false on NaN)
+    if ((thi >> 20) == 0x7ffu || (shi >> 20) == 0x7ffu) return false;             // NaN / Inf
+    if (!(from_abs_hi(thi) > 1e-18 * from_abs_hi(shi))) return true;              // converged
     mm<n, n, n>(M, M, SM);
     LQ_UNROLL for (int i = 0; i < n * n; ++i) M[i] = SM[i];
   }

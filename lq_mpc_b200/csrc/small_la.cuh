@@ -9,6 +9,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define LQ_HD __host__ __device__ __forceinline__
@@ -25,6 +26,30 @@ namespace lq {
 LQ_HD double dmax(double a, double b) { return a > b ? a : b; }
 LQ_HD double dmin(double a, double b) { return a < b ? a : b; }
 LQ_HD double dsign(double a, double b) { return b >= 0.0 ? fabs(a) : -fabs(a); }
+
+// Sign-stripped high word of a double: for finite values the order of |v| is the order of this word up to a relative
+// 2^-20, and NaN / Inf sort above every finite value. Magnitude tracking for convergence tests runs on it so that it
+// costs integer-pipe instructions (LOP + IMNMX) instead of FP64-pipe compares (DSETP + 2 SEL per dmax).
+LQ_HD uint32_t abs_hi(double v) {
+#if defined(__CUDA_ARCH__)
+  return (uint32_t)__double2hiint(v) & 0x7fffffffu;
+#else
+  uint64_t b;
+  memcpy(&b, &v, sizeof(b));
+  return (uint32_t)(b >> 32) & 0x7fffffffu;
+#endif
+}
+LQ_HD double from_abs_hi(uint32_t h) {
+#if defined(__CUDA_ARCH__)
+  return __hiloint2double((int)h, 0);
+#else
+  const uint64_t b = (uint64_t)h << 32;
+  double v;
+  memcpy(&v, &b, sizeof(v));
+  return v;
+#endif
+}
+LQ_HD uint32_t umax32(uint32_t a, uint32_t b) { return a > b ? a : b; }
 
 // Reciprocal for normal, non-zero x: hardware seed (MUFU.RCP64H, >= 20 good bits) + two Newton steps = 1 MUFU +
 // 4 DFMA and <= 1 ulp error, versus ~12 FP64-pipe instructions plus a slow-path call for an IEEE `1.0 / x`.

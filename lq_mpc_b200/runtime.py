@@ -42,6 +42,35 @@ def box_from_F(F_u):
     return lo, hi
 
 
+def bind_to_gpu_numa(device_index: int):
+    """Pin the calling process to the CPU cores NVML reports as local to GPU `device_index` (its NUMA node), so that
+    host buffers allocated afterwards (first touch) sit behind the same root complex as the GPU: the host-buffer entry
+    points (`lqmpc_eval_batch_host`, `..._tiled_host`) are PCIe-bound, and with one process per GPU the copies of all
+    ranks otherwise meet on one socket's memory controllers. Returns the core list, or None when NVML is unavailable
+    (the process is then left as it was)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        idx = device_index
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if device_index < len(ids) and ids[device_index].isdigit():
+                idx = int(ids[device_index])
+        h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = [64 * w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1]
+        allowed = os.sched_getaffinity(0)
+        cpus = [c for c in cpus if c in allowed]
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def is_box(F_u) -> bool:
     """Every row of F_u has exactly one non-zero (the only shape the reference's own scripts build)."""
     F_u = np.atleast_2d(np.asarray(F_u, dtype=np.float64))
