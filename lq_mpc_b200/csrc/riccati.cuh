@@ -113,7 +113,12 @@ LQ_HD bool lyapunov_doubling(const double* Acl, const double* W, double* S) {
     if ((thi >> 20) == 0x7ffu || (shi >> 20) == 0x7ffu) return false;             // NaN / Inf
     if (!(from_abs_hi(thi) > 1e-18 * from_abs_hi(shi))) return true;              // converged
     mm<n, n, n>(M, M, SM);
-    LQ_UNROLL for (int i = 0; i < n * n; ++i) M[i] = SM[i];
+    uint32_t mhi = 0;
+    LQ_UNROLL for (int i = 0; i < n * n; ++i) { M[i] = SM[i]; mhi = umax32(mhi, abs_hi(SM[i])); }
+    // the next increment is bounded entrywise by n^2 max|M|^2 max|S| (S is PSD and non-decreasing, its largest entry
+    // sits on the diagonal): once that is below the threshold the iteration that would only confirm it is skipped
+    const double mb = from_abs_hi(mhi) * 1.000002;                       // abs_hi truncates the mantissa by < 2^-20
+    if ((double)(n * n) * mb * mb <= 1e-18) return true;
   }
   return false;
 }
