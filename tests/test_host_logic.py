@@ -63,6 +63,15 @@ def test_input_set_constants_and_box_parsing(known):
         U.bar_u_solve(np.array([[10.0]]))                 # unbounded below (Gurobi would report unbounded)
 
 
+def test_numa_binding_is_optional():
+    """bind_to_gpu_numa never raises: without NVML / a GPU it returns None and leaves the affinity mask alone."""
+    import os
+    before = os.sched_getaffinity(0)
+    r = rt.bind_to_gpu_numa(0)
+    assert r is None or set(r) <= before
+    os.sched_setaffinity(0, before)
+
+
 def test_vertex_constants_vs_reference_answers(polytope):
     """bar_u_solve / bar_d_u_solve on general polytopes vs the untouched reference (Gurobi models replaced by vertex
     enumeration in the oracle's shim; both are maxima of convex functions over the same vertex set)."""
