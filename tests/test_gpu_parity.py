@@ -696,6 +696,37 @@ def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
         assert np.array_equal(hp[k].numpy(), g[k]), k
 
 
+def test_k4_full_size_properties(engine):
+    """BASELINE cfg 5 size (n = 32, m = 8, N = 30, 125 000 samples per GPU): size-independent properties instead of an
+    oracle run — J is quadratic in x0 (J(2 x0) = 4 J(x0) exactly in binary FP), rho and the ratio do not depend on
+    the scaling, the result does not depend on where a sample sits in the batch (persistent grid, 5 CTAs/SM), no entry
+    is left pending for the QR kernel's flags, a subsample matches the oracle."""
+    import torch
+    from oracle import np_batched as nb
+    n, m, N, S = 32, 8, 30, 125_000
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    engine.set_problem_tiled(A, B, Q, R, Q, 30)
+    g = torch.Generator(device="cuda").manual_seed(11)
+    dA = (torch.rand((S, n, n), device="cuda", dtype=torch.float64, generator=g) - 0.5) * 2e-3
+    dB = (torch.rand((S, n, m), device="cuda", dtype=torch.float64, generator=g) - 0.5) * 2e-3
+    x0 = torch.randn((S, n), device="cuda", dtype=torch.float64, generator=g)
+    r1 = engine.eval_batch_tiled(dA, dB, x0, N, N)
+    r2 = engine.eval_batch_tiled(dA, dB, 2.0 * x0, N, N)
+    assert torch.equal(r2["J"], 4.0 * r1["J"]) and torch.equal(r2["rho"], r1["rho"])
+    assert torch.equal(r2["ratio"], r1["ratio"])
+    assert int((r1["flags"] != 0).sum()) == 0
+    assert float(r1["ratio"].min()) >= 1.0 - 1e-9 and float(r1["rho"].max()) < 1.0
+    perm = torch.randperm(S, device="cuda", generator=g)
+    r3 = engine.eval_batch_tiled(dA[perm], dB[perm], x0[perm], N, N)
+    assert torch.equal(r3["J"], r1["J"][:, perm]) and torch.equal(r3["rho"], r1["rho"][:, perm])
+    idx = torch.arange(0, S, 997, device="cuda")
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA[idx].cpu().numpy(), dB[idx].cpu().numpy(), x0[idx].cpu().numpy(), N, N)
+    assert relerr(r1["J"][:, idx].cpu().numpy(), ref["J"]) < TOL
+    assert relerr(r1["rho"][:, idx].cpu().numpy(), ref["rho"]) < TOL
+    assert relerr(r1["ratio"][:, idx].cpu().numpy(), ref["ratio"]) < TOL
+
+
 def test_k4_spectral_radius_by_squaring_and_qr_fallback(engine, monkeypatch):
     """k4a's spectral radius (rescaled repeated squaring, accepted when two depths agree) vs the QR kernel on the same
     batch, and the cases squaring must NOT decide alone: a 16 x 16 Jordan block (estimates at the two depths disagree
