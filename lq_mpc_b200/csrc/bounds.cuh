@@ -168,6 +168,10 @@ LQ_HD int sturm_count(const WsView& ws, int64_t od, int64_t oe, int k, double x,
   return cnt;
 }
 
+// Smallest and largest eigenvalue of the tridiagonal (d, e) by Sturm counts. Both searches advance together and each
+// pass over the matrix evaluates THREE shifts per search (quarter points: 2 bits per pass): one load of (d_i, e_i)
+// feeds six independent pivot recurrences, so the workspace is streamed ~26 times instead of ~104 and the reciprocal
+// chains overlap (the one-shift-per-pass version was bound by the latency of its divisions and of the strided loads).
 LQ_HD_NOINLINE void ws_tridiag_extremes(const WsView& ws, int64_t od, int64_t oe, int k, double* lmin, double* lmax) {
   double gl = ws[od], gu = ws[od], emax = 0.0;
   for (int i = 0; i < k; ++i) {
@@ -182,28 +186,50 @@ LQ_HD_NOINLINE void ws_tridiag_extremes(const WsView& ws, int64_t od, int64_t oe
   gl -= 2.2e-16 * span * k + 1e-300;
   gu += 2.2e-16 * span * k + 1e-300;
   const double pivmin = dmax(1e-300, 2.3e-308 * dmax(1.0, emax * emax));
-  // smallest eigenvalue: largest x with count(x) == 0
-  {
-    double lo = gl, hi = gu;
-    for (int it = 0; it < 200; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      if (!(mid > lo && mid < hi)) break;
-      if (sturm_count(ws, od, oe, k, mid, pivmin) >= 1) hi = mid; else lo = mid;
-      if (hi - lo <= 4.5e-16 * dmax(fabs(lo), fabs(hi))) break;
+  // search 0: smallest eigenvalue = largest x with count(x) == 0   (target count 1)
+  // search 1: largest eigenvalue  = smallest x with count(x) == k  (target count k)
+  double lo[2] = {gl, gl}, hi[2] = {gu, gu};
+  bool live[2] = {true, true};
+  for (int it = 0; it < 200 && (live[0] || live[1]); ++it) {
+    double x[2][3], q[2][3];
+    int cnt[2][3];
+    LQ_UNROLL for (int s = 0; s < 2; ++s) {
+      const double w = hi[s] - lo[s];
+      LQ_UNROLL for (int j = 0; j < 3; ++j) {
+        x[s][j] = fma(w, 0.25 * (j + 1), lo[s]);
+        double q0 = ws[od] - x[s][j];
+        if (fabs(q0) < pivmin) q0 = -pivmin;
+        q[s][j] = q0;
+        cnt[s][j] = (q0 < 0.0);
+      }
     }
-    *lmin = 0.5 * (lo + hi);
-  }
-  // largest eigenvalue: smallest x with count(x) == k
-  {
-    double lo = gl, hi = gu;
-    for (int it = 0; it < 200; ++it) {
-      const double mid = 0.5 * (lo + hi);
-      if (!(mid > lo && mid < hi)) break;
-      if (sturm_count(ws, od, oe, k, mid, pivmin) >= k) hi = mid; else lo = mid;
-      if (hi - lo <= 4.5e-16 * dmax(fabs(lo), fabs(hi))) break;
+    for (int i = 1; i < k; ++i) {
+      const double e = ws[oe + i], di = ws[od + i];
+      const double e2 = e * e;
+      LQ_UNROLL for (int s = 0; s < 2; ++s)
+        LQ_UNROLL for (int j = 0; j < 3; ++j) {
+          double qn = fma(-e2, rcp(q[s][j]), di - x[s][j]);
+          if (fabs(qn) < pivmin) qn = -pivmin;
+          q[s][j] = qn;
+          cnt[s][j] += (qn < 0.0);
+        }
     }
-    *lmax = 0.5 * (lo + hi);
+    LQ_UNROLL for (int s = 0; s < 2; ++s) {
+      if (!live[s]) continue;
+      const int target = (s == 0) ? 1 : k;
+      // counts are non-decreasing in x: the first quarter point that reaches the target bounds the eigenvalue above
+      double nlo = lo[s], nhi = hi[s];
+      if (cnt[s][0] >= target) nhi = x[s][0];
+      else if (cnt[s][1] >= target) { nlo = x[s][0]; nhi = x[s][1]; }
+      else if (cnt[s][2] >= target) { nlo = x[s][1]; nhi = x[s][2]; }
+      else nlo = x[s][2];
+      if (!(nlo > lo[s] || nhi < hi[s])) live[s] = false;            // the quarter points no longer separate lo / hi
+      lo[s] = nlo; hi[s] = nhi;
+      if (hi[s] - lo[s] <= 4.5e-16 * dmax(fabs(lo[s]), fabs(hi[s]))) live[s] = false;
+    }
   }
+  *lmin = 0.5 * (lo[0] + hi[0]);
+  *lmax = 0.5 * (lo[1] + hi[1]);
 }
 
 template <int n, int m>

@@ -16,6 +16,12 @@ namespace {
 
 constexpr int kWarps = 4;
 
+__host__ __device__ inline int lq_gram_ldc(int k) {
+  int ld = (k + 1) & ~1;              // even, >= k
+  if (((ld >> 1) & 1) == 0) ld += 2;  // ld / 2 odd
+  return ld;
+}
+
 __device__ __forceinline__ double wsum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -35,14 +41,18 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
                                                                     const GramArgs a, const int per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
-  const int N = a.N, k = N * m, LDC = k + 1;
+  // leading dimension: even with LDC/2 odd — rows are 16-byte aligned and the 128-bit loads of 8 consecutive rows fall
+  // into 8 distinct bank groups (no conflicts), so the Householder loops move TWO entries per shared-memory
+  // instruction (the kernel is bound by instruction issue: ~1 LDS/STS per FMA with 64-bit accesses)
+  const int N = a.N, k = N * m, LDC = lq_gram_ldc(k);
   double* base = reinterpret_cast<double*>(smem_raw) + (int64_t)wib * per_warp;
+  const int ke = (k + 1) & ~1;         // vectors padded to an even length: 16-byte aligned starts
   double* C = base;                    // k x LDC
-  double* G = C + k * LDC;             // N x (n*m): G_d = A^d B
-  double* v = G + N * n * m;           // k
-  double* q = v + k;                   // k
-  double* dd = q + k;                  // k  diagonal of the tridiagonal form
-  double* e2 = dd + k;                 // k  squared off-diagonal
+  double* v = C + k * LDC;             // k
+  double* q = v + ke;                  // k
+  double* dd = q + ke;                 // k  diagonal of the tridiagonal form
+  double* e2 = dd + ke;                // k  squared off-diagonal
+  double* G = e2 + ke;                 // N x (n*m): G_d = A^d B
   const int64_t wid = (int64_t)blockIdx.x * kWarps + wib, nw = (int64_t)gridDim.x * kWarps;
 #define C_(i, j) C[(i) * LDC + (j)]
   for (int64_t s = wid; s < a.S; s += nw) {
@@ -118,14 +128,21 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
       __syncwarp();
       if (lane == 0) v[l] = f0 - g0;
       __syncwarp();
-      // p = C v / h on the leading (l+1) block; f = p . v
+      // p = C v / h on the leading (l+1) block; f = p . v   (two columns per shared-memory instruction)
       const double ih = 1.0 / h;
+      const int lp = (l + 1) & ~1;                          // paired part of 0..l
       double fl = 0.0;
       for (int j = lane; j <= l; j += 32) {
-        double g = 0.0;
+        double g0 = 0.0, g1 = 0.0;
         const double* row = C + j * LDC;
-        for (int kk = 0; kk <= l; ++kk) g = fma(row[kk], v[kk], g);
-        g *= ih;
+        for (int kk = 0; kk < lp; kk += 2) {
+          const double2 c2 = *reinterpret_cast<const double2*>(row + kk);
+          const double2 v2 = *reinterpret_cast<const double2*>(v + kk);
+          g0 = fma(c2.x, v2.x, g0);
+          g1 = fma(c2.y, v2.y, g1);
+        }
+        if (lp <= l) g0 = fma(row[l], v[l], g0);
+        const double g = (g0 + g1) * ih;
         q[j] = g;
         fl = fma(g, v[j], fl);
       }
@@ -136,9 +153,17 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
       __syncwarp();
       // rank-2 update of the whole leading block (both triangles are kept)
       for (int j = lane; j <= l; j += 32) {
-        const double vj = v[j], qj = q[j];
+        const double nvj = -v[j], nqj = -q[j];
         double* row = C + j * LDC;
-        for (int kk = 0; kk <= l; ++kk) row[kk] -= fma(vj, q[kk], qj * v[kk]);
+        for (int kk = 0; kk < lp; kk += 2) {
+          double2 c2 = *reinterpret_cast<const double2*>(row + kk);
+          const double2 v2 = *reinterpret_cast<const double2*>(v + kk);
+          const double2 q2 = *reinterpret_cast<const double2*>(q + kk);
+          c2.x = fma(nvj, q2.x, fma(nqj, v2.x, c2.x));
+          c2.y = fma(nvj, q2.y, fma(nqj, v2.y, c2.y));
+          *reinterpret_cast<double2*>(row + kk) = c2;
+        }
+        if (lp <= l) row[l] = fma(nvj, q[l], fma(nqj, v[l], row[l]));
       }
       __syncwarp();
     }
@@ -161,7 +186,7 @@ template <int n, int m>
 int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri) {
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int k = N * m;
-  const int per_warp = ((k * (k + 1) + N * n * m + 4 * k) + 1) & ~1;
+  const int per_warp = ((k * lq_gram_ldc(k) + N * n * m + 4 * ((k + 1) & ~1)) + 1) & ~1;
   const size_t smem = (size_t)kWarps * per_warp * sizeof(double);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
@@ -183,7 +208,7 @@ int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB,
 // shared-memory footprint decides eligibility: 4 warps x (k (k+1) + ...) doubles must fit one CTA
 bool lq_gram_warp_eligible(int n, int m, int N) {
   const int k = N * m;
-  const size_t per_warp = (size_t)(k * (k + 1) + N * n * m + 4 * k + 2);
+  const size_t per_warp = (size_t)(k * lq_gram_ldc(k) + N * n * m + 4 * ((k + 1) & ~1) + 2);
   return k >= 12 && (size_t)kWarps * per_warp * sizeof(double) <= 200 * 1024;
 }
 
