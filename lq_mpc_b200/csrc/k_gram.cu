@@ -14,7 +14,8 @@
 
 namespace {
 
-constexpr int kWarps = 4;
+constexpr int kWarps = 4;      // default CTA size in warps (eligibility test); the launcher picks 1..8 per launch
+constexpr int kMaxWarps = 8;
 
 __host__ __device__ inline int lq_gram_ldc(int k) {
   int ld = (k + 1) & ~1;              // even, >= k
@@ -37,7 +38,7 @@ struct GramArgs {
 };
 
 template <int n, int m>
-__global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+__global__ void __launch_bounds__(kMaxWarps * 32) gram_extremes_kernel(const __grid_constant__ lq::Problem<n, m> pb,
                                                                     const GramArgs a, const int per_warp) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -53,7 +54,8 @@ __global__ void __launch_bounds__(kWarps * 32) gram_extremes_kernel(const __grid
   double* dd = q + ke;                 // k  diagonal of the tridiagonal form
   double* e2 = dd + ke;                // k  squared off-diagonal
   double* G = e2 + ke;                 // N x (n*m): G_d = A^d B
-  const int64_t wid = (int64_t)blockIdx.x * kWarps + wib, nw = (int64_t)gridDim.x * kWarps;
+  const int wpc = blockDim.x >> 5;     // warps per CTA, chosen by the launcher
+  const int64_t wid = (int64_t)blockIdx.x * wpc + wib, nw = (int64_t)gridDim.x * wpc;
 #define C_(i, j) C[(i) * LDC + (j)]
   for (int64_t s = wid; s < a.S; s += nw) {
     // ---- G_d = A^^d B^ (every lane runs the tiny recurrence; lane d % 32 stores G_d)
@@ -187,18 +189,26 @@ int launch_gram_t(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB,
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int k = N * m;
   const int per_warp = ((k * lq_gram_ldc(k) + N * n * m + 4 * ((k + 1) & ~1)) + 1) & ~1;
-  const size_t smem = (size_t)kWarps * per_warp * sizeof(double);
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  // The kernel is latency-bound (profile r01k3g2: 8 warps/SM at k = 50, issue slots 28 %): pick the CTA size that
+  // puts the most warps on an SM for this k (shared memory per warp grows with k^2; 1 KB is reserved per CTA).
+  int best_w = 1, best_per_sm = 1, best_total = 0;
+  for (int w = kMaxWarps; w >= 1; --w) {
+    const size_t sm_w = (size_t)w * per_warp * sizeof(double);
+    if (sm_w > 200 * 1024) continue;
+    cudaFuncSetAttribute(gram_extremes_kernel<n, m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_w);
+    int ps = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ps, gram_extremes_kernel<n, m>, w * 32, sm_w);
+    if (ps * w > best_total) { best_total = ps * w; best_w = w; best_per_sm = ps; }
+  }
+  const size_t smem = (size_t)best_w * per_warp * sizeof(double);
   cudaFuncSetAttribute(gram_extremes_kernel<n, m>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int per_sm = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, gram_extremes_kernel<n, m>, kWarps * 32, smem);
-  if (per_sm < 1) per_sm = 1;
-  int64_t blocks = (int64_t)sms * per_sm;
-  const int64_t want = (S + kWarps - 1) / kWarps;
+  int64_t blocks = (int64_t)sms * best_per_sm;
+  const int64_t want = (S + best_w - 1) / best_w;
   if (blocks > want) blocks = want;
   GramArgs a{S, dA, dB, N, tri};
-  gram_extremes_kernel<n, m><<<(unsigned)blocks, kWarps * 32, smem, ctx->stream>>>(pb, a, per_warp);
+  gram_extremes_kernel<n, m><<<(unsigned)blocks, best_w * 32, smem, ctx->stream>>>(pb, a, per_warp);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "gram_extremes_kernel launch");
 }
