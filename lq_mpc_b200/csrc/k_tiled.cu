@@ -868,13 +868,13 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
   KernT kerns[4] = {tiled_eval_kernel<n, m, false, 4>, tiled_eval_kernel<n, m, true, 4>,
                     tiled_eval_kernel<n, m, false, 5>, tiled_eval_kernel<n, m, true, 5>};
   KernT kern = kerns[(occ5 ? 2 : 0) + (use_dmma ? 1 : 0)];
-  static bool attr_done = false;
-  if (!attr_done) {
+  static uint64_t attr_done = 0;                             // function attributes are per DEVICE: one bit each
+  if (!((attr_done >> (ctx->device & 63)) & 1)) {
     for (KernT kf : kerns)
       cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)k4a_smem_bytes<n, m>(5));
     cudaFuncSetAttribute(tiled_rho_kernel<n>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                          (int)((kT / 32) * (n * (n + 1) + 32) * sizeof(double)));
-    attr_done = true;
+    attr_done |= (uint64_t)1 << (ctx->device & 63);
   }
   int per_sm = 1;
   cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kT, smem);
