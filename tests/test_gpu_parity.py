@@ -552,6 +552,22 @@ def test_bounds_detail_vs_oracle(engine):
     assert checked > 40
 
 
+def test_bounds_unit_norm_branch_of_geo_M(engine):
+    """geo_M's exact-equality branch `norm == 1` (utils.py:404-405) on the device: ||diag(1, 0.3)||_2 is exactly 1.0
+    (geometric sum = N - 1), the neighbour 1 - 2^-30 takes the quotient branch; both vs the oracle."""
+    from oracle import np_oracle as o
+    for a11 in (1.0, 1.0 - 2.0 ** -30):
+        A = np.diag([a11, 0.3]); B = np.array([[1.0], [0.5]]); Q = 2 * np.eye(2); R = np.eye(1)
+        lo, hi = np.array([-0.1]), np.array([0.1])
+        engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+        K = -o.dlqr(A, B, Q, R)[0]
+        b = engine.bounds_batch(None, None, 7, 5e-3, 5e-3, 0.05, np.array([0.05, 0.02]), (0.1, 1, 0.6), 0.2, K=K, S=1)
+        assert (float(b["norm_A"].cpu()[0]) == 1.0) == (a11 == 1.0)
+        dec = o.energy_decreasing(A, B, Q, R, lo, hi, 7, 5e-3, 5e-3, K, 0.05)
+        for key in ("xi", "eta", "omega_N1", "omega_N0d5"):
+            assert abs(float(b[key].cpu()[0]) - dec[key]) <= TOL * abs(dec[key]), (a11, key)
+
+
 def test_bounds_long_horizon(engine, example):
     """N = 50 (cfg-sweep upper end): 50 x 50 Gram matrix through the in-kernel tridiagonal/bisection path."""
     from oracle import np_oracle as o

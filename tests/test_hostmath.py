@@ -300,3 +300,22 @@ def test_k3_math_vs_oracle_multi_input():
             bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, 0.01, 0.01, x0[s], p)
             for key, ref in (("xi", dec["xi"]), ("eta", dec["eta"]), ("alpha", bnd["alpha"]), ("beta", bnd["beta"])):
                 assert abs(b[key][s] - ref) <= TOL * abs(ref), (n, m, key)
+
+
+def test_k3_math_unit_norm_branch_of_geo_M():
+    """geo_M's exact-equality branch `norm == 1` (utils.py:404-405): for ||A||_2 == 1.0 the geometric sum is N - 1, not
+    (1 - f^(2N-2)) / (1 - f^2) = 0 / 0. A = diag(1, 0.3) has the 2-norm exactly 1 in LAPACK and in the engine's Jacobi
+    norm alike; a neighbour 1 - 2^-30 takes the other branch. Both must match the oracle."""
+    for a11 in (1.0, 1.0 - 2.0 ** -30):
+        A = np.diag([a11, 0.3]); B = np.array([[1.0], [0.5]]); Q = 2 * np.eye(2); R = np.eye(1)
+        lo, hi = np.array([-0.1]), np.array([0.1])
+        N = 7
+        z = np.zeros
+        x = np.array([[0.05], [0.02]])
+        K = -o.dlqr(A, B, Q, R)[0]
+        b = hm.bounds(A, B, Q, R, lo, hi, z((4, 1)), z((2, 1)), N, np.array([5e-3]), np.array([5e-3]),
+                      np.array([0.05]), x, K.reshape(-1, 1), np.array([0.1, 1, 0.6]), 0.2)
+        assert (b["norm_A"][0] == 1.0) == (a11 == 1.0)
+        dec = o.energy_decreasing(A, B, Q, R, lo, hi, N, 5e-3, 5e-3, K, 0.05)
+        for key in ("xi", "eta", "omega_N1", "omega_N0d5"):
+            assert abs(b[key][0] - dec[key]) <= TOL * abs(dec[key]), (a11, key)
