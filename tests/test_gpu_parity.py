@@ -23,7 +23,7 @@ def _soa(dA, dB, x0):
 
 # ------------------------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
-                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02)])
+                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02), (2, 2, 0.1), (3, 1, 0.1)])
 def test_k1_matches_oracle(engine, n, m, e):
     from oracle import np_batched as nb
     A, B, Q, R = nb.synth_problem(n, m, seed=0)
@@ -669,7 +669,8 @@ def test_golden_column_stats(engine, golden):
 
 
 # ------------------------------------------------------------------------------------------------------- K4
-@pytest.mark.parametrize("n,m,e,dmma", [(32, 8, 1e-3, "0"), (32, 8, 1e-3, "1"), (16, 4, 5e-3, "0"), (32, 8, 0.2, "1")])
+@pytest.mark.parametrize("n,m,e,dmma", [(32, 8, 1e-3, "0"), (32, 8, 1e-3, "1"), (16, 4, 5e-3, "0"), (16, 4, 5e-3, "1"),
+                                        (32, 8, 0.2, "1")])
 def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
     """Large-n path (CTA per sample, TMA-staged operands, warp-synchronous QR) vs the batched oracle: nested
     horizons, the single-horizon buffer plan, DFMA and FP64-tensor-core GEMM variants, and (e = 0.2) a batch

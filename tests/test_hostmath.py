@@ -67,7 +67,7 @@ def test_closed_form_spectral_radius_is_trusted_only_when_accurate(n):
 
 
 @pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
-                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02)])
+                                   (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02), (2, 2, 0.1), (3, 1, 0.1)])
 def test_k1_math_vs_batched_oracle(n, m, e):
     A, B, Q, R = nb.synth_problem(n, m, seed=0)
     S = 257
