@@ -467,15 +467,19 @@ int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, c
 int lqmpc_set_input_polytope(lqmpc_ctx* ctx, int p, const double* F_host) {
   if (!ctx) return LQMPC_EINVAL;
   if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  // validate first: a rejected call leaves the installed polytope (or the box) as it was
+  const bool clear = (p <= 0 || !F_host);
+  if (!clear) {
+    if (p > lq::kPolyMaxRows) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: at most 12 rows");
+    for (int e = 0; e < p * ctx->m; ++e)
+      if (!(fabs(F_host[e]) <= 1.79e308)) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: non-finite entry");
+  }
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->poly_dev) { cudaFree(ctx->poly_dev); ctx->poly_dev = nullptr; }
   ctx->poly_p = 0;
-  if (p <= 0 || !F_host) return LQMPC_OK;                              // cleared: the box of lqmpc_set_problem
-  if (p > lq::kPolyMaxRows) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: at most 12 rows");
+  if (clear) return LQMPC_OK;                                          // cleared: the box of lqmpc_set_problem
   const size_t bytes = (size_t)p * ctx->m * sizeof(double);
-  for (int e = 0; e < p * ctx->m; ++e)
-    if (!(fabs(F_host[e]) <= 1.79e308)) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: non-finite entry");
   int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->poly_dev, bytes), "cudaMalloc F_u");
   if (rc) return rc;
   rc = lq_check_cuda(ctx, cudaMemcpy(ctx->poly_dev, F_host, bytes, cudaMemcpyHostToDevice), "H2D F_u");

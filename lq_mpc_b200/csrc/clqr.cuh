@@ -37,6 +37,14 @@ struct Refs {
   LQ_HD double u(int j, int k) const { return ur ? ur[j * ld + k] : 0.0; }
 };
 
+// Working sets of the active-set iterations: one bit per (stage, input component) / (stage, polytope row).
+struct Mask128 {
+  uint64_t lo = 0, hi = 0;
+  LQ_HD bool test(int b) const { return (((b < 64) ? (lo >> b) : (hi >> (b - 64))) & 1u) != 0; }
+  LQ_HD void set(int b) { if (b < 64) lo |= (uint64_t)1 << b; else hi |= (uint64_t)1 << (b - 64); }
+  LQ_HD void clear(int b) { if (b < 64) lo &= ~((uint64_t)1 << b); else hi &= ~((uint64_t)1 << (b - 64)); }
+};
+
 template <int n, int m>
 struct ClqrLayout {
   int N;
@@ -96,7 +104,7 @@ LQ_HD void step_model(const double* A, const double* B, const double* x, const d
 
 // Backward affine Riccati sweep for the working set (fixed, athi): stores K_k (m x n) and k_k (m).
 template <int n, int m>
-LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, uint64_t fixed, uint64_t athi,
+LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const Mask128& fixed, const Mask128& athi,
                          const WsView& ws, const Refs& rf = Refs()) {
   const ClqrLayout<n, m> L(N);
   // cost-to-go INCLUDING the state's own stage term: Phi_k(x) = x'S x + 2 s'x + const; Phi_N = (x - r_{N-1})'P(x - r_{N-1})
@@ -133,9 +141,9 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, u
     double uc[m];
     bool fx[m];
     LQ_UNROLL for (int j = 0; j < m; ++j) {
-      const uint64_t bit = (uint64_t)1 << (k * m + j);
-      fx[j] = (fixed & bit) != 0;
-      uc[j] = (athi & bit) ? pb.uhi[j] : pb.ulo[j];
+      const int bit = k * m + j;
+      fx[j] = fixed.test(bit);
+      uc[j] = athi.test(bit) ? pb.uhi[j] : pb.ulo[j];
     }
     LQ_UNROLL for (int i = 0; i < m; ++i) {
       if (!fx[i]) {
@@ -206,7 +214,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   int flags = 0;
   // ---- 1. unconstrained plan; feasible => optimal. With references the plan is affine: gains AND offsets come from
   //         the affine sweep with an empty working set (stored where the constrained sweeps store theirs).
-  if (trk && !clqr_backward<n, m>(pb, pl, N, 0, 0, ws, rf)) flags |= FLAG_CHOL_FAIL;
+  if (trk && !clqr_backward<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf)) flags |= FLAG_CHOL_FAIL;
   const int64_t oK = trk ? L.oKc : L.oKu;
   bool feas = true;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
@@ -236,9 +244,9 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     return flags;
   }
   flags |= FLAG_QP_ACTIVE;
-  if (N * m > 64) return flags | FLAG_QP_MAXITER;   // working set is a 64-bit mask
+  if (N * m > 128) return flags | FLAG_QP_MAXITER;   // working set is a 128-bit mask
   // ---- 2. feasible start: saturated rollout of the unconstrained gains; clipped components enter the working set
-  uint64_t fixed = 0, athi = 0;
+  Mask128 fixed, athi;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
   for (int k = 0; k < N; ++k) {
     double K[m * n];
@@ -246,9 +254,9 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     mv<m, n>(K, x, u);
     LQ_UNROLL for (int j = 0; j < m; ++j) {
       if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
-      const uint64_t bit = (uint64_t)1 << (k * m + j);
-      if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed |= bit; athi |= bit; }
-      else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed |= bit; }
+      const int bit = k * m + j;
+      if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed.set(bit); athi.set(bit); }
+      else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed.set(bit); }
       ws[L.oz + (int64_t)k * m + j] = u[j];
     }
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
@@ -270,10 +278,11 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       mv<m, n>(K, x, u);
       LQ_UNROLL for (int j = 0; j < m; ++j) {
         u[j] += ws[L.okc + (int64_t)k * m + j];
-        const uint64_t bit = (uint64_t)1 << (k * m + j);
-        if (fixed & bit) u[j] = (athi & bit) ? pb.uhi[j] : pb.ulo[j];
+        const int bit = k * m + j;
+        const bool isfx = fixed.test(bit);
+        if (isfx) u[j] = athi.test(bit) ? pb.uhi[j] : pb.ulo[j];
         ws[L.ozs + (int64_t)k * m + j] = u[j];
-        if (!(fixed & bit)) {
+        if (!isfx) {
           const double zc = ws[L.oz + (int64_t)k * m + j];
           if (u[j] > pb.uhi[j]) {
             const double a = (pb.uhi[j] - zc) / (u[j] - zc);
@@ -296,8 +305,8 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       }
       const int j = block % m;
       ws[L.oz + block] = block_hi ? pb.uhi[j] : pb.ulo[j];
-      fixed |= (uint64_t)1 << block;
-      if (block_hi) athi |= (uint64_t)1 << block; else athi &= ~((uint64_t)1 << block);
+      fixed.set(block);
+      if (block_hi) athi.set(block); else athi.clear(block);
       continue;
     }
     // full step: z = z*; multipliers from the costate sweep over the stored trajectory
@@ -319,11 +328,11 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
         double acc = 0.0;
         LQ_UNROLL for (int r = 0; r < n; ++r) acc = fma(pl.Bh[r * m + j], lam[r], acc);
         g2[j] = acc;
-        const uint64_t bit = (uint64_t)1 << (k * m + j);
-        if (fixed & bit) {
+        const int bit = k * m + j;
+        if (fixed.test(bit)) {
           const double g = 2.0 * g1[j] + g2[j];            // dJ/du_{k,j}
           const double tol = 1e-11 * (fabs(2.0 * g1[j]) + fabs(g2[j])) + 1e-300;
-          const double viol = (athi & bit) ? g : -g;       // at hi need g <= 0 ; at lo need g >= 0
+          const double viol = athi.test(bit) ? g : -g;     // at hi need g <= 0 ; at lo need g >= 0
           if (viol > tol && viol > worst) { worst = viol; rel = k * m + j; }
         }
       }
@@ -340,7 +349,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       }
     }
     if (rel < 0) done = true;
-    else fixed &= ~((uint64_t)1 << rel);
+    else fixed.clear(rel);
   }
   if (!done) flags |= FLAG_QP_MAXITER;
   // ---- 4. objective along z

@@ -26,13 +26,6 @@ struct Poly {
   LQ_HD double f(int i, int j, int m) const { return F[i * m + j]; }
 };
 
-struct Mask128 {
-  uint64_t lo = 0, hi = 0;
-  LQ_HD bool test(int b) const { return (((b < 64) ? (lo >> b) : (hi >> (b - 64))) & 1u) != 0; }
-  LQ_HD void set(int b) { if (b < 64) lo |= (uint64_t)1 << b; else hi |= (uint64_t)1 << (b - 64); }
-  LQ_HD void clear(int b) { if (b < 64) lo &= ~((uint64_t)1 << b); else hi &= ~((uint64_t)1 << (b - 64)); }
-};
-
 // F_i u for row i
 template <int m>
 LQ_HD double poly_row(const Poly& py, int i, const double* u) {

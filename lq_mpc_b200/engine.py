@@ -332,14 +332,15 @@ class Engine:
         """General input polytope F_u u <= 1 (p x m) for the following K2 / K3 calls; None clears it (box of
         set_problem). set_problem also clears it. bar_u / bar_d_u (utils.py:592-650, vertex maxima) become the defaults
         of bounds_batch while the polytope is installed."""
-        self._poly_bar = None
         if F_u is None:
             self._check(self.lib.lqmpc_set_input_polytope(self._h, 0, None), "lqmpc_set_input_polytope")
+            self._poly_bar = None
             return self
         F = _np_f64(F_u)
         if F.ndim != 2 or F.shape[1] != self.m:
             raise EngineError("F_u must be (p, m) with m = %d input columns, got %r" % (self.m, F.shape))
         self._check(self.lib.lqmpc_set_input_polytope(self._h, F.shape[0], _ptr(F)), "lqmpc_set_input_polytope")
+        self._poly_bar = None
         if bar_u >= 0.0 and bar_d_u >= 0.0:
             self._poly_bar = (float(bar_u), float(bar_d_u))
         return self

@@ -363,17 +363,26 @@ def test_clqr_stress_vs_dense_qp(engine):
 
 
 def test_clqr_max_working_set_size(engine):
-    """N*m = 64 is the largest working set (64-bit mask); N*m = 65 with an active bound must flag QP_MAXITER."""
+    """N*m = 128 is the largest working set (128-bit mask): N = 64 and N = 128 (m = 1) and N = 64 with m = 2 are
+    solved exactly; N*m = 129 with an active bound must flag QP_MAXITER instead of answering."""
+    from oracle import np_oracle as o
     A = np.array([[1.0, 0.3], [0.0, 1.0]]); B = np.array([[0.0], [1.0]])
     engine.set_problem(A, B, np.eye(2), np.eye(1), np.eye(2), [-0.05], [0.05], 10)
-    from oracle import np_oracle as o
     x0 = np.array([[1.0], [0.5]])
-    got = engine.mpc_solve_batch(None, None, 64, x0=x0, S=1)
-    ur, Vr, act = o.mpc_solve(64, A, B, np.eye(2), np.eye(1), np.eye(2), np.array([-0.05]), np.array([0.05]), x0[:, 0],
-                              exact_fast=False)
-    assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
-    over = engine.mpc_solve_batch(None, None, 65, x0=x0, S=1)
+    for N in (64, 128):
+        got = engine.mpc_solve_batch(None, None, N, x0=x0, S=1)
+        ur, Vr, act = o.mpc_solve(N, A, B, np.eye(2), np.eye(1), np.eye(2), np.array([-0.05]), np.array([0.05]),
+                                  x0[:, 0], exact_fast=False)
+        assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
+        assert abs(float(got["u0"][0, 0, 0]) - ur[0]) < 1e-9
+    over = engine.mpc_solve_batch(None, None, 129, x0=x0, S=1)
     assert int(over["flags"][0, 0]) & 4
+    B2 = np.array([[0.0, 0.1], [1.0, 0.0]])
+    lo2, hi2 = np.array([-0.05, -0.2]), np.array([0.05, 0.2])
+    engine.set_problem(A, B2, np.eye(2), np.eye(2), np.eye(2), lo2, hi2, 10)
+    got = engine.mpc_solve_batch(None, None, 64, x0=x0, S=1)
+    ur, Vr, act = o.mpc_solve(64, A, B2, np.eye(2), np.eye(2), np.eye(2), lo2, hi2, x0[:, 0], exact_fast=False)
+    assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
 
 
 # ------------------------------------------------------------------------------------------------------- K3
