@@ -241,22 +241,26 @@ def run_ours(args):
         return float(t.item())
 
     # ---- (1) device-resident throughput: W warm-up steps, K timed steps, CUDA events, max over ranks
-    # the clock sampler (one `nvidia-smi -lms` process) starts BEFORE the warm-up and gets time to initialise: its
-    # NVML start-up takes driver locks for a few hundred ms and, begun at the edge of the timed region, stalled launches
-    # there (erratic 3.9-6.2 ms steps around a steady 3.8 ms kernel)
+    # the clock sampler (one `nvidia-smi -lms` process) starts BEFORE the warm-up and gets time to initialise (its NVML
+    # start-up takes driver locks for a few hundred ms: not at the edge of the timed region)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
         time.sleep(1.0)
-    n_warm = 0
-    t_w = time.perf_counter()
-    # W warm-up steps, and keep going until the GPU has been under this load for ~0.5 s (the kernel draws the board's
-    # power cap: the timed region should not start on a cold power state)
-    while n_warm < max(3, args.warmup) or (time.perf_counter() - t_w) < 0.5:
+    # W warm-up steps, then as many more as keep the GPU under this load for ~0.5 s (the kernel draws the board's power
+    # cap: the timed region should not start on a cold power state). The count is agreed across ranks — every step
+    # carries the all-gather, so ranks must not leave the warm-up at different steps.
+    n_warm = max(3, args.warmup)
+    for _ in range(n_warm):
         r, st = step()      # bound exactly as in the timed loop: two result sets alternate, so the second 350 MB block
-        n_warm += 1         # is allocated HERE (a cudaMalloc of it inside the timed region cost 6-150 ms at step 2)
-        if n_warm % 8 == 0:
-            torch.cuda.synchronize()
+    barrier()               # is allocated HERE (a cudaMalloc of it inside the timed region cost 6-150 ms at step 2)
+    t_w = time.perf_counter()
+    r, st = step()
+    torch.cuda.synchronize()
+    extra = int(max_over_ranks(float(min(400, int(0.5 / max(time.perf_counter() - t_w, 1e-4))))))
+    for _ in range(extra):
+        r, st = step()
+    n_warm += 1 + extra
     barrier()
     if rank == 0:
         sampler.rows.clear()                      # samples from here on: the three timed regions
