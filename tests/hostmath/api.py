@@ -141,3 +141,11 @@ def sample_error_grid(seed, which, rows, cols, N_sys, levels, n_boundary, norm_t
                                     {"f": 0, "2": 1}[norm_type], _p(out), st.ctypes.data_as(ctypes.POINTER(ctypes.c_int64)))
     assert rc == 0
     return out.reshape(rows, cols, N_sys, lev.size), int(st[0]), int(st[1])
+
+
+def tridiag_extremes(d, e):
+    """(lambda_min, lambda_max) of the symmetric tridiagonal with diagonal d and off-diagonal e[1:] (e[0] unused)."""
+    d, e = _c(d), _c(e)
+    out = np.zeros(2)
+    lib().hm_tridiag_extremes(_p(d), _p(e), len(d), _p(out))
+    return out[0], out[1]

@@ -237,6 +237,14 @@ void hm_set_poly(const double* F, int p) {
   g_poly.p = p;
 }
 
+// extremes of a symmetric tridiagonal (d[k], e[k] with e[0] unused) by K3's Sturm search
+void hm_tridiag_extremes(const double* d, const double* e, int k, double* out2) {
+  std::vector<double> buf((size_t)2 * k);
+  for (int i = 0; i < k; ++i) { buf[i] = d[i]; buf[k + i] = e[i]; }
+  const lq::WsView ws{buf.data(), 1};
+  lq::ws_tridiag_extremes(ws, 0, k, k, out2, out2 + 1);
+}
+
 int hm_bounds_fields(void) { return (int)lq::BF_COUNT; }
 
 int hm_bounds(int n, int m, const double* A, const double* B, const double* Q, const double* R, const double* P,

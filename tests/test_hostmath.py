@@ -319,3 +319,31 @@ def test_k3_math_unit_norm_branch_of_geo_M():
         dec = o.energy_decreasing(A, B, Q, R, lo, hi, N, 5e-3, 5e-3, K, 0.05)
         for key in ("xi", "eta", "omega_N1", "omega_N0d5"):
             assert abs(b[key][0] - dec[key]) <= TOL * abs(dec[key]), (a11, key)
+
+
+def test_k3_sturm_search_vs_lapack():
+    """K3's search for both extremes of a symmetric tridiagonal (three shifts per search and pass) vs LAPACK on random,
+    Toeplitz (clustered ends), identity, graded, tightly clustered, 16-decade and split matrices, k = 1..78."""
+    import scipy.linalg as sla
+    rng = np.random.default_rng(0)
+
+    def check(d, e):
+        k = len(d)
+        ev = sla.eigvalsh_tridiagonal(d, e[1:]) if k > 1 else np.array(d)
+        lo, hi = hm.tridiag_extremes(d, e)
+        nrm = max(abs(ev[0]), abs(ev[-1]), 1e-300)
+        assert max(abs(lo - ev[0]), abs(hi - ev[-1])) <= 5e-15 * nrm
+
+    check(np.array([3.5]), np.zeros(1))
+    for k in (2, 3, 4, 5, 8, 13, 20, 36, 50, 64, 78):
+        for _ in range(20):
+            check(rng.normal(size=k) * rng.uniform(0.1, 10),
+                  np.concatenate(([0], rng.normal(size=k - 1) * rng.uniform(0.01, 5))))
+        check(2 * np.ones(k), np.concatenate(([0], -np.ones(k - 1))))
+        check(np.ones(k), np.zeros(k))
+        check(np.arange(k, dtype=float), np.concatenate(([0], np.full(k - 1, 1e-8))))
+        check(np.ones(k), np.concatenate(([0], np.full(k - 1, 1e-9))))
+        d = 10.0 ** rng.uniform(-8, 8, size=k)
+        check(d, np.concatenate(([0], np.sqrt(d[:-1] * d[1:]) * rng.uniform(0, 0.5, k - 1))))
+        e = np.full(k, 0.3); e[0] = 0.0; e[k // 2] = 0.0
+        check(np.concatenate((np.ones(k // 2), 5 * np.ones(k - k // 2))), e)
