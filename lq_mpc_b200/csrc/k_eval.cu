@@ -65,12 +65,16 @@ __global__ void prepare_kernel(lq::Problem<n, m>* pb, int N_opc) {
   }
 }
 
-// Register budget per (n, m): 128-thread CTAs, MINB CTAs/SM -> 65536 / (128 MINB) registers per thread.
+// Register budget per (n, m) and mode: 128-thread CTAs, MINB CTAs/SM -> 65536 / (128 MINB) registers per thread.
 template <int n, int m>
 struct K1Tune {
-  // measured on B200 (scripts/k1_probe.py, n=4 m=2, 1.25e7 samples): 220 regs/no spills (MINB 1-2) 3.67 ms,
-  // 128 regs (MINB 4) 3.70 ms for N=10 only; with all horizons 1..10 emitted 19.5-22 ms vs 17.5 ms -> MINB 4.
-  static constexpr int minb = (n <= 4) ? 4 : 2;
+  // measured on B200 (scripts/k1_probe.py and k1_sustained_probe.py, n=4 m=2, 1.25e7 samples). From a cold power state
+  // every budget ties for one horizon per sample (2 / 3 / 4 / 5 CTAs per SM: 3.50 / 3.61 / 3.55 / 3.51 ms), but the
+  // kernel runs into the board's power cap and SUSTAINED the spill-free 255-register build wins clearly
+  // (3.49 / 3.73 / 3.89 / 3.97 ms: spill traffic and the extra instructions cost power, i.e. clock). With all horizons
+  // 1..10 emitted the order flips (18.0 / 16.4 / 15.9 / 15.6 ms sustained): occupancy hides the per-horizon stores.
+  static constexpr int minb_single = 2;                 // N_min == N_max
+  static constexpr int minb_nested = (n <= 4) ? 4 : 2;  // several horizons per sample
 };
 
 template <int n, int m>
@@ -92,7 +96,10 @@ int launch_eval_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
     return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
   }
 #endif
-  eval_kernel<n, m, K1Tune<n, m>::minb><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+  if (a.N_min == a.N_max)
+    eval_kernel<n, m, K1Tune<n, m>::minb_single><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
+  else
+    eval_kernel<n, m, K1Tune<n, m>::minb_nested><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
 }
