@@ -114,8 +114,9 @@ int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host
  * Initial states: either `pts` — npts states shared by all samples, device [npts][n] (the ring of
  * OL_energy_bound, utils_class.py:439-466) — or `x0`, one state per sample, device [n][S] (then P = 1).
  *   V [P][S] open-loop value V_N (incl. x0'Qx0), u0 [P][m][S] first input, M_V [S] = max_p V (utils_class.py:464),
- *   flags [P][S]; any output may be NULL. Needs N*m <= 128 (N*p <= 128 with an input polytope of p rows)
- *   whenever a constraint is active; beyond that the entry is flagged LQMPC_FLAG_QP_MAXITER, never approximated. */
+ *   flags [P][S]; any output may be NULL. Needs N*m <= 256 (N*p <= 256 with an input polytope of p rows)
+ *   whenever a constraint is active; beyond that the entry is flagged LQMPC_FLAG_QP_MAXITER, never approximated:
+ *   its V is NaN and its u0 the unconstrained first input clipped into the input set. */
 int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int npts,
                           const double* pts, const double* x0, double* V, double* u0, double* M_V, int32_t* flags);
 
@@ -128,7 +129,7 @@ int lqmpc_set_references(lqmpc_ctx* ctx, int n_cols, const double* x_ref_host, c
 
 /* General input polytope F_u u <= 1 (utils_class.py:23,81: F_u is an arbitrary p x m matrix; rows with several
  * non-zeros couple the inputs) for the following lqmpc_mpc_solve_batch / lqmpc_simulate_batch / lqmpc_bounds_batch
- * calls: HOST pointer, row-major (p x m), p <= 12, N * p <= 128 per solve. p <= 0 or NULL clears it (back to the box of
+ * calls: HOST pointer, row-major (p x m), p <= 12, N * p <= 256 per solve. p <= 0 or NULL clears it (back to the box of
  * lqmpc_set_problem, the state after lqmpc_set_problem). The origin must be interior (it is: the right-hand side is 1).
  * With a polytope installed lqmpc_bounds_batch takes local_radius (utils.py:548-564) over these rows and needs bar_u /
  * bar_d_u (utils.py:592-650: maxima of convex functions, attained at vertices) from the caller. A rejected call

@@ -13,7 +13,7 @@ def dlqr(A, B, Q, R):
     n = A.shape[0]
     B = np.asarray(B, dtype=np.float64).reshape(n, -1)
     m = B.shape[1]
-    eng = _rt.problem_for(A, B, Q, R)
+    eng = _rt.problem_for(A, B, Q, R, scratch=True)
     out = eng.dlqr_batch(S=1)
     K = out["K"].cpu().numpy()[:, 0].reshape(m, n)
     P = out["P"].cpu().numpy()[:, 0].reshape(n, n)

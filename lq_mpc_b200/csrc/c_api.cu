@@ -83,6 +83,24 @@ int ensure_pipe(lqmpc_ctx* ctx, size_t bytes_per_slot) {
   return LQMPC_OK;
 }
 
+// Error path of the host pipelines: asynchronous copies already enqueued still read from / write to the caller's
+// host buffers — drain every stream involved before handing control (and the buffers) back.
+int pipe_abort(lqmpc_ctx* ctx, int rc) {
+  const std::string keep = ctx->err;
+  for (int i = 0; i < 2; ++i)
+    if (ctx->pipe_stream[i]) cudaStreamSynchronize(ctx->pipe_stream[i]);
+  cudaStreamSynchronize(ctx->stream);
+  (void)cudaGetLastError();
+  ctx->err = keep;
+  return rc;
+}
+
+#define LQ_PIPE(call, what)                                   \
+  do {                                                        \
+    const int rc__ = lq_check_cuda(ctx, (call), (what));      \
+    if (rc__) return pipe_abort(ctx, rc__);                   \
+  } while (0)
+
 }  // namespace
 
 extern "C" {
@@ -279,31 +297,30 @@ int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, c
     double* d_rho = d_J + (int64_t)H * chunk;
     double* d_ratio = d_rho + (int64_t)H * chunk;
     int32_t* d_flags = reinterpret_cast<int32_t*>(d_ratio + (int64_t)H * chunk);
-    if (c >= 2) cudaStreamWaitEvent(s_in, ctx->tp_ev[2 + b], 0);      // slot inputs free once chunk c-2 was computed
-    rc = lq_check_cuda(ctx, cudaMemcpyAsync(d_dA, dA_h + s0 * n * n, (size_t)cs * n * n * 8, cudaMemcpyHostToDevice, s_in),
-                       "H2D dA");
-    if (rc) return rc;
-    cudaMemcpyAsync(d_dB, dB_h + s0 * n * m, (size_t)cs * n * m * 8, cudaMemcpyHostToDevice, s_in);
-    cudaMemcpyAsync(d_x0, x0_h + s0 * n, (size_t)cs * n * 8, cudaMemcpyHostToDevice, s_in);
-    cudaEventRecord(ev_in, s_in);
-    cudaStreamWaitEvent(s_cmp, ev_in, 0);
-    if (c >= 2) cudaStreamWaitEvent(s_cmp, ctx->tp_ev[4 + b], 0);     // slot outputs free once chunk c-2 was copied back
+    if (c >= 2) LQ_PIPE(cudaStreamWaitEvent(s_in, ctx->tp_ev[2 + b], 0), "wait slot inputs");   // chunk c-2 computed
+    LQ_PIPE(cudaMemcpyAsync(d_dA, dA_h + s0 * n * n, (size_t)cs * n * n * 8, cudaMemcpyHostToDevice, s_in), "H2D dA");
+    LQ_PIPE(cudaMemcpyAsync(d_dB, dB_h + s0 * n * m, (size_t)cs * n * m * 8, cudaMemcpyHostToDevice, s_in), "H2D dB");
+    LQ_PIPE(cudaMemcpyAsync(d_x0, x0_h + s0 * n, (size_t)cs * n * 8, cudaMemcpyHostToDevice, s_in), "H2D x0");
+    LQ_PIPE(cudaEventRecord(ev_in, s_in), "record H2D");
+    LQ_PIPE(cudaStreamWaitEvent(s_cmp, ev_in, 0), "wait H2D");
+    if (c >= 2) LQ_PIPE(cudaStreamWaitEvent(s_cmp, ctx->tp_ev[4 + b], 0), "wait slot outputs");   // chunk c-2 copied back
     TiledEval t;
     t.S = cs; t.dA = d_dA; t.dB = d_dB; t.x0 = d_x0; t.N_min = N_min; t.N_max = N_max;
     t.J = d_J; t.rho = d_rho; t.ratio = d_ratio; t.Vn = nullptr; t.flags = d_flags; t.Pout = nullptr;
     // [H][cs] tables inside the slot: the kernels index outputs with leading dimension S = cs
     rc = lq_launch_tiled(ctx, t);
-    if (rc) return rc;
-    cudaEventRecord(ev_cmp, s_cmp);
-    cudaStreamWaitEvent(s_out, ev_cmp, 0);
+    if (rc) return pipe_abort(ctx, rc);
+    LQ_PIPE(cudaEventRecord(ev_cmp, s_cmp), "record compute");
+    LQ_PIPE(cudaStreamWaitEvent(s_out, ev_cmp, 0), "wait compute");
     const size_t w = (size_t)cs * 8, sp = (size_t)S * 8;
-    if (J_h) cudaMemcpy2DAsync(J_h + s0, sp, d_J, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
-    if (rho_h) cudaMemcpy2DAsync(rho_h + s0, sp, d_rho, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
-    if (ratio_h) cudaMemcpy2DAsync(ratio_h + s0, sp, d_ratio, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out);
+    if (J_h) LQ_PIPE(cudaMemcpy2DAsync(J_h + s0, sp, d_J, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out), "D2H J");
+    if (rho_h) LQ_PIPE(cudaMemcpy2DAsync(rho_h + s0, sp, d_rho, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out), "D2H rho");
+    if (ratio_h)
+      LQ_PIPE(cudaMemcpy2DAsync(ratio_h + s0, sp, d_ratio, w, w, (size_t)H, cudaMemcpyDeviceToHost, s_out), "D2H ratio");
     if (flags_h)
-      cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)cs * 4, (size_t)cs * 4, (size_t)H,
-                        cudaMemcpyDeviceToHost, s_out);
-    cudaEventRecord(ev_out, s_out);
+      LQ_PIPE(cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)cs * 4, (size_t)cs * 4, (size_t)H,
+                                cudaMemcpyDeviceToHost, s_out), "D2H flags");
+    LQ_PIPE(cudaEventRecord(ev_out, s_out), "record D2H");
   }
   rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_out), "pipeline sync (D2H)");
   if (rc) return rc;
@@ -392,41 +409,41 @@ int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const d
     // stream order makes slot reuse safe: chunk c+2 is enqueued on the same stream after chunk c's D2H
     rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_dA, dp, dA_h + s0, sp, w, (size_t)n * n, cudaMemcpyHostToDevice, st),
                        "H2D dA");
-    if (rc) return rc;
+    if (rc) return pipe_abort(ctx, rc);
     rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_dB, dp, dB_h + s0, sp, w, (size_t)n * m, cudaMemcpyHostToDevice, st),
                        "H2D dB");
-    if (rc) return rc;
+    if (rc) return pipe_abort(ctx, rc);
     rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(d_x0, dp, x0_h + s0, sp, w, (size_t)n, cudaMemcpyHostToDevice, st),
                        "H2D x0");
-    if (rc) return rc;
+    if (rc) return pipe_abort(ctx, rc);
     EvalArgs a;
     a.S = cs; a.ld = chunk; a.dA = d_dA; a.dB = d_dB; a.x0 = d_x0;
     a.N_min = N_min; a.N_max = N_max; a.T = 0;
     a.J = J_h ? d_J : nullptr; a.rho = rho_h ? d_rho : nullptr; a.ratio = ratio_h ? d_ratio : nullptr;
     a.Vn = nullptr; a.JT = nullptr; a.flags = flags_h ? d_flags : nullptr; a.K0 = nullptr;
     rc = lq_launch_eval(ctx, a, st);
-    if (rc) return rc;
+    if (rc) return pipe_abort(ctx, rc);
     if (J_h) {
       rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(J_h + s0, sp, d_J, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st),
                          "D2H J");
-      if (rc) return rc;
+      if (rc) return pipe_abort(ctx, rc);
     }
     if (rho_h) {
       rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(rho_h + s0, sp, d_rho, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st),
                          "D2H rho");
-      if (rc) return rc;
+      if (rc) return pipe_abort(ctx, rc);
     }
     if (ratio_h) {
       rc = lq_check_cuda(
           ctx, cudaMemcpy2DAsync(ratio_h + s0, sp, d_ratio, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st), "D2H ratio");
-      if (rc) return rc;
+      if (rc) return pipe_abort(ctx, rc);
     }
     if (flags_h) {
       rc = lq_check_cuda(ctx,
                          cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)chunk * 4, (size_t)cs * 4,
                                            (size_t)H, cudaMemcpyDeviceToHost, st),
                          "D2H flags");
-      if (rc) return rc;
+      if (rc) return pipe_abort(ctx, rc);
     }
   }
   for (int b = 0; b < 2; ++b) {

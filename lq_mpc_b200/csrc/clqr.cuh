@@ -37,12 +37,22 @@ struct Refs {
   LQ_HD double u(int j, int k) const { return ur ? ur[j * ld + k] : 0.0; }
 };
 
-// Working sets of the active-set iterations: one bit per (stage, input component) / (stage, polytope row).
-struct Mask128 {
-  uint64_t lo = 0, hi = 0;
-  LQ_HD bool test(int b) const { return (((b < 64) ? (lo >> b) : (hi >> (b - 64))) & 1u) != 0; }
-  LQ_HD void set(int b) { if (b < 64) lo |= (uint64_t)1 << b; else hi |= (uint64_t)1 << (b - 64); }
-  LQ_HD void clear(int b) { if (b < 64) lo &= ~((uint64_t)1 << b); else hi &= ~((uint64_t)1 << (b - 64)); }
+// Working sets of the active-set iterations: one bit per (stage, input component) / (stage, polytope row), 256 bits
+// (N m = 240 at BASELINE cfg 5's shape). Word selection is a chain of selects, never a dynamically indexed array,
+// so the four words stay in registers.
+constexpr int kMaskBits = 256;
+struct Mask128 {   // (name kept from the 128-bit first version)
+  uint64_t w0 = 0, w1 = 0, w2 = 0, w3 = 0;
+  LQ_HD uint64_t word(int b) const { return (b < 128) ? ((b < 64) ? w0 : w1) : ((b < 192) ? w2 : w3); }
+  LQ_HD bool test(int b) const { return ((word(b) >> (b & 63)) & 1u) != 0; }
+  LQ_HD void put(int b, bool v) {
+    const uint64_t bit = (uint64_t)1 << (b & 63);
+    uint64_t w = word(b);
+    w = v ? (w | bit) : (w & ~bit);
+    if (b < 64) w0 = w; else if (b < 128) w1 = w; else if (b < 192) w2 = w; else w3 = w;
+  }
+  LQ_HD void set(int b) { put(b, true); }
+  LQ_HD void clear(int b) { put(b, false); }
 };
 
 template <int n, int m>
@@ -244,7 +254,11 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     return flags;
   }
   flags |= FLAG_QP_ACTIVE;
-  if (N * m > 128) return flags | FLAG_QP_MAXITER;   // working set is a 128-bit mask
+  if (N * m > kMaskBits) {   // beyond the working-set mask: never approximated — V = NaN, u0 clipped into the box, flagged
+    LQ_UNROLL for (int j = 0; j < m; ++j) u0[j] = dmin(dmax(u0[j], pb.ulo[j]), pb.uhi[j]);
+    *V = NAN;
+    return flags | FLAG_QP_MAXITER;
+  }
   // ---- 2. feasible start: saturated rollout of the unconstrained gains; clipped components enter the working set
   Mask128 fixed, athi;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];

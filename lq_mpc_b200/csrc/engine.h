@@ -5,6 +5,7 @@
 
 #include <string>
 
+#include "../../include/lqmpc_b200.h"
 #include "riccati.cuh"
 
 // (n, m) pairs every templated kernel is instantiated for. The thread-per-sample register design targets n <= 4;

@@ -150,7 +150,7 @@ int lq_launch_bounds(lqmpc_ctx* ctx, const BoundsArgs& a) {
   if (ctx->n == N_ && ctx->m == M_) return launch_bounds_t<N_, M_>(ctx, a);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }
 
 int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P,
@@ -159,5 +159,5 @@ int lq_launch_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB
   if (ctx->n == N_ && ctx->m == M_) return launch_dlqr_t<N_, M_>(ctx, S, dA, dB, K, P, flags);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }

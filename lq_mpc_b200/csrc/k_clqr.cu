@@ -8,5 +8,5 @@ int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool sim) {
   if (ctx->n == N_ && ctx->m == M_) return launch_mpc_t<N_, M_, false>(ctx, a, sim);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }

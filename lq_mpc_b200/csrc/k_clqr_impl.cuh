@@ -118,7 +118,7 @@ int launch_mpc_t(lqmpc_ctx* ctx, MpcArgs a, bool sim) {
   if (rc) return rc;
   a.ws = reinterpret_cast<double*>(ctx->ws);
   if (ctx->ref_ld >= a.N) { a.xr = ctx->ref_x; a.ur = ctx->ref_u; a.ref_ld = ctx->ref_ld; }
-  else if (ctx->ref_ld > 0) return lq_set_error(ctx, -1, "references hold fewer than N columns");
+  else if (ctx->ref_ld > 0) return lq_set_error(ctx, LQMPC_EINVAL, "references hold fewer than N columns");
   if (POLY) { a.polyF = ctx->poly_dev; a.polyP = ctx->poly_p; }
   if (sim)
     simulate_kernel<n, m, POLY><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a);

@@ -82,7 +82,7 @@ int launch_eval_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int threads = 128;
   const int64_t blocks = (a.S + threads - 1) / threads;
-  if (blocks > 0x7fffffffLL) return lq_set_error(ctx, -1, "batch too large for one launch");
+  if (blocks > 0x7fffffffLL) return lq_set_error(ctx, LQMPC_EINVAL, "batch too large for one launch");
 #ifdef LQ_K1_VARIANTS
   if (n == 4 && m == 2) {   // development switch: occupancy experiments on the headline size
     const char* v = getenv("LQMPC_K1_MINB");
@@ -142,7 +142,7 @@ int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
   if (ctx->n == N_ && ctx->m == M_) return launch_eval_t<N_, M_>(ctx, a, stream);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }
 
 int lq_launch_prepare(lqmpc_ctx* ctx) {
@@ -150,7 +150,7 @@ int lq_launch_prepare(lqmpc_ctx* ctx) {
   if (ctx->n == N_ && ctx->m == M_) return launch_prepare_t<N_, M_>(ctx);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }
 
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops) {

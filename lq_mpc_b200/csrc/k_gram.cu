@@ -227,5 +227,5 @@ int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB
   if (ctx->n == N_ && ctx->m == M_) return launch_gram_t<N_, M_>(ctx, S, dA, dB, N, tri);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  return lq_set_error(ctx, -1, "unsupported (n, m); see lqmpc_supported_dims()");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
 }

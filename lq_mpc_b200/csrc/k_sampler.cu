@@ -47,7 +47,7 @@ template <int r, int c>
 int launch_sampler_t(lqmpc_ctx* ctx, const SamplerArgs& a) {
   const int64_t S = a.N_sys * a.n_err;
   const int64_t blocks = (S + 255) / 256;
-  if (blocks > 0x7fffffffLL) return lq_set_error(ctx, -1, "grid too large for one launch");
+  if (blocks > 0x7fffffffLL) return lq_set_error(ctx, LQMPC_EINVAL, "grid too large for one launch");
   sampler_kernel<r, c><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "sampler_kernel launch");
@@ -73,7 +73,7 @@ int lq_launch_sampler(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int co
   if (rc == -100 && rows == N_ && cols == M_) rc = launch_sampler_t<N_, M_>(ctx, a);
   LQ_FOR_EACH_DIM(X)
 #undef X
-  if (rc == -100) return lq_set_error(ctx, -1, "unsupported sampler shape (rows x cols must be n x n or n x m of a compiled pair)");
+  if (rc == -100) return lq_set_error(ctx, LQMPC_EINVAL, "unsupported sampler shape (rows x cols must be n x n or n x m of a compiled pair)");
   if (rc) return rc;
   if (stats_host) {
     unsigned long long h[2] = {0, 0};

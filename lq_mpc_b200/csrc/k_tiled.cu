@@ -893,7 +893,7 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
   double* vexp = jraw + (size_t)H * chunk;
   int32_t* fscratch = reinterpret_cast<int32_t*>(vexp + chunk);
   if (t.S > chunk && H > 1)
-    return lq_set_error(ctx, -1, "tiled path: nested horizons need the batch to fit one chunk (reduce S or H)");
+    return lq_set_error(ctx, LQMPC_EINVAL, "tiled path: nested horizons need the batch to fit one chunk (reduce S or H)");
   for (int64_t s0 = 0; s0 < t.S; s0 += chunk) {
     const int64_t cs = (s0 + chunk <= t.S) ? chunk : t.S - s0;
     TiledArgs a;
@@ -997,5 +997,5 @@ size_t lq_tiled_pb_doubles(int n, int m) { return (size_t)(4 * n * n + n * m + m
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t) {
   if (ctx->tn == 32 && ctx->tm == 8) return launch_tiled_t<32, 8>(ctx, t);
   if (ctx->tn == 16 && ctx->tm == 4) return launch_tiled_t<16, 4>(ctx, t);
-  return lq_set_error(ctx, -1, "unsupported tiled (n, m): 32x8 and 16x4 are compiled");
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported tiled (n, m): 32x8 and 16x4 are compiled");
 }

@@ -11,7 +11,7 @@
 // which keeps the law affine in x (gain and offset), so the cost-to-go recursion is unchanged. Rows join the working
 // set by the ratio test along z* - z (a blocking row is never a combination of the rows already active at its stage:
 // those have F_W dz = 0), rows leave by the sign of their KKT multiplier, recovered stage by stage from the costate
-// sweep as mu = -(F_W F_W')^-1 F_W dJ/du_k. Working sets are 128-bit masks: N * p <= 128.
+// sweep as mu = -(F_W F_W')^-1 F_W dJ/du_k. Working sets are 256-bit masks: N * p <= 256.
 #pragma once
 #include "clqr.cuh"
 
@@ -204,7 +204,13 @@ LQ_HD int pclqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, cons
     return flags;
   }
   flags |= FLAG_QP_ACTIVE;
-  if (N * p > 128 || p > kPolyMaxRows) return flags | FLAG_QP_MAXITER;   // working set is a 128-bit mask
+  if (N * p > kMaskBits || p > kPolyMaxRows) {   // beyond the working-set mask: V = NaN, u0 shrunk onto the polytope, flagged
+    double worst = 1.0;
+    for (int i = 0; i < p; ++i) worst = dmax(worst, poly_row<m>(py, i, u0));
+    LQ_UNROLL for (int j = 0; j < m; ++j) u0[j] /= worst;
+    *V = NAN;
+    return flags | FLAG_QP_MAXITER;
+  }
   // ---- 2. feasible start: roll the unconstrained law out, shrinking each infeasible input radially onto the polytope
   //         (the origin is interior: F_u 0 = 0 < 1); the row that stops it enters the working set
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];

@@ -116,6 +116,19 @@ def _ptr(t):
     return t.data_ptr()
 
 
+def _streamed(fn):
+    """Run a public Engine method with the engine's stream as torch's CURRENT stream: staging copies (`_dev`), output
+    allocations (caching-allocator stream ownership) and the kernels the C ABI enqueues then share one stream order,
+    whichever stream the Engine was created on."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        with self.torch.cuda.stream(self._stream):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class Engine:
     """One engine context per (device, stream). Not thread-safe."""
 
@@ -196,6 +209,7 @@ class Engine:
     # ------------------------------------------------------------------------------------------------ K4
     TILED_DIMS = ((32, 8), (16, 4))
 
+    @_streamed
     def set_problem_tiled(self, A, B, Q, R, P=None, N_opc: int = 30):
         """Large-n path (K4; n x m in TILED_DIMS): unconstrained law, array-of-matrices operands."""
         A = _np_f64(A)
@@ -215,6 +229,7 @@ class Engine:
         self._check(self.lib.lqmpc_get_prepared_tiled(self._h, _ptr(out), out.size), "lqmpc_get_prepared_tiled")
         return {"Pexp": out.reshape(self.tn, self.tn)}
 
+    @_streamed
     def eval_batch_tiled(self, dA, dB, x0, N_min: int, N_max: int, want=("J", "rho", "ratio", "flags")):
         """dA [S][n][n], dB [S][n][m], x0 [S][n] (array of matrices, device or host). Returns [H][S] device tensors
         plus the contiguous `table` like eval_batch."""
@@ -237,6 +252,7 @@ class Engine:
         self._check(rc, "lqmpc_eval_batch_tiled")
         return out
 
+    @_streamed
     def eval_batch_tiled_host(self, dA, dB, x0, N_min: int, N_max: int, out=None, chunk: int = 16384):
         """eval_batch_tiled from/to HOST buffers (numpy arrays or CPU tensors [S][n*n] ..., ideally pinned), chunked
         with copies overlapping the kernels. `out` may hold preallocated host tensors J/rho/ratio/flags [H][S]."""
@@ -263,6 +279,7 @@ class Engine:
                 "minR": out[2 * n * n + 3]}
 
     # ------------------------------------------------------------------------------------------------ K1
+    @_streamed
     def eval_batch(self, dA, dB, x0, N_min: int, N_max: int, T: int = 0, want=("J", "rho", "ratio", "flags")):
         """dA [n*n][S], dB [n*m][S], x0 [n][S] (SoA, device). Returns dict of [H][S] device tensors."""
         torch = self.torch
@@ -290,6 +307,7 @@ class Engine:
         self._check(rc, "lqmpc_eval_batch")
         return out
 
+    @_streamed
     def eval_batch_host(self, dA, dB, x0, N_min: int, N_max: int, out=None, chunk: int = 1 << 20):
         """Same as eval_batch but from/to HOST buffers (numpy arrays or CPU tensors, ideally pinned), pipelined in
         chunks with copies overlapping compute. `out` may hold preallocated host arrays J/rho/ratio/flags [H][S]."""
@@ -362,6 +380,7 @@ class Engine:
     def _opt_dev(self, a):
         return None if a is None else self._dev(a)
 
+    @_streamed
     def mpc_solve_batch(self, dA, dB, N: int, pts=None, x0=None, S: Optional[int] = None,
                         want=("V", "u0", "M_V", "flags")):
         """Batched LQ_MPC_Controller.solve. dA/dB: [n*n][S]/[n*m][S] or None (true model; give S).
@@ -394,6 +413,7 @@ class Engine:
         self._check(rc, "lqmpc_mpc_solve_batch")
         return out
 
+    @_streamed
     def simulate_batch(self, dA, dB, N: int, T: int, x0_shared=None, x0=None, S: Optional[int] = None,
                        want=("J_T", "flags", "n_active")):
         """Batched LQ_MPC_Simulator.simulate. x0_shared: (n,) one state for all samples, or x0: [n][S]."""
@@ -422,6 +442,7 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------------------------------------ K3
+    @_streamed
     def bounds_batch(self, dA, dB, N: int, e_A, e_B, M_V, x, p, V_expert: float, K=None, S: Optional[int] = None,
                      bar_u: float = -1.0, bar_d_u: float = -1.0, strict_reference: bool = True, want_K=False,
                      want_P=False):
@@ -477,6 +498,7 @@ class Engine:
             out["P"] = P_out
         return out
 
+    @_streamed
     def dlqr_batch(self, dA=None, dB=None, S: Optional[int] = None):
         """Batched control.dlqr: returns K [m*n][S] (u = -Kx), P [n*n][S], flags [S]."""
         torch = self.torch
@@ -492,6 +514,7 @@ class Engine:
         return {"K": K, "P": P, "flags": fl}
 
     # ------------------------------------------------------------------------------------------------ K5
+    @_streamed
     def column_stats_raw(self, table):
         """table: [cols][S] device tensor (rows contiguous). Returns [cols][5] = max, min, sum, n_finite, n_bad."""
         torch = self.torch
@@ -505,6 +528,7 @@ class Engine:
         self._check(self.lib.lqmpc_column_stats(self._h, _ptr(t), cols, S, S, _ptr(stats)), "lqmpc_column_stats")
         return stats
 
+    @_streamed
     def column_moments_raw(self, table):
         """table: [cols][S] device tensor. Returns device [cols][6] = max, min, n_finite, n_nonfinite, mean, M2."""
         torch = self.torch
@@ -519,6 +543,7 @@ class Engine:
         self._check(self.lib.lqmpc_column_moments(self._h, _ptr(t), cols, S, S, _ptr(out)), "lqmpc_column_moments")
         return out
 
+    @_streamed
     def column_sqdev_raw(self, table, mean):
         torch = self.torch
         t = self._dev(table)
@@ -534,6 +559,7 @@ class Engine:
         return out
 
     # ------------------------------------------------------------------------------------------------ K6
+    @_streamed
     def sample_error_grid(self, seed: int, which: int, rows: int, cols: int, N_sys: int, levels, n_boundary: int,
                           norm_type: str = "f", j_first: int = 0, want_stats: bool = False):
         """Device-side `random_matrix` grid (utils.py:779-847 restated, seeded): returns the SoA tensor

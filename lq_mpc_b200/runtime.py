@@ -16,11 +16,16 @@ def default_device() -> int:
     return int(os.environ.get("LOCAL_RANK", "0"))
 
 
-def get_engine(device=None) -> Engine:
+def get_engine(device=None, scratch: bool = False) -> Engine:
+    """The process-wide engine of a device, or (scratch=True) a SECOND context on the same device that the stateless
+    helper functions of `utils` / `control` install their throw-away problems in (my_eigen, local_radius, geo_M,
+    ex_stability_lq, dlqr, ...): a helper call never disturbs the problem, references or polytope a caller installed
+    on the main engine."""
     d = default_device() if device is None else int(device)
-    if d not in _engines:
-        _engines[d] = Engine(d)
-    return _engines[d]
+    key = (d, bool(scratch))
+    if key not in _engines:
+        _engines[key] = Engine(d)
+    return _engines[key]
 
 
 def box_from_F(F_u):
@@ -102,10 +107,11 @@ def polytope_vertices(F_u):
     return V
 
 
-def problem_for(A, B, Q, R, P=None, F_u=None, N_opc=30, device=None) -> Engine:
+def problem_for(A, B, Q, R, P=None, F_u=None, N_opc=30, device=None, scratch: bool = False) -> Engine:
     """Engine with (A, B, Q, R, P, F_u) installed as the TRUE/nominal problem: a box-shaped F_u goes into the problem
-    itself, a general polytope is installed behind it (lqmpc_set_input_polytope)."""
-    eng = get_engine(device)
+    itself, a general polytope is installed behind it (lqmpc_set_input_polytope). scratch=True: the helper context
+    (see get_engine)."""
+    eng = get_engine(device, scratch)
     lo = hi = None
     general = F_u is not None and not is_box(F_u)
     if F_u is not None and not general:

@@ -73,16 +73,31 @@ def seeded_error_grids(n, m, error_vec, N_matrix, norm_type, seed=20240522):
     return eA, eB
 
 
-def device_error_grids(engine, n, m, error_vec, N_matrix, norm_type, seed=20240522, j_first=0, N_sys=None):
+def device_error_grids(engine, n, m, error_vec, N_matrix, norm_type, seed=20240522, j_first=0, N_sys=None,
+                        allow_projected=False, return_stats=False):
     """cfg-sweep grids generated in HBM by K6 (`lqmpc_sample_error_grid`): the counter-based restatement of
     error_matrix_generator (utils.py:826-847). Returns SoA device tensors dA [n*n][N_sys*n_err], dB [n*m][N_sys*n_err]
     (sample s = j*n_err + i) — reshape(n, n|m, N_sys, n_err) gives the reference's file layout. `j_first`/`N_sys`
-    select a shard of the 5*N_matrix perturbations per level; the first N_matrix (global) sit on the norm boundary."""
+    select a shard of the 5*N_matrix perturbations per level; the first N_matrix (global) sit on the norm boundary.
+
+    The interior perturbations are REJECTION samples of the norm ball, as upstream (utils.py:803-823); K6 gives up after
+    256 draws and projects the last one onto the boundary, which changes the distribution. The acceptance rate of a
+    uniform cube draw is ~0.31 for 2 x 2 (the shipped system: never exhausted) but ~6e-3 for 3 x 3 and ~4e-6 for
+    4 x 4 in the Frobenius norm, where upstream's own loop would effectively not terminate either. The projected count
+    is therefore always fetched and a non-zero count raises unless allow_projected=True."""
     total = 5 * N_matrix
     N_sys = total - j_first if N_sys is None else N_sys
-    dA = engine.sample_error_grid(seed, 0, n, n, N_sys, error_vec, N_matrix, norm_type, j_first=j_first)
-    dB = engine.sample_error_grid(seed, 1, n, m, N_sys, error_vec, N_matrix, norm_type, j_first=j_first)
-    return dA, dB
+    dA, sa = engine.sample_error_grid(seed, 0, n, n, N_sys, error_vec, N_matrix, norm_type, j_first=j_first,
+                                      want_stats=True)
+    dB, sb = engine.sample_error_grid(seed, 1, n, m, N_sys, error_vec, N_matrix, norm_type, j_first=j_first,
+                                      want_stats=True)
+    stats = {"rejected": sa["rejected"] + sb["rejected"], "projected": sa["projected"] + sb["projected"]}
+    if stats["projected"] and not allow_projected:
+        from .engine import EngineError
+        raise EngineError("device_error_grids: %d interior perturbations exhausted the 256 rejection draws and were "
+                          "projected onto the norm boundary (distribution changed); pass allow_projected=True to "
+                          "accept that" % stats["projected"])
+    return (dA, dB, stats) if return_stats else (dA, dB)
 
 
 def grids_to_soa(error_A, error_B, level=None):

@@ -48,6 +48,7 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
       '<q>_<stat>' for q in QUANTITIES, stat in max/min/mean/std : arrays [n_err][n_horizons],
       'ratio_true_max' / 'ratio_bound_max' (performance ratios J / V_expert, worst case per cell),
       'n_invalid' [n_err][n_horizons] (samples whose bound is void or raised in the reference),
+      'n_failed' [n_err][n_horizons] (samples with an incomplete solve: QP_MAXITER / *_NOCONV / CHOL_FAIL — expected 0),
       'evals', 'seconds' (device time of the sweep loop), and with keep_tables the raw [n_horizons][q][n_err][N_sys].
     """
     import torch
@@ -78,6 +79,7 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
     ring = engine._dev(x0_vec.T.copy())
     res = {q + "_" + s: np.zeros((n_err, len(horizons))) for q in QUANTITIES for s in ("max", "min", "mean", "std")}
     n_invalid = np.zeros((n_err, len(horizons)))
+    n_failed = np.zeros((n_err, len(horizons)))
     tables = [] if keep_tables else None
     torch.cuda.synchronize(engine.device)
     t0 = time.perf_counter()
@@ -85,7 +87,8 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
     e0.record()
     for h, N in enumerate(horizons):
         N = int(N)
-        mv = engine.mpc_solve_batch(dA, dB, N, pts=ring, want=("M_V",))["M_V"]
+        rs = engine.mpc_solve_batch(dA, dB, N, pts=ring, want=("M_V", "flags"))
+        mv = rs["M_V"]
         sim = engine.simulate_batch(dA, dB, N, T, x0_shared=x_start, want=("J_T", "flags"))
         b = engine.bounds_batch(dA, dB, N, e_per, e_per, mv, x_start, p, V_expert, strict_reference=strict_reference)
         cols = torch.cat([_strided_columns(v, n_err) for v in
@@ -96,17 +99,23 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
                 res[q + "_" + s][:, h] = st[s][qi * n_err:(qi + 1) * n_err]
         bad = ((b["flags"] & (32 | 512)) != 0).to(torch.float64)       # BOUND_INVALID | DOMAIN_ERROR
         n_invalid[:, h] = _strided_columns(bad, n_err).sum(dim=1).cpu().numpy()
+        # incomplete solves (QP_MAXITER | DARE_NOCONV | LYAP_NOCONV | EIG_NOCONV | CHOL_FAIL) anywhere in the cell
+        any_f = b["flags"] | sim["flags"]
+        for row in rs["flags"]:
+            any_f = any_f | row
+        fail = ((any_f & (4 | 8 | 64 | 128 | 256)) != 0).to(torch.float64)
+        n_failed[:, h] = _strided_columns(fail, n_err).sum(dim=1).cpu().numpy()
         if keep_tables:
             tables.append(cols.reshape(len(QUANTITIES), n_err, N_sys).cpu().numpy())
     e1.record()
     torch.cuda.synchronize(engine.device)
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        t = torch.from_numpy(n_invalid).to(engine.device)            # (column_stats merged the moments already)
+        t = torch.from_numpy(np.stack([n_invalid, n_failed])).to(engine.device)   # (column_stats merged the moments)
         dist.all_reduce(t, group=group)
-        n_invalid = t.cpu().numpy()
+        n_invalid, n_failed = t.cpu().numpy()
     res.update({"error": np.asarray(error_vec, dtype=np.float64), "horizon": np.asarray(horizons),
-                "V_expert": V_expert, "x_start": x_start, "epsilon_lqr": eps_lqr, "n_invalid": n_invalid,
+                "V_expert": V_expert, "x_start": x_start, "epsilon_lqr": eps_lqr, "n_invalid": n_invalid, "n_failed": n_failed,
                 "ratio_true_max": res["true_cost_max"] / V_expert, "ratio_bound_max": res["bound_max"] / V_expert,
                 "evals": int(N_sys) * n_err * len(horizons), "seconds": e0.elapsed_time(e1) * 1e-3,
                 "wall_seconds": time.perf_counter() - t0})

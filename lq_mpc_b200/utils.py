@@ -24,7 +24,7 @@ def _detail(A, B, Q, R, K=None, N=1, e_A=0.0, e_B=0.0, M_V=0.0, x=None, p=(1.0, 
     A = np.atleast_2d(np.asarray(A, dtype=np.float64))
     n = A.shape[0]
     B = np.asarray(B, dtype=np.float64).reshape(n, -1)
-    eng = _rt.problem_for(A, B, Q, R, None, F_u)
+    eng = _rt.problem_for(A, B, Q, R, None, F_u, scratch=True)
     x = np.zeros(n) if x is None else np.asarray(x, dtype=np.float64).reshape(n)
     out = eng.bounds_batch(None, None, int(N), float(e_A), float(e_B), float(M_V), x, p, 0.0, K=K, S=1,
                            bar_u=bar_u, bar_d_u=bar_d_u)
@@ -40,7 +40,7 @@ def my_eigen(M):
     if not np.array_equal(M, M.T):
         raise NotImplementedError("my_eigen: only symmetric matrices (Q, R) are supported by the engine")
     n = M.shape[0]
-    eng = _rt.problem_for(np.eye(n), np.eye(n, 1), M, np.eye(1), None, None)
+    eng = _rt.problem_for(np.eye(n), np.eye(n, 1), M, np.eye(1), None, None, scratch=True)
     pr = eng.prepared()
     return {'max': pr['maxQ'], 'min': pr['minQ'], 'ratio': pr['maxQ'] / pr['minQ']}
 
@@ -177,9 +177,10 @@ def local_radius(F_u, K, Q):
     F_u = np.atleast_2d(np.asarray(F_u, dtype=np.float64))
     K = np.atleast_2d(np.asarray(K, dtype=np.float64))
     n = K.shape[1]
-    Qinv = _rt.problem_for(np.eye(n), np.eye(n, 1), Q, np.eye(1)).prepared()['Qinv']
+    Qinv = _rt.problem_for(np.eye(n), np.eye(n, 1), Q, np.eye(1), scratch=True).prepared()['Qinv']
     Mx = F_u @ K
-    return 1 / max(float(r @ Qinv @ r) for r in Mx)
+    with np.errstate(divide='ignore'):                     # numpy semantics as upstream: a zero gain gives inf
+        return float(np.float64(1.0) / np.float64(max(float(r @ Qinv @ r) for r in Mx)))
 
 
 def ex_stability_bounds(gamma, epsilon_K, M_V):

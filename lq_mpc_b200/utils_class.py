@@ -3,7 +3,7 @@ dict keys; citations are into /root/reference/utils_class.py). Every numeric res
 single calls are S = 1 batches, the sweep drivers pack all (system, level) pairs of a table into one launch.
 
 Not carried over: the three Plotter_* classes (presentation, out of scope) — importing them raises a clear error.
-Both box-shaped and general polytopic F_u are supported (the latter up to 12 rows and N * rows <= 128, beyond which the
+Both box-shaped and general polytopic F_u are supported (the latter up to 12 rows and N * rows <= 256, beyond which the
 solve is flagged, not approximated); non-zero references are supported by the controller / simulator / M_V paths (K2);
 the bound formulas have no reference terms upstream either.
 """
@@ -29,6 +29,19 @@ def _raise_if_domain_error(flags):
         raise ValueError("math domain error")
 
 
+def _raise_if_solver_failed(flags, what):
+    """A solve the engine could not complete exactly (working set beyond 256 entries, R + B'PB not positive definite,
+    DARE / Lyapunov / eigenvalue iteration not converged) must not flow silently into tables: the reference's third
+    party solvers raise in these situations (cvxpy SolverError, scipy LinAlgError)."""
+    from .engine import (EngineError, FLAG_CHOL_FAIL, FLAG_DARE_NOCONV, FLAG_EIG_NOCONV, FLAG_LYAP_NOCONV,
+                         FLAG_QP_MAXITER)
+    bad = int(np.bitwise_or.reduce(np.asarray(flags, dtype=np.int64).reshape(-1), initial=0)) & (
+        FLAG_QP_MAXITER | FLAG_CHOL_FAIL | FLAG_DARE_NOCONV | FLAG_LYAP_NOCONV | FLAG_EIG_NOCONV)
+    if bad:
+        raise EngineError("%s: the engine flagged an incomplete solve (flags 0x%x: QP_MAXITER=4, DARE_NOCONV=8, "
+                          "LYAP_NOCONV=64, EIG_NOCONV=128, CHOL_FAIL=256)" % (what, bad))
+
+
 class LQ_MPC_Controller:
     """utils_class.py:18-91 — open-loop input-constrained LQ MPC; solved exactly on the GPU (K2)."""
 
@@ -40,7 +53,8 @@ class LQ_MPC_Controller:
         eng = _rt.problem_for(self.A, self.B, self.Q, self.R, self.P, self.F_u)
         x0 = np.asarray(x0, dtype=np.float64).reshape(1, -1)
         with eng.references(x_ref, u_ref):        # utils_class.py:62-81; all-zero references = regulation
-            out = eng.mpc_solve_batch(None, None, self.N, pts=x0, S=1, want=("V", "u0"))
+            out = eng.mpc_solve_batch(None, None, self.N, pts=x0, S=1, want=("V", "u0", "flags"))
+        _raise_if_solver_failed(_cpu(out["flags"]), "LQ_MPC_Controller.solve")
         return {'u_0': _cpu(out["u0"])[0, :, 0].copy(), 'V_N': float(_cpu(out["V"])[0, 0])}
 
 
@@ -63,7 +77,8 @@ class LQ_MPC_Simulator:
         dB = (np.asarray(self.B, dtype=np.float64).reshape(n, -1) - B_true).reshape(-1, 1)
         with eng.references(x_ref, u_ref):        # the same reference window at every step (utils_class.py:269)
             out = eng.simulate_batch(dA, dB, self.N, self.T, x0_shared=np.asarray(x0, dtype=np.float64).reshape(n),
-                                     want=("J_T", "X", "U"))
+                                     want=("J_T", "X", "U", "flags"))
+        _raise_if_solver_failed(_cpu(out["flags"]), "LQ_MPC_Simulator.simulate")
         self.X[:, :] = _cpu(out["X"])[:, :, 0].T
         self.U[:, :] = _cpu(out["U"])[:, :, 0].T
         return {'X': self.X, 'U': self.U, 'J_T': float(_cpu(out["J_T"])[0])}
@@ -123,7 +138,8 @@ class LQ_RDP_Behavior:
         x0_vec = circle_generator(N_points, ext_radius_max, self.epsilon, self.Q)
         eng = self._engine()
         with eng.references(x_ref, u_ref):
-            out = eng.mpc_solve_batch(None, None, int(N), pts=x0_vec.T, S=1, want=("M_V",))
+            out = eng.mpc_solve_batch(None, None, int(N), pts=x0_vec.T, S=1, want=("M_V", "flags"))
+        _raise_if_solver_failed(_cpu(out["flags"]), "OL_energy_bound")
         return float(_cpu(out["M_V"])[0])
 
     def _bounds_over(self, N, e_vec, K, M_V, x, p):
@@ -244,10 +260,14 @@ class LQ_RDP_Behavior_Multiple:
         (ring solves -> M_V, closed-loop simulate -> J_T, bounds -> alpha, beta, xi, eta, bound)."""
         eng = self.engine
         with eng.references(*refs):
-            mv = eng.mpc_solve_batch(dA, dB, int(N), pts=x0_vec.T, want=("M_V",))["M_V"]  # utils_class.py:813-824
+            ring = eng.mpc_solve_batch(dA, dB, int(N), pts=x0_vec.T, want=("M_V", "flags"))  # utils_class.py:813-824
+            mv = ring["M_V"]
             J = eng.simulate_batch(dA, dB, int(N), int(self.N_mpc), x0_shared=x_start, want=("J_T", "flags"))  # 828-833
         b = eng.bounds_batch(dA, dB, int(N), e, e, mv, x_start, p, V_expert, K=None,                       # 840-859
                              strict_reference=strict_reference)
+        _raise_if_solver_failed(_cpu(ring["flags"]), "data_generation (M_V ring solves)")
+        _raise_if_solver_failed(_cpu(J["flags"]), "data_generation (closed-loop simulation)")
+        _raise_if_solver_failed(_cpu(b["flags"]), "data_generation (bounds)")
         return {'alpha': b['alpha'], 'beta': b['beta'], 'xi': b['xi'], 'bound': b['bound'], 'J': J['J_T'],
                 'flags': b['flags'] | J['flags'], 'M_V': mv, 'eta': b['eta']}
 

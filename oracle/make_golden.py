@@ -189,7 +189,7 @@ def main():
 
 if __name__ == "__main__":
     import sys as _sys
-    if "--tracking" not in _sys.argv and "--polytope" not in _sys.argv:
+    if not any(a in _sys.argv for a in ("--tracking", "--polytope", "--round2")):
         main()
 
 
@@ -285,3 +285,99 @@ if __name__ == "__main__":
         main_tracking()
     if "--polytope" in _sys.argv:
         main_polytope()
+
+
+def extension_cases(u, uc, ct, seed=31):
+    """energy_decreasing_extension / fc_omega_eta_extension (utils_class.py:375-406, utils.py:412-466) through the
+    untouched reference, m = 1 (its `A + B * K` is an outer product only then): the shipped 2-state example with the
+    LQR gain and detuned second gains, random well-damped plants, and cases whose math.log argument is <= 0."""
+    rng = np.random.default_rng(seed)
+    cases = []
+    A0 = np.array([[1, 0.7], [0.12, 0.4]])
+    B0 = np.array([[1], [1.2]])
+    for c in range(14):
+        if c < 4:
+            n, A, B, q, r, ub = 2, A0, B0, 2.0, 1.0, 0.1
+        else:
+            n = 2 if c % 2 == 0 else 3
+            A = rng.normal(size=(n, n))
+            A *= rng.uniform(0.3, 0.95) / np.max(np.abs(np.linalg.eigvals(A)))
+            B = rng.normal(size=(n, 1))
+            q, r, ub = rng.uniform(0.5, 3.0), rng.uniform(0.3, 2.0), rng.uniform(0.05, 0.4)
+        Q, R = q * np.eye(n), r * np.eye(1)
+        F_u = np.array([[1 / ub], [-1 / ub]])
+        K_lqr, _, _ = ct.dlqr(A, B, Q, R)
+        K = -K_lqr
+        # second gain: the LQR gain of a detuned weight pair (c == 0: the same gain)
+        r2 = r * (1.0 if c == 0 else rng.uniform(0.2, 5.0))
+        hatK = -ct.dlqr(A, B, Q, r2 * np.eye(1))[0]
+        N = int(rng.integers(3, 12))
+        e = float(rng.uniform(1e-3, 2e-2))
+        M_V = float(rng.uniform(0.02, 1.5))
+        if c in (3, 13):                      # a gain that leaves rho(A + BK) + 0.4 >= 1: log of a negative number
+            K = np.zeros((1, n)) if c == 3 else 0.05 * K
+        rec = {'n': n, 'A': _l(A), 'B': _l(B), 'q': q, 'r': r, 'ub': ub, 'K': _l(K), 'hatK': _l(hatK), 'N': N,
+               'e': e, 'M_V': M_V}
+        calc = uc.LQ_RDP_Calculator(A, B, Q, R, F_u)
+        try:
+            eps = u.local_radius(F_u, K, Q)
+            st = u.ex_stability_lq(A, B, Q, R, K)
+            bd = u.ex_stability_bounds(st['gamma'], eps, M_V)
+            oe = u.fc_omega_eta_extension(N, A, B, Q, R, K, hatK, bd['L_V'], bd['N_0'])
+            dec = calc.energy_decreasing_extension(N, e, e, K, hatK, M_V)
+            rec.update({'L_V': float(bd['L_V']), 'N_0': int(bd['N_0']),
+                        'omega_eta': {k: float(v) for k, v in oe.items()},
+                        'xi': float(dec['xi']), 'eta': float(dec['eta'])})
+        except ValueError as ex:
+            rec['raises'] = str(ex)
+        cases.append(rec)
+    return cases
+
+
+def cfg4_cases(uc, seed=41):
+    """BASELINE configs[3] shape (n = 4, m = 2, N = 10, Q = I, R = I, the seed-0 synthetic plant of
+    lq_mpc_b200/sampling.py) through the UNTOUCHED LQ_MPC_Controller / LQ_MPC_Simulator (utils_class.py:48-91, 245-285)
+    with a loose input box (never active, so the cvxpy shim's QP is the unconstrained one): the first-step gain K0
+    (u_0 for the four unit states), J_T for T = 400 (= J_inf to rounding: rho^800 ~ 0) and the last state."""
+    import sys
+    sys.path.insert(0, os.path.dirname(HERE))
+    from lq_mpc_b200 import sampling as sp
+    A, B, Q, R = sp.synth_problem(4, 2, seed=0)
+    rng = np.random.default_rng(seed)
+    n, m, N, T = 4, 2, 10, 400
+    F_u = np.vstack((np.eye(m) / 1e6, -np.eye(m) / 1e6))
+    zx, zu = np.zeros((n, N)), np.zeros((m, N))
+    cases = []
+    for c in range(12):
+        e = 0.01 if c < 8 else 0.05
+        dA = rng.uniform(-e, e, size=(n, n))
+        dB = rng.uniform(-e, e, size=(n, m))
+        x0 = rng.normal(size=n)
+        ctl = uc.LQ_MPC_Controller(N, A + dA, B + dB, Q, R, Q, F_u)
+        K0 = np.column_stack([ctl.solve(np.eye(n)[:, i], zx, zu)['u_0'] for i in range(n)])
+        sol = ctl.solve(x0, zx, zu)
+        sim = uc.LQ_MPC_Simulator(T, N, A + dA, B + dB, Q, R, Q, F_u).simulate(x0, A, B, zx, zu)
+        cases.append({'dA': _l(dA), 'dB': _l(dB), 'x0': _l(x0), 'K0': _l(K0), 'V_N': float(sol['V_N']),
+                      'u_0': _l(sol['u_0']), 'J_T': float(sim['J_T']), 'x_T': _l(sim['X'][:, -1]),
+                      'U_head': _l(sim['U'][:, :5])})
+    return {'n': n, 'm': m, 'N': N, 'T': T, 'A': _l(A), 'B': _l(B), 'cases': cases}
+
+
+def main_round2():
+    """Adds tests/golden/ref_extension_cases.json and ref_cfg4_cases.json without touching the other fixtures."""
+    u, uc = ro.load()
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_shim_control", os.path.join(HERE, "shims", "control.py"))
+    ct = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ct)
+    with open(os.path.join(GOLD, "ref_extension_cases.json"), "w") as f:
+        json.dump(extension_cases(u, uc, ct), f, indent=0)
+    with open(os.path.join(GOLD, "ref_cfg4_cases.json"), "w") as f:
+        json.dump(cfg4_cases(uc), f, indent=0)
+    print("extension + cfg4 fixtures written")
+
+
+if __name__ == "__main__":
+    import sys as _sys
+    if "--round2" in _sys.argv:
+        main_round2()

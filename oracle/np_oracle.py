@@ -330,7 +330,8 @@ def local_radius(lo, hi, K, Q):
         for b in (lo[j], hi[j]):
             if np.isfinite(b):
                 a.append(kq / (b * b))
-    return 1.0 / max(a)
+    with np.errstate(divide='ignore'):
+        return float(np.float64(1.0) / np.float64(max(a)))      # numpy semantics: 1/0 = inf (utils.py:564)
 
 
 def ex_stability_lq(A, B, Q, R, K):
@@ -395,6 +396,38 @@ def energy_decreasing(A, B, Q, R, lo, hi, N, e_A, e_B, K, M_V, F_u=None):
     return {'xi': float(xi), 'eta': oe['eta'], 'epsilon_K': eps, 'h': float(h), **st, **bd,
             'omega_N1': oe['omega_N1'], 'omega_N0d5': oe['omega_N0d5'], 'err_th': oe['err_th'],
             'N_min': oe['N_min']}
+
+
+def fc_omega_eta_extension(N, A, B, Q, R, K, hatK, L_V, N_0):
+    """utils.py:412-466 — the variant with a second gain hatK: the terminal-cost propagation term becomes
+    C_K(hatK) + ||A + B K||_2^2 cond(Q) and N_min is NOT rounded up (no math.ceil at utils.py:446)."""
+    K, hatK = np.atleast_2d(K), np.atleast_2d(hatK)
+    f_A = norm2(A)
+    f_cl = norm2(A + B @ K)
+    iQ = my_eigen(Q)
+    G_A = geo_M(A, N - 1)
+    st = ex_stability_lq(A, B, Q, R, K)
+    st_dev = ex_stability_lq(A, B, Q, R, hatK)
+    term = st_dev['C_K'] + f_cl ** 2 * iQ['ratio']
+    N_min = N_0 - math.log((term - 1) * st['gamma']) / math.log(st['rho_gamma'])
+    w1 = iQ['max'] * (term * f_A ** (2 * N - 2) + G_A)
+    decay = iQ['max'] * f_A ** (2 * N - 2) * st['gamma'] * st['rho_gamma'] ** (N - N_0)
+    w05 = math.sqrt(iQ['max'] * (L_V - 1) * G_A) + 0.5 * term * math.sqrt(decay)
+    eta = (term - 1) * st['gamma'] * st['rho_gamma'] ** (N - N_0)
+    err_th = ((math.sqrt(w05 ** 2 + w1 * (1 - eta)) - w05) / w1) ** 2
+    return {'omega_N1': float(w1), 'omega_N0d5': float(w05), 'eta': float(eta), 'err_th': float(err_th),
+            'N_min': float(N_min)}
+
+
+def energy_decreasing_extension(A, B, Q, R, lo, hi, N, e_A, e_B, K, hatK, M_V):
+    """LQ_RDP_Calculator.energy_decreasing_extension (utils_class.py:375-406). K, hatK in the u = +Kx convention."""
+    eps = local_radius(lo, hi, K, Q)
+    st = ex_stability_lq(A, B, Q, R, K)
+    bd = ex_stability_bounds(st['gamma'], eps, M_V)
+    oe = fc_omega_eta_extension(N, A, B, Q, R, K, hatK, bd['L_V'], bd['N_0'])
+    h = fc_ec_h(e_A, e_B, Q, R)
+    xi = h * oe['omega_N1'] + 2 * math.sqrt(h) * oe['omega_N0d5']
+    return {'xi': float(xi), 'eta': oe['eta'], **oe}
 
 
 # ----------------------------------------------------------------------------------------------- a8: x0 ring

@@ -104,3 +104,18 @@ def relerr(a, b):
     if not fin.any():
         return 0.0
     return float(np.max(np.abs(a[fin] - b[fin]) / np.maximum(np.abs(b[fin]), 1e-300)))
+
+
+@pytest.fixture(scope="session")
+def extension_cases():
+    """energy_decreasing_extension / fc_omega_eta_extension runs of the untouched reference (make_golden.py --round2)."""
+    with open(os.path.join(GOLD, "ref_extension_cases.json")) as f:
+        return json.load(f)
+
+
+@pytest.fixture(scope="session")
+def cfg4():
+    """n = 4, m = 2, N = 10 (BASELINE configs[3]) through the untouched LQ_MPC_Controller / LQ_MPC_Simulator
+    (make_golden.py --round2): K0, V_N, J_T(T = 400)."""
+    with open(os.path.join(GOLD, "ref_cfg4_cases.json")) as f:
+        return json.load(f)

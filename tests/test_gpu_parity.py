@@ -2,7 +2,9 @@
 (lq_mpc_b200.engine -> liblqmpc_b200.so) or through the drop-in classes on top of it, and is compared with
   * the reference's shipped golden file and the answers generated from the untouched reference (tests/golden/),
   * the CPU oracle (oracle/np_oracle.py, oracle/np_batched.py) on the same seeded inputs.
-Tolerance: 1e-9 relative (BASELINE.json north_star) unless a test states a tighter one.
+Tolerance: 1e-9 relative (BASELINE.json north_star) unless a test states a tighter one. Where the engine and the
+float64 oracle differ by more than that, NEITHER is trusted: tests/mp_truth.py recomputes the quantity in 50-digit
+arithmetic and the engine must be within 1e-9 of THAT (or within the stated, computed condition bound).
 """
 import math
 import os
@@ -21,6 +23,22 @@ def _soa(dA, dB, x0):
     return nb.to_soa(dA, dB, x0)
 
 
+def _k1_arbitrate(A, B, Q, R, dA, dB, x0, N_min, got_J, ref_J, ref_rho, max_cases=12):
+    """Entries where engine and oracle disagree on J_inf by more than 1e-9 (only possible next to the stability
+    boundary, where J ~ 1/(1 - rho) is ill-conditioned): both are measured against the 50-digit value; the engine must
+    be within max(1e-9, 16 u rho / (1 - rho)) of it (mp_truth.j_condition_bound)."""
+    from tests import mp_truth as mt
+    fin = np.isfinite(ref_J) & np.isfinite(got_J)
+    err = np.where(fin, np.abs(got_J - ref_J) / np.where(fin, np.abs(ref_J), 1.0), 0.0)
+    bad = np.argwhere(err > TOL)
+    assert len(bad) <= max_cases, "engine and oracle disagree beyond 1e-9 on %d entries" % len(bad)
+    for h, s in bad:
+        t = mt.k1_truth(A, B, Q, R, Q, dA[s], dB[s], x0[s], N_min + h)
+        assert abs(got_J[h, s] - t["J"]) <= mt.j_condition_bound(t["rho"]) * abs(t["J"]), (h, s, t["rho"])
+        assert 1.0 - ref_rho[h, s] < 2e-6, "disagreement away from the stability boundary"
+    return len(bad)
+
+
 # ------------------------------------------------------------------------------------------------------- K1
 @pytest.mark.parametrize("n,m,e", [(4, 2, 0.01), (2, 1, 0.05), (1, 1, 0.1), (3, 2, 0.3), (3, 3, 0.1), (4, 1, 0.05),
                                    (4, 4, 0.2), (6, 2, 0.05), (8, 2, 0.02), (2, 2, 0.1), (3, 1, 0.1)])
@@ -35,13 +53,17 @@ def test_k1_matches_oracle(engine, n, m, e):
     got = engine.eval_batch(*_soa(dA, dB, x0), 2, 11, T=25, want=("J", "rho", "ratio", "flags", "V_N", "J_T", "K0"))
     g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
     assert relerr(engine.prepared()["Pexp"], Pexp) < 1e-12
-    # samples whose closed loop is within 1e-6 of the stability boundary have an ill-conditioned J_inf
-    well = np.abs(ref["rho"] - 1.0) > 1e-6
     assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"])
     for k, kr in (("rho", "rho"), ("V_N", "Vn"), ("J_T", "JT")):
         assert relerr(g[k], ref[kr]) < TOL, k
-    for k in ("J", "ratio"):
-        assert relerr(np.where(well, g[k], 0.0), np.where(well, ref[k], 0.0)) < 1e-8, k
+    # J_inf, ratio: 1e-9 on EVERY entry; an entry that misses it is arbitrated in 50-digit arithmetic (J ~ 1/(1 - rho)
+    # is ill-conditioned within ~2e-6 of the stability boundary — n = m = 1, e = 0.1 has a few such samples)
+    n_arb = _k1_arbitrate(A, B, Q, R, dA, dB, x0, 2, g["J"], ref["J"], ref["rho"])
+    assert np.array_equal(np.isfinite(g["J"]), np.isfinite(ref["J"]))
+    fin = np.isfinite(ref["J"])
+    assert np.max(np.abs(g["ratio"][fin] / g["J"][fin] - ref["ratio"][fin] / ref["J"][fin])
+                  * np.abs(ref["J"][fin] / ref["ratio"][fin])) < TOL      # ratio = J / V_expert: same V_expert
+    assert n_arb == 0 or (n, m) == (1, 1)
     K = g["K0"].reshape(10, m, n, S).transpose(0, 3, 1, 2)
     assert np.max(np.abs(K - ref["K0"])) < 1e-10 * max(1.0, np.max(np.abs(ref["K0"])))
     assert not np.any(g["flags"] & ~1)
@@ -71,6 +93,38 @@ def test_k1_per_sample_oracle_and_edges(engine):
     assert one["J"].shape == (1, 1) and float(one["J"][0, 0]) == J[5, 0]         # nested == single, bit for bit
     empty = engine.eval_batch(np.zeros((16, 0)), np.zeros((8, 0)), np.zeros((4, 0)), 1, 2)
     assert empty["J"].shape == (2, 0)
+
+
+def test_k1_cfg4_vs_untouched_reference(engine, cfg4):
+    """BASELINE configs[3] shape (n = 4, m = 2, N = 10) pinned on the reference ITSELF: twelve samples that went
+    through the untouched LQ_MPC_Controller / LQ_MPC_Simulator (utils_class.py:48-91, 245-285; loose input box, so the
+    cvxpy problem is the unconstrained one; T = 400). K1's first-step gain, V_N, J_T(400) and J_inf vs those answers,
+    and the exact-QP kernels (K2) on the same samples."""
+    A, B = np.array(cfg4["A"]), np.array(cfg4["B"])
+    n, m, N, T = cfg4["n"], cfg4["m"], cfg4["N"], cfg4["T"]
+    cs = cfg4["cases"]
+    dA = np.array([c["dA"] for c in cs]); dB = np.array([c["dB"] for c in cs]); x0 = np.array([c["x0"] for c in cs])
+    engine.set_problem(A, B, np.eye(n), np.eye(m), np.eye(n), None, None, 30)
+    got = engine.eval_batch(*_soa(dA, dB, x0), N, N, T=T, want=("J", "rho", "V_N", "J_T", "K0", "flags"))
+    g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
+    assert not g["flags"].any()
+    for s, c in enumerate(cs):
+        K = g["K0"][0, :, s].reshape(m, n)
+        assert np.max(np.abs(K - np.array(c["K0"]))) < 1e-10 * max(1.0, np.max(np.abs(K)))
+        assert abs(g["J_T"][0, s] - c["J_T"]) <= TOL * c["J_T"]                # finite sum, reference semantics
+        assert abs(g["J"][0, s] - c["J_T"]) <= TOL * c["J_T"]                  # Lyapunov limit == J_T(400) to rounding
+        assert abs(g["V_N"][0, s] - c["V_N"]) <= TOL * c["V_N"]
+        assert g["rho"][0, s] < 1.0
+    engine.set_problem(A, B, np.eye(n), np.eye(m), np.eye(n), -1e6 * np.ones(m), 1e6 * np.ones(m), 30)
+    sa, sb, sx = _soa(dA, dB, x0)
+    sol = engine.mpc_solve_batch(sa, sb, N, x0=sx)
+    sim = engine.simulate_batch(sa, sb, N, T, x0=sx, want=("J_T", "X", "U", "flags"))
+    assert not sol["flags"].cpu().numpy().any() and not sim["flags"].cpu().numpy().any()
+    for s, c in enumerate(cs):
+        assert abs(float(sol["V"][0, s]) - c["V_N"]) <= TOL * c["V_N"]
+        assert np.max(np.abs(sol["u0"].cpu().numpy()[0, :, s] - np.array(c["u_0"]))) < 1e-10
+        assert abs(float(sim["J_T"][s]) - c["J_T"]) <= TOL * c["J_T"]
+        assert np.max(np.abs(sim["U"].cpu().numpy()[:5, :, s].T - np.array(c["U_head"]))) < 1e-10
 
 
 def test_k1_unstable_flagged(engine):
@@ -323,8 +377,10 @@ def test_general_input_polytope(engine, polytope):
     assert torch.equal(pol["flags"], box["flags"]) and bool((box["flags"] & 2).any())
     with pytest.raises(EngineError):
         engine.set_input_polytope(np.ones((13, m)))                      # more than 12 rows
-    too_long = engine.mpc_solve_batch(dA[:, :8], dB[:, :8], 40, x0=5 * x0[:, :8])   # N * p = 160 > 128
-    assert bool((too_long["flags"] & 4).all())
+    too_long = engine.mpc_solve_batch(dA[:, :8], dB[:, :8], 70, x0=5 * x0[:, :8])   # N * p = 280 > 256
+    assert bool((too_long["flags"] & 4).all()) and bool(torch.isnan(too_long["V"]).all())
+    Fbox = np.vstack((np.diag(1 / hi), np.diag(1 / lo)))
+    assert float((Fbox @ too_long["u0"][0].cpu().numpy()).max()) <= 1.0 + 1e-12       # shrunk onto the polytope
     engine.set_input_polytope(None)
     again = engine.simulate_batch(dA, dB, N, 8, x0=x0, want=("J_T", "U", "flags"))
     assert torch.equal(again["J_T"], box["J_T"]) and torch.equal(again["U"], box["U"])
@@ -336,7 +392,8 @@ def test_clqr_stress_vs_dense_qp(engine):
     from oracle import np_oracle as o
     rng = np.random.default_rng(11)
     n_active = 0
-    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1)]:
+    n_arb = 0
+    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1), (6, 2), (8, 2)]:
         for rep in range(3):
             N = int(rng.integers(2, min(24, 64 // m) + 1))
             A = rng.normal(size=(n, n))
@@ -357,32 +414,53 @@ def test_clqr_stress_vs_dense_qp(engine):
             for s in range(0, S, 5):
                 ur, Vr, _ = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi,
                                         x0[:, s], exact_fast=False)
-                assert abs(V[0, s] - Vr) < 1e-8 * abs(Vr)
-                assert np.max(np.abs(u0[0, :, s] - ur)) < 1e-8
-    assert n_active > 100
+                if abs(V[0, s] - Vr) < TOL * abs(Vr) and np.max(np.abs(u0[0, :, s] - ur)) < TOL:
+                    continue
+                # engine and dense-Cholesky oracle disagree beyond 1e-9: certify the oracle's active set in 50-digit
+                # arithmetic and hold the ENGINE to 1e-9 against that solution
+                from tests import mp_truth as mt
+                Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+                H, gq, _ = o.condensed_qp(N, Ah, Bh, Q, R, Q, x0[:, s])
+                z = o.box_qp(H, gq, np.tile(lo, N), np.tile(hi, N))
+                ut, Vt, ok = mt.qp_truth(N, Ah, Bh, Q, R, Q, lo, hi, x0[:, s], np.flatnonzero(z <= np.tile(lo, N)),
+                                         np.flatnonzero(z >= np.tile(hi, N)))
+                assert ok, "oracle active set not optimal in extended precision"
+                assert abs(V[0, s] - Vt) < TOL * abs(Vt) and np.max(np.abs(u0[0, :, s] - ut)) < TOL, (n, m, N, s)
+                n_arb += 1
+    assert n_active > 100 and n_arb <= 10
 
 
 def test_clqr_max_working_set_size(engine):
-    """N*m = 128 is the largest working set (128-bit mask): N = 64 and N = 128 (m = 1) and N = 64 with m = 2 are
-    solved exactly; N*m = 129 with an active bound must flag QP_MAXITER instead of answering."""
+    """N*m = 256 is the largest working set (256-bit mask): N = 64, 128, 256 (m = 1) and N = 64, 128 with m = 2 are
+    solved exactly; N*m = 257 with an active bound must flag QP_MAXITER, return V = NaN and a first input clipped into
+    the box (never an approximation, never uninitialised memory), and the drop-in controller must raise on it."""
     from oracle import np_oracle as o
+    from lq_mpc_b200.engine import EngineError
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller
     A = np.array([[1.0, 0.3], [0.0, 1.0]]); B = np.array([[0.0], [1.0]])
     engine.set_problem(A, B, np.eye(2), np.eye(1), np.eye(2), [-0.05], [0.05], 10)
     x0 = np.array([[1.0], [0.5]])
-    for N in (64, 128):
+    for N in (64, 128, 256):
         got = engine.mpc_solve_batch(None, None, N, x0=x0, S=1)
         ur, Vr, act = o.mpc_solve(N, A, B, np.eye(2), np.eye(1), np.eye(2), np.array([-0.05]), np.array([0.05]),
                                   x0[:, 0], exact_fast=False)
-        assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
+        assert act and abs(float(got["V"][0, 0]) - Vr) < TOL * Vr and int(got["flags"][0, 0]) == 2
         assert abs(float(got["u0"][0, 0, 0]) - ur[0]) < 1e-9
-    over = engine.mpc_solve_batch(None, None, 129, x0=x0, S=1)
-    assert int(over["flags"][0, 0]) & 4
+    over = engine.mpc_solve_batch(None, None, 257, x0=x0, S=1)
+    assert int(over["flags"][0, 0]) & 4 and math.isnan(float(over["V"][0, 0]))
+    assert -0.05 <= float(over["u0"][0, 0, 0]) <= 0.05
+    sim = engine.simulate_batch(None, None, 257, 3, x0=x0, S=1, want=("J_T", "U", "flags"))
+    assert int(sim["flags"][0]) & 4 and float(sim["U"].abs().max()) <= 0.05
+    with pytest.raises(EngineError):
+        LQ_MPC_Controller(257, A, B, np.eye(2), np.eye(1), np.eye(2), np.array([[20.0], [-20.0]])).solve(
+            x0[:, 0], np.zeros((2, 257)), np.zeros((1, 257)))
     B2 = np.array([[0.0, 0.1], [1.0, 0.0]])
     lo2, hi2 = np.array([-0.05, -0.2]), np.array([0.05, 0.2])
     engine.set_problem(A, B2, np.eye(2), np.eye(2), np.eye(2), lo2, hi2, 10)
-    got = engine.mpc_solve_batch(None, None, 64, x0=x0, S=1)
-    ur, Vr, act = o.mpc_solve(64, A, B2, np.eye(2), np.eye(2), np.eye(2), lo2, hi2, x0[:, 0], exact_fast=False)
-    assert act and abs(float(got["V"][0, 0]) - Vr) < 1e-8 * Vr and int(got["flags"][0, 0]) == 2
+    for N in (64, 128):
+        got = engine.mpc_solve_batch(None, None, N, x0=x0, S=1)
+        ur, Vr, act = o.mpc_solve(N, A, B2, np.eye(2), np.eye(2), np.eye(2), lo2, hi2, x0[:, 0], exact_fast=False)
+        assert act and abs(float(got["V"][0, 0]) - Vr) < TOL * Vr and int(got["flags"][0, 0]) == 2
 
 
 # ------------------------------------------------------------------------------------------------------- K3
@@ -432,6 +510,36 @@ def test_working_example_single(known):
         assert abs(E[f] - k["E"][f]) < TOL * abs(k["E"][f]), f
     for f in ("theta_u", "theta_x_u"):
         assert abs(th[f] - k["theta"][f]) < TOL * abs(k["theta"][f]), f
+
+
+def test_extension_variant_vs_untouched_reference(extension_cases):
+    """LQ_RDP_Calculator.energy_decreasing_extension / utils.fc_omega_eta_extension
+    (utils_class.py:375-406, utils.py:412-466) through the drop-in modules vs fourteen runs of the untouched reference
+    (m = 1), including the five where the reference raises ValueError (math.log of a non-positive number)."""
+    from lq_mpc_b200.utils import ex_stability_bounds, ex_stability_lq, fc_omega_eta_extension, local_radius
+    from lq_mpc_b200.utils_class import LQ_RDP_Calculator
+    n_raise = n_ok = 0
+    for c in extension_cases:
+        n = c["n"]
+        A, B, K, hatK = (np.array(c[k]) for k in ("A", "B", "K", "hatK"))
+        Q, R = c["q"] * np.eye(n), c["r"] * np.eye(1)
+        F_u = np.array([[1 / c["ub"]], [-1 / c["ub"]]])
+        calc = LQ_RDP_Calculator(A, B, Q, R, F_u)
+        if "raises" in c:
+            with pytest.raises(ValueError):
+                calc.energy_decreasing_extension(c["N"], c["e"], c["e"], K, hatK, c["M_V"])
+            n_raise += 1
+            continue
+        eps = local_radius(F_u, K, Q)
+        bd = ex_stability_bounds(ex_stability_lq(A, B, Q, R, K)["gamma"], eps, c["M_V"])
+        assert bd["N_0"] == c["N_0"] and abs(bd["L_V"] - c["L_V"]) <= TOL * c["L_V"]
+        oe = fc_omega_eta_extension(c["N"], A, B, Q, R, K, hatK, bd["L_V"], bd["N_0"])
+        for f in ("omega_N1", "omega_N0d5", "eta", "err_th", "N_min"):
+            assert abs(oe[f] - c["omega_eta"][f]) <= TOL * abs(c["omega_eta"][f]), f
+        dec = calc.energy_decreasing_extension(c["N"], c["e"], c["e"], K, hatK, c["M_V"])
+        assert abs(dec["xi"] - c["xi"]) <= TOL * abs(c["xi"]) and abs(dec["eta"] - c["eta"]) <= TOL * abs(c["eta"])
+        n_ok += 1
+    assert n_ok >= 8 and n_raise >= 1
 
 
 def test_behavior_test_scenario(known):
@@ -518,7 +626,7 @@ def test_bounds_detail_vs_oracle(engine):
     from oracle import np_oracle as o
     rng = np.random.default_rng(5)
     checked = 0
-    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1), (1, 1)]:
+    for n, m in [(2, 1), (2, 2), (3, 1), (3, 2), (4, 2), (4, 1), (1, 1), (6, 2), (8, 2)]:
         for general in (False, True):
             for strict in ((True, False) if general else (True,)):
                 N = int(rng.integers(1, 13))
@@ -555,8 +663,12 @@ def test_bounds_detail_vs_oracle(engine):
                     for f in ("xi", "eta", "C_K", "rho_K", "gamma", "rho_gamma", "L_V", "N_0", "omega_N1",
                               "omega_N0d5", "err_th", "N_min", "h", "epsilon_K"):
                         assert abs(g[f][s] - dec[f]) <= TOL * abs(dec[f]), (n, m, general, f)
-                    bound = (bnd["alpha"] * 0.37 + bnd["beta"]) / (1 - dec["xi"] - dec["eta"])
-                    assert abs(g["bound"][s] - bound) <= 1e-8 * abs(bound)
+                    den = 1 - dec["xi"] - dec["eta"]
+                    bound = (bnd["alpha"] * 0.37 + bnd["beta"]) / den
+                    # alpha, beta, xi, eta each hold 1e-9 (asserted above); the quotient propagates the errors of
+                    # xi and eta with the computed factor (|xi| + |eta|) / |1 - xi - eta|
+                    kappa = 1.0 + (abs(dec["xi"]) + abs(dec["eta"])) / abs(den)
+                    assert abs(g["bound"][s] - bound) <= TOL * kappa * abs(bound)
                     checked += 1
     assert checked > 40
 
@@ -699,14 +811,28 @@ def test_k4_tiled_matches_oracle(engine, n, m, e, dmma, monkeypatch):
     assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"])
     if e >= 0.2:
         assert ref["unstable"].any() and not ref["unstable"].all()
-    well = np.abs(ref["rho"] - 1.0) > 1e-6
-    # e = 0.2 drives the 30-step recursion of a 32-state, open-loop-unstable model to costs ~1e2-1e3 with a
-    # conditioning of ~1e7: two FP64 summation orders agree to ~1e-9 only; that case checks flags / stability logic.
-    tol = 1e-7 if e >= 0.2 else TOL
-    assert relerr(g["rho"], ref["rho"]) < tol
-    assert relerr(g["V_N"], ref["Vn"]) < tol
-    for k in ("J", "ratio"):
-        assert relerr(np.where(well, g[k], 0.0), np.where(well, ref[k], 0.0)) < 10 * tol, k
+    if e < 0.2:
+        assert relerr(g["rho"], ref["rho"]) < TOL and relerr(g["V_N"], ref["Vn"]) < TOL
+        for k in ("J", "ratio"):
+            assert relerr(g[k], ref[k]) < TOL, k
+    else:
+        # e = 0.2 drives the 30-step recursion of a 32-state, open-loop-unstable model to costs ~1e2-1e3; engine and
+        # float64 oracle use different summation orders. Entries beyond 1e-9 are arbitrated in extended precision
+        # (numpy longdouble, 64-bit mantissa: tests/mp_truth.k1_truth_ld) together with the MEASURED conditioning of the
+        # sample (relative change of the value under a 1e-13 relative perturbation of dA): the engine must be within
+        # max(1e-9, 64 u kappa) of the extended-precision value, and closer to it than 1e-7 in any case.
+        from tests import mp_truth as mt
+        for k, kr in (("V_N", "Vn"), ("J", "J"), ("rho", "rho")):
+            fin = np.isfinite(ref[kr])
+            err = np.where(fin, np.abs(g[k] - ref[kr]) / np.where(fin, np.abs(ref[kr]), 1.0), 0.0)
+            bad = np.argwhere(err > TOL)
+            worst = sorted(bad.tolist(), key=lambda hs: -err[hs[0], hs[1]])[:3]
+            for h, s in worst:
+                t = mt.k1_truth_ld(A, B, Q, R, Q, dA[s], dB[s], x0[s], N - 2 + h)
+                key = {"V_N": "Vn", "J": "J", "rho": "rho"}[k]
+                tol_s = max(TOL, 64 * 2.0 ** -53 * t["kappa_" + key])
+                assert abs(g[k][h, s] - t[key]) <= min(tol_s, 1e-7) * abs(t[key]), (k, h, s, t["kappa_" + key])
+            assert err.max() < 1e-6, k
     assert not np.any(g["flags"] & ~1)
     one = engine.eval_batch_tiled(dA, dB, x0, N, N)      # 3-buffer plan (A^ and P storage reused by the doubling)
     assert relerr(one["J"].cpu().numpy()[0], g["J"][2]) < 1e-12

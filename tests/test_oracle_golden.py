@@ -191,6 +191,51 @@ def test_oracle_general_polytope_cases(polytope):
 
 
 # ------------------------------------------------------------------------------------------- analytic cross-checks
+def test_oracle_extension_variant(extension_cases):
+    """energy_decreasing_extension / fc_omega_eta_extension (utils_class.py:375-406, utils.py:412-466): the oracle
+    restatement vs the untouched reference, including the cases where the reference raises (math.log of a
+    non-positive number)."""
+    n_raise = n_ok = 0
+    for c in extension_cases:
+        n = c["n"]
+        A, B, K, hatK = (np.array(c[k]) for k in ("A", "B", "K", "hatK"))
+        Q, R = c["q"] * np.eye(n), c["r"] * np.eye(1)
+        lo, hi = np.array([-c["ub"]]), np.array([c["ub"]])
+        if "raises" in c:
+            with pytest.raises(ValueError):
+                o.energy_decreasing_extension(A, B, Q, R, lo, hi, c["N"], c["e"], c["e"], K, hatK, c["M_V"])
+            n_raise += 1
+            continue
+        oe = o.fc_omega_eta_extension(c["N"], A, B, Q, R, K, hatK, c["L_V"], c["N_0"])
+        for f in ("omega_N1", "omega_N0d5", "eta", "err_th", "N_min"):
+            assert abs(oe[f] - c["omega_eta"][f]) <= TOL * abs(c["omega_eta"][f]), f
+        dec = o.energy_decreasing_extension(A, B, Q, R, lo, hi, c["N"], c["e"], c["e"], K, hatK, c["M_V"])
+        assert abs(dec["xi"] - c["xi"]) <= TOL * abs(c["xi"]) and abs(dec["eta"] - c["eta"]) <= TOL * abs(c["eta"])
+        n_ok += 1
+    assert n_ok >= 8 and n_raise >= 1
+
+
+def test_oracle_cfg4_samples_vs_untouched_reference(cfg4):
+    """BASELINE configs[3] shape (n = 4, m = 2, N = 10): the restatement AND the batched K1 oracle vs the untouched
+    LQ_MPC_Controller / LQ_MPC_Simulator — first-step gain, V_N, J_T over T = 400 steps (= J_inf to rounding)."""
+    A, B = np.array(cfg4["A"]), np.array(cfg4["B"])
+    n, m, N, T = cfg4["n"], cfg4["m"], cfg4["N"], cfg4["T"]
+    Q, R = np.eye(n), np.eye(m)
+    cs = cfg4["cases"]
+    dA = np.array([c["dA"] for c in cs]); dB = np.array([c["dB"] for c in cs]); x0 = np.array([c["x0"] for c in cs])
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    bat = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, N, N, T=T, want_K=True)
+    for s, c in enumerate(cs):
+        K = o.riccati(A + dA[s], B + dB[s], Q, R, Q, N)[0][0]
+        assert np.max(np.abs(K - np.array(c["K0"]))) < 1e-10 * max(1.0, np.max(np.abs(K)))
+        assert np.max(np.abs(bat["K0"][0, s] - np.array(c["K0"]))) < 1e-10 * max(1.0, np.max(np.abs(K)))
+        J_inf, rho = o.closed_loop_inf_cost(A, B, K, Q, R, x0[s])
+        assert rho < 1 and abs(J_inf - c["J_T"]) <= TOL * c["J_T"]
+        assert abs(bat["J"][0, s] - c["J_T"]) <= TOL * c["J_T"] and abs(bat["JT"][0, s] - c["J_T"]) <= TOL * c["J_T"]
+        assert abs(bat["Vn"][0, s] - c["V_N"]) <= TOL * c["V_N"]
+        assert np.max(np.abs(K @ x0[s] - np.array(c["u_0"]))) < 1e-10
+
+
 def test_riccati_equals_condensed_qp_when_unconstrained():
     """utils_class.py:59-91 unconstrained == Riccati: u_0 = K_0 x0, V_N = x0' P_0 x0."""
     rng = np.random.default_rng(0)
