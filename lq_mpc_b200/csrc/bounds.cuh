@@ -12,12 +12,15 @@
 //   fc_ec_theta, fc_ec_E            utils.py:226-334
 //   energy_bound / energy_decreasing  utils_class.py:308-373 ; J_bound  utils_class.py:858-859
 //
-// ||Gamma||_2 and lambda_min(H^) need extreme eigenvalues of (N m) x (N m) symmetric matrices: the Gram matrix
-// Gamma'Gamma is assembled by a block recurrence (O(N^2 m^2 n)), reduced to tridiagonal form by Householder
-// reflections inside the strided per-thread workspace and the two extreme eigenvalues are located by Sturm
-// bisection. When Q = qI and R = rI (every shipped scenario) H^ = rI + q Gamma'Gamma shares that reduction.
+// ||Gamma||_2 and lambda_min(H^) need extreme eigenvalues of (N m) x (N m) symmetric matrices. They are obtained
+// MATRIX-FREE (gramspec.cuh): Gamma is a simulation operator, so "H^ - x I is positive definite" is decided by an
+// N-stage Riccati-type elimination on n x n blocks and the extremes follow by bisection — O(N n^3) per probe, no
+// scratch memory. Only the literal kron(Q, I) weight ordering of utils.py:317-318 with NON-scalar Q, R (not a stage-wise
+// cost) still takes the dense route: Gram matrix by a block recurrence (O(N^2 m^2 n)), Householder tridiagonalisation
+// inside the strided per-thread workspace, Sturm bisection (also reachable with LQMPC_K3_DENSE=1 for A/B tests).
 #pragma once
 #include "clqr.cuh"
+#include "gramspec.cuh"
 
 namespace lq {
 
@@ -236,19 +239,24 @@ template <int n, int m>
 struct BoundsLayout {
   int N, k;
   int64_t oG, oC, od, oe, total;
-  // compact: the Gram spectrum comes precomputed (warp-per-sample kernel, k_gram.cu) — only G_d is kept per thread
-  LQ_HD explicit BoundsLayout(int N_, bool compact = false) : N(N_), k(N_ * m) {
+  LQ_HD explicit BoundsLayout(int N_) : N(N_), k(N_ * m) {
     oG = 0;
     oC = oG + (int64_t)N * n * m;
-    od = oC + (compact ? 0 : (int64_t)k * k);
-    oe = od + (compact ? 0 : k);
-    total = oe + (compact ? 0 : k);
+    od = oC + (int64_t)k * k;
+    oe = od + k;
+    total = oe + k;
   }
 };
 
+// per-thread scratch of the DENSE route only (the matrix-free route needs none)
 template <int n, int m>
-LQ_HD int64_t bounds_ws_doubles(int N, bool compact = false) {
-  return BoundsLayout<n, m>(N, compact).total;
+LQ_HD int64_t bounds_ws_doubles(int N) {
+  return BoundsLayout<n, m>(N).total;
+}
+
+// which route a problem takes (host and device agree through this one predicate)
+LQ_HD bool bounds_matrix_free(int qr_scalar, int strict_reference, int force_dense) {
+  return (qr_scalar || !strict_reference) && !force_dense;
 }
 
 struct BoundsScalars {
@@ -258,8 +266,7 @@ struct BoundsScalars {
   double V_expert;
   double bar_u, bar_d_u;   // < 0: derive from the input box
   int strict_reference;    // literal kron ordering of utils.py:317-318 (only matters when Q, R are not scalar)
-  int has_gram = 0;        // extreme eigenvalues of Gamma'Gamma supplied by gram_extremes_kernel (Q = qI, R = rI only)
-  double cmin = 0.0, cmax = 0.0;
+  int force_dense = 0;     // take the dense Householder route even where the matrix-free one applies (A/B tests)
   const double* polyF = nullptr;   // general input polytope rows [p][m] (then bar_u / bar_d_u must be supplied), or NULL
   int polyP = 0;
 };
@@ -275,8 +282,9 @@ LQ_HD double gamma_entry(const WsView& ws, const BoundsLayout<n, m>& L, int t, i
 template <int n, int m>
 LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double* Bh, const double* K,
                         const double* x, const BoundsScalars& sc, const WsView& ws, double* out) {
-  const BoundsLayout<n, m> L(sc.N, sc.has_gram != 0);
+  const BoundsLayout<n, m> L(sc.N);
   const int N = sc.N, k = L.k;
+  const bool matrix_free = bounds_matrix_free(pb.qr_scalar, sc.strict_reference, sc.force_dense);
   int flags = 0;
   LQ_UNROLL for (int i = 0; i < BF_COUNT; ++i) out[i] = 0.0;
   // ---------------- input-set constants (utils.py:592-650 for a box: attained at vertices)
@@ -367,12 +375,13 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
   {
     double Gd[n * m], Mt[n * n], acc[n * n];
     LQ_UNROLL for (int i = 0; i < n * m; ++i) Gd[i] = Bh[i];
-    for (int d = 0; d < N; ++d) {
-      LQ_UNROLL for (int e = 0; e < n * m; ++e) ws[L.oG + (int64_t)d * (n * m) + e] = Gd[e];
-      double Gn[n * m];
-      mm<n, n, m>(Ah, Gd, Gn);
-      LQ_UNROLL for (int i = 0; i < n * m; ++i) Gd[i] = Gn[i];
-    }
+    if (!matrix_free)
+      for (int d = 0; d < N; ++d) {
+        LQ_UNROLL for (int e = 0; e < n * m; ++e) ws[L.oG + (int64_t)d * (n * m) + e] = Gd[e];
+        double Gn[n * m];
+        mm<n, n, m>(Ah, Gd, Gn);
+        LQ_UNROLL for (int i = 0; i < n * m; ++i) Gd[i] = Gn[i];
+      }
     LQ_UNROLL for (int i = 0; i < n; ++i)
       LQ_UNROLL for (int j = 0; j < n; ++j) { Mt[i * n + j] = (i == j) ? 1.0 : 0.0; acc[i * n + j] = Mt[i * n + j]; }
     for (int t = 1; t <= N; ++t) {
@@ -386,9 +395,14 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     sym_eig_minmax<n>(acc, &lo, &hi);
     out[BF_NORM_PHI] = sqrt(dmax(hi, 0.0));
   }
-  // ---------------- Gamma'Gamma by the block recurrence C[j][j'] = C[j+1][j'+1] + G_{N-1-j}' G_{N-1-j'}
-  double cmin = sc.cmin, cmax = sc.cmax;
-  if (!sc.has_gram) {
+  double cmin = 0.0, cmax = 0.0, min_H;
+  if (matrix_free) {
+    // ---------------- matrix-free: bisection on the N-stage elimination (gramspec.cuh); Q, R enter stage-wise
+    const GramSpectrum gs = gram_spectrum<n, m>(Ah, Bh, pb.Q, pb.R, minR, N);
+    cmax = gs.cmax;
+    min_H = gs.min_H;
+  } else {
+  // ---------------- dense: Gamma'Gamma by the block recurrence C[j][j'] = C[j+1][j'+1] + G_{N-1-j}' G_{N-1-j'}
   for (int j = N - 1; j >= 0; --j)
     for (int jp = j; jp >= 0; --jp) {
       double ga[n * m], gb[n * m];
@@ -406,10 +420,6 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     }
   ws_tridiagonalize(ws, L.oC, L.od, L.oe, k);
   ws_tridiag_extremes(ws, L.od, L.oe, k, &cmin, &cmax);
-  }
-  const double nG = sqrt(dmax(cmax, 0.0));
-  out[BF_NORM_GAMMA] = nG;
-  double min_H;
   if (pb.qr_scalar) {
     min_H = pb.R[0] + pb.Q[0] * cmin;
   } else {
@@ -446,6 +456,9 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     ws_tridiagonalize(ws, L.oC, L.od, L.oe, k);
     ws_tridiag_extremes(ws, L.od, L.oe, k, &min_H, &hmax);
   }
+  }
+  const double nG = sqrt(dmax(cmax, 0.0));
+  out[BF_NORM_GAMMA] = nG;
   out[BF_MIN_H] = min_H;
   // ---------------- error-consistent sums (utils.py:78-117, 186-223, 296-305)
   double nx2 = 0.0;

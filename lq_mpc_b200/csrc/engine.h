@@ -114,7 +114,7 @@ struct BoundsArgs {
   double* P_out;          // [n*n][S] (DARE solution; only when the gain is computed here)
   int32_t* flags;
   double* ws;
-  const double* gtri = nullptr;   // [2 N m][S] tridiagonal form of Gamma'Gamma from gram_extremes_kernel, or NULL
+  int dense = 0;                  // force the dense Householder route (LQMPC_K3_DENSE; A/B tests)
   const double* polyF = nullptr;  // general input polytope rows (device, [p][m]) for local_radius, or NULL -> the box
   int polyP = 0;
 };
@@ -152,8 +152,6 @@ int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, in
 bool lq_tiled_supported(int n, int m);
 size_t lq_tiled_pb_doubles(int n, int m);
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);
-bool lq_gram_warp_eligible(int n, int m, int N);
-int lq_launch_gram(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, double* tri);
 int lq_launch_sampler(lqmpc_ctx* ctx, uint64_t seed, int which, int rows, int cols, int64_t N_sys, int64_t j_first,
                       int n_err, const double* levels_host, int64_t n_boundary, int norm_type, double* out,
                       int64_t* stats_host);

@@ -1,0 +1,151 @@
+// gramspec.cuh — extreme eigenvalues of the horizon-N Gram operators WITHOUT forming them (matrix-free, O(N n^3) per probe).
+//
+// energy_bound needs ||Gamma||_2 = sqrt(lambda_max(Gamma'Gamma)) and lambda_min(H^), H^ = barR + Gamma' barQ Gamma
+// (reference utils.py:248-258: np.linalg.norm(Gamma, 2); utils.py:316-322: np.min(np.linalg.eigvals(hatH))) where
+// Gamma (utils.py:145-174) is the block lower-triangular Toeplitz map from the stacked inputs u_0..u_{N-1} to the
+// stacked states x_0..x_N of x+ = A x + B u, x_0 = 0. Both matrices are (N m) x (N m); round 1 assembled the Gram
+// matrix and reduced it by Householder reflections ((N m)^3 flops, (N m)^2 doubles of scratch per sample).
+//
+// Gamma is a SIMULATION OPERATOR, so the quadratic form it induces is an N-stage LQ cost,
+//     u' (barR - x I + Gamma' barQ Gamma) u  =  sum_t  x_t' Q x_t + u_t' (R - x I) u_t ,   x_{t+1} = A x_t + B u_t, x_0 = 0,
+// and dynamic programming from the last stage eliminates u_{N-1}, ..., u_0 one block at a time:
+//     G_s = (R - x I) + B' P B,     P <- Q + A' (P - P B G_s^-1 B' P) A,     P_0 = Q        (s = 1..N)
+// This IS the block LDL' factorisation of the (N m) x (N m) matrix in that elimination order (Sylvester: its inertia is
+// the sum of the inertias of the G_s). Hence
+//     H^ - x I  positive definite   <=>   every G_s is positive definite              (lambda_min(H^) > x)
+//     x I - Gamma'Gamma  pos. def.  <=>   every G'_s = x I - B' P B is pos. def. with P <- I + A'(P + P B G'_s^-1 B' P) A
+// Each probe is a Cholesky factorisation in disguise: when every pivot is positive the computed factors are the exact
+// factors of a matrix within a few ulps ||.|| of the probed one, so the yes/no answer is reliable down to the same
+// backward error LAPACK's eigvals has on the assembled matrix. The two extremes are located by bisection on these
+// one-sided predicates: ~52 probes x N stages x O(n^3) flops, all in registers, no scratch memory, one sample per
+// thread with two independent recursions (the two searches) interleaved for instruction-level parallelism.
+// General (non-scalar) weights in the time-major convention cost nothing extra: Q and R simply enter the recursion.
+// (The literal kron(Q, I) ordering of utils.py:317-318 with non-scalar Q is NOT a stage-wise cost; it stays on the
+// dense path of bounds.cuh.)
+#pragma once
+#include "riccati.cuh"
+
+namespace lq {
+
+// One elimination stage. G = Rd + sigma B'PB (Rd already carries the shift), Cholesky test, and unless `last`
+// P <- Qw + A' (P - sigma (P B) G^-1 (P B)') A. Returns "G is positive definite".
+template <int n, int m>
+LQ_HD bool gs_stage(const double* Ah, const double* Bh, const double* Qw, const double* Rd, double sigma, bool last,
+                    double* P) {
+  double Y[n * m], L[m * m], Li[m];
+  mm<n, n, m>(P, Bh, Y);
+  LQ_UNROLL for (int i = 0; i < m; ++i)
+    LQ_UNROLL for (int j = 0; j <= i; ++j) {
+      double acc = 0.0;
+      LQ_UNROLL for (int k = 0; k < n; ++k) acc = fma(Bh[k * m + i], Y[k * m + j], acc);
+      const double g = fma(sigma, acc, Rd[i * m + j]);
+      L[i * m + j] = g;
+      L[j * m + i] = g;
+    }
+  const bool ok = chol_inv<m>(L, Li);
+  if (last) return ok;
+  solve_right_lt_inv<n, m>(L, Li, Y);             // Y = P B L^-T
+  double Mx[n * n], MA[n * n];
+  LQ_UNROLL for (int i = 0; i < n; ++i)
+    LQ_UNROLL for (int j = i; j < n; ++j) {
+      double acc = 0.0;
+      LQ_UNROLL for (int k = 0; k < m; ++k) acc = fma(Y[i * m + k], Y[j * m + k], acc);
+      const double v = fma(-sigma, acc, P[i * n + j]);
+      Mx[i * n + j] = v;
+      Mx[j * n + i] = v;
+    }
+  mm<n, n, n>(Mx, Ah, MA);
+  sym_add_mtm<n, n>(Qw, Ah, MA, P);
+  return ok;
+}
+
+struct GramSpectrum {
+  double min_H;    // lambda_min(barR + Gamma' barQ Gamma), time-major weights (== R[0] + Q[0] lambda_min(Gamma'Gamma) for scalar weights)
+  double cmax;     // lambda_max(Gamma'Gamma)
+  int probes;      // bisection passes used (diagnostics)
+};
+
+// Both extremes for the estimated model (Ah, Bh) and horizon N. Q, R: stage weights (R positive definite, Q >= 0);
+// minR = lambda_min(R).
+template <int n, int m>
+LQ_HD GramSpectrum gram_spectrum(const double* Ah, const double* Bh, const double* Q, const double* R, double minR,
+                                 int N) {
+  double eye[n * n];
+  LQ_UNROLL for (int i = 0; i < n; ++i)
+    LQ_UNROLL for (int j = 0; j < n; ++j) eye[i * n + j] = (i == j) ? 1.0 : 0.0;
+  // ---- brackets. lambda_max(Gamma'Gamma): Rayleigh quotients of the unit inputs at stage 0 from below, the l1 bound
+  //      on a Toeplitz operator norm (sum of the impulse-response norms) from above.
+  double colsq[m], sumF = 0.0;
+  LQ_UNROLL for (int j = 0; j < m; ++j) colsq[j] = 0.0;
+  {
+    double Gd[n * m];
+    LQ_UNROLL for (int e = 0; e < n * m; ++e) Gd[e] = Bh[e];
+    for (int d = 0; d < N; ++d) {
+      double fro = 0.0;
+      LQ_UNROLL for (int r = 0; r < n; ++r)
+        LQ_UNROLL for (int j = 0; j < m; ++j) {
+          const double g = Gd[r * m + j];
+          colsq[j] = fma(g, g, colsq[j]);
+          fro = fma(g, g, fro);
+        }
+      sumF += sqrt(fro);
+      double Gn[n * m];
+      mm<n, n, m>(Ah, Gd, Gn);
+      LQ_UNROLL for (int e = 0; e < n * m; ++e) Gd[e] = Gn[e];
+    }
+  }
+  double loC = 0.0;
+  LQ_UNROLL for (int j = 0; j < m; ++j) loC = dmax(loC, colsq[j]);
+  loC *= (1.0 - 1e-14);
+  double hiC = sumF * sumF * (1.0 + 1e-14);
+  // lambda_min(H^): H^ >= barR from below; the Rayleigh quotient of a unit input at the LAST stage (it only moves x_N)
+  // from above: min_j (R + B'QB)_jj.
+  double loH = minR * (1.0 - 1e-15), hiH = HUGE_VAL;
+  {
+    double QB[n * m];
+    mm<n, n, m>(Q, Bh, QB);
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      double acc = R[j * m + j];
+      LQ_UNROLL for (int k = 0; k < n; ++k) acc = fma(Bh[k * m + j], QB[k * m + j], acc);
+      hiH = dmin(hiH, acc);
+    }
+    hiH *= (1.0 + 1e-14);
+  }
+  GramSpectrum out;
+  bool liveH = (hiH > loH), liveC = (hiC > loC) && (hiC == hiC) && (hiC < 1.7e308);
+  if (!(hiC == hiC) || !(hiC < 1.7e308)) { loC = hiC = sumF * sumF; }      // overflow / NaN operands: propagate
+  int pass = 0;
+  for (; pass < 128 && (liveH || liveC); ++pass) {
+    const double xH = 0.5 * (loH + hiH), xC = 0.5 * (loC + hiC);
+    double RdH[m * m], RdC[m * m], PH[n * n], PC[n * n];
+    LQ_UNROLL for (int i = 0; i < m; ++i)
+      LQ_UNROLL for (int j = 0; j < m; ++j) {
+        RdH[i * m + j] = R[i * m + j] - ((i == j) ? xH : 0.0);
+        RdC[i * m + j] = (i == j) ? xC : 0.0;
+      }
+    LQ_UNROLL for (int e = 0; e < n * n; ++e) { PH[e] = Q[e]; PC[e] = eye[e]; }
+    bool okH = true, okC = true;
+    for (int s = 1; s <= N; ++s) {
+      const bool last = (s == N);
+      okH = gs_stage<n, m>(Ah, Bh, Q, RdH, 1.0, last, PH) && okH;
+      okC = gs_stage<n, m>(Ah, Bh, eye, RdC, -1.0, last, PC) && okC;
+      if (!okH && !okC) break;          // both probes already decided
+    }
+    if (liveH) {
+      if (okH) loH = xH; else hiH = xH;
+      const double mid = 0.5 * (loH + hiH);
+      liveH = (hiH - loH > 4.5e-16 * hiH) && (mid > loH) && (mid < hiH);
+    }
+    if (liveC) {
+      if (okC) hiC = xC; else loC = xC;
+      const double mid = 0.5 * (loC + hiC);
+      liveC = (hiC - loC > 4.5e-16 * hiC) && (mid > loC) && (mid < hiC);
+    }
+  }
+  out.min_H = 0.5 * (loH + hiH);
+  out.cmax = 0.5 * (loC + hiC);
+  out.probes = pass;
+  return out;
+}
+
+}  // namespace lq

@@ -1,5 +1,7 @@
 // k_bounds.cu — K3: batched bound coefficients (alpha, beta, xi, eta, J_bound) and batched dlqr.
-// One sample per thread, grid-stride; Gram matrix / tridiagonal scratch in the [element][thread] workspace.
+// One sample per thread. The extreme eigenvalues of the (N m) x (N m) Gram operators come from the matrix-free
+// bisection of gramspec.cuh (registers only, no scratch); only the literal-kron ordering with non-scalar weights (and
+// LQMPC_K3_DENSE=1) takes the dense Householder route with its [element][thread] workspace.
 #include "bounds.cuh"
 #include <stdlib.h>
 
@@ -55,12 +57,7 @@ __global__ void __launch_bounds__(128) bounds_kernel(const __grid_constant__ lq:
     sc.bar_u = a.bar_u; sc.bar_d_u = a.bar_d_u;
     sc.strict_reference = a.strict;
     sc.polyF = a.polyF; sc.polyP = a.polyP;
-    if (a.gtri) {   // tridiagonal form of Gamma'Gamma precomputed by the warp kernel: only the Sturm bisection is left
-      const int k = a.N * m;
-      const lq::WsView tv{const_cast<double*>(a.gtri) + s, a.S};
-      sc.has_gram = 1;
-      lq::ws_tridiag_extremes(tv, 0, k, k, &sc.cmin, &sc.cmax);
-    }
+    sc.force_dense = a.dense;
     double out[lq::BF_COUNT];
     flags |= lq::bounds_sample<n, m>(pb, Ah, Bh, K, x, sc, ws, out);
     if (a.alpha) a.alpha[s] = out[lq::BF_ALPHA];
@@ -111,21 +108,18 @@ int launch_bounds_t(lqmpc_ctx* ctx, BoundsArgs a) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int threads = 128;
   int64_t blocks = (a.S + threads - 1) / threads;
-  const int64_t cap = (int64_t)sms * 8;
-  if (blocks > cap) blocks = cap;
-  // Large N m with scalar weights: the Gram spectrum comes from the warp-per-sample shared-memory kernel (k_gram.cu)
-  // and the per-thread workspace shrinks to G_d; otherwise everything stays in the per-thread global workspace.
-  const bool gram = pb.qr_scalar && lq_gram_warp_eligible(n, m, a.N) && getenv("LQMPC_K3_NO_GRAM_KERNEL") == nullptr;
-  const int64_t per = lq::bounds_ws_doubles<n, m>(a.N, gram);
-  const size_t ws_main = (size_t)(per * blocks * threads) * sizeof(double);
-  int rc = lq_reserve_ws(ctx, ws_main + (gram ? (size_t)2 * a.N * m * a.S * sizeof(double) : 0));
-  if (rc) return rc;
-  a.ws = reinterpret_cast<double*>(ctx->ws);
-  if (gram) {
-    double* g = a.ws + per * blocks * threads;
-    rc = lq_launch_gram(ctx, a.S, a.dA, a.dB, a.N, g);
+  a.dense = getenv("LQMPC_K3_DENSE") != nullptr ? 1 : 0;
+  a.ws = nullptr;
+  if (!lq::bounds_matrix_free(pb.qr_scalar, a.strict, a.dense)) {
+    // dense route: (N m)^2 doubles of scratch per thread — cap the grid and stride over the batch
+    const int64_t cap = (int64_t)sms * 8;
+    if (blocks > cap) blocks = cap;
+    const int64_t per = lq::bounds_ws_doubles<n, m>(a.N);
+    int rc = lq_reserve_ws(ctx, (size_t)(per * blocks * threads) * sizeof(double));
     if (rc) return rc;
-    a.gtri = g;
+    a.ws = reinterpret_cast<double*>(ctx->ws);
+  } else if (blocks > 0x7fffffffLL) {
+    return lq_set_error(ctx, LQMPC_EINVAL, "batch too large for one launch");
   }
   bounds_kernel<n, m><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a);
   ctx->launches++;

@@ -159,7 +159,8 @@ int bounds_t(const double* A, const double* B, const double* Q, const double* R,
     lq::BoundsScalars sc;
     sc.N = N; sc.e_A = eA[s]; sc.e_B = eB[s]; sc.M_V = MV[s];
     sc.p[0] = p3[0]; sc.p[1] = p3[1]; sc.p[2] = p3[2];
-    sc.V_expert = V_expert; sc.bar_u = -1.0; sc.bar_d_u = -1.0; sc.strict_reference = strict;
+    sc.V_expert = V_expert; sc.bar_u = -1.0; sc.bar_d_u = -1.0; sc.strict_reference = strict & 1;
+    sc.force_dense = (strict >> 1) & 1;            // bit 1 of `strict`: dense Householder route (A/B tests)
     double out[lq::BF_COUNT];
     fl |= lq::bounds_sample<n, m>(pb, Ah, Bh, K, xx, sc, ws, out);
     for (int f = 0; f < lq::BF_COUNT; ++f) detail[(int64_t)f * S + s] = out[f];

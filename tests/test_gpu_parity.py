@@ -708,11 +708,13 @@ def test_bounds_long_horizon(engine, example):
                 assert abs(g[f][s] - bnd[f]) <= TOL * abs(bnd[f]), (N, e, f)
 
 
-def test_k3_gram_warp_kernel_matches_thread_path(engine, monkeypatch):
-    """Large N m: the extreme eigenvalues of Gamma'Gamma come from the warp-per-sample shared-memory kernel
-    (k_gram.cu); it must agree with the thread-per-sample workspace path and with numpy on Gamma itself."""
+def test_k3_matrix_free_spectrum_matches_dense_path_and_svd(engine, monkeypatch):
+    """||Gamma||_2 and lambda_min(H^) come from the matrix-free bisection of csrc/gramspec.cuh (N-stage elimination,
+    no Gram matrix). It must agree with the dense route (Gram matrix + Householder + Sturm, LQMPC_K3_DENSE=1), with
+    numpy's SVD of the assembled Gamma, and — general NON-scalar weights, time-major convention — with numpy's
+    eigenvalues of the assembled H^ (utils.py:316-322)."""
     from oracle import np_batched as nb, np_oracle as o
-    for n, m, N in [(4, 2, 10), (4, 2, 16), (2, 1, 50), (3, 3, 11), (2, 2, 33)]:
+    for n, m, N in [(4, 2, 10), (4, 2, 16), (2, 1, 50), (3, 3, 11), (2, 2, 33), (1, 1, 1), (2, 1, 1), (6, 2, 8)]:
         A, B, Q, R = nb.synth_problem(n, m, seed=5)
         Q, R = 1.5 * Q, 0.7 * R
         engine.set_problem(A, B, Q, R, Q, -0.3 * np.ones(m), 0.3 * np.ones(m), 10)
@@ -720,17 +722,30 @@ def test_k3_gram_warp_kernel_matches_thread_path(engine, monkeypatch):
         sA, sB, sx = _soa(dA, dB, x0)
         args = (sA, sB, N, 0.01, 0.01, 1.0, sx, (0.1, 1, 0.6), 1.0)
         new = engine.bounds_batch(*args)
-        monkeypatch.setenv("LQMPC_K3_NO_GRAM_KERNEL", "1")
+        monkeypatch.setenv("LQMPC_K3_DENSE", "1")
         old = engine.bounds_batch(*args)
-        monkeypatch.delenv("LQMPC_K3_NO_GRAM_KERNEL")
+        monkeypatch.delenv("LQMPC_K3_DENSE")
         for k in ("norm_Gamma", "min_H", "alpha", "beta", "theta_u", "E_u"):
             assert relerr(new[k].cpu().numpy(), old[k].cpu().numpy()) < 1e-11, (n, m, N, k)
         assert np.array_equal(new["flags"].cpu().numpy(), old["flags"].cpu().numpy())
         for s in (0, 33, 66):
             G = o.sl_syn_Gamma(N, A + dA[s], B + dB[s])
             sv = np.linalg.svd(G, compute_uv=False)
-            assert abs(float(new["norm_Gamma"][s]) - sv[0]) < 1e-11 * sv[0]
-            assert abs(float(new["min_H"][s]) - (R[0, 0] + Q[0, 0] * sv[-1] ** 2)) < 1e-10 * R[0, 0]
+            assert abs(float(new["norm_Gamma"][s]) - sv[0]) < 1e-12 * sv[0]
+            assert abs(float(new["min_H"][s]) - (R[0, 0] + Q[0, 0] * sv[-1] ** 2)) < 1e-11 * R[0, 0]
+    rng = np.random.default_rng(8)
+    for n, m, N in [(2, 1, 40), (3, 2, 12), (4, 2, 9), (4, 4, 5)]:
+        A, B, _, _ = nb.synth_problem(n, m, seed=6)
+        Mq, Mr = rng.normal(size=(n, n)), rng.normal(size=(m, m))
+        Q, R = Mq @ Mq.T + 0.5 * np.eye(n), Mr @ Mr.T + 0.5 * np.eye(m)
+        engine.set_problem(A, B, Q, R, Q, -0.3 * np.ones(m), 0.3 * np.ones(m), 10)
+        dA, dB, x0 = nb.synth_samples(n, m, 9, seed=3, e=0.02)
+        got = engine.bounds_batch(*_soa(dA, dB, x0)[:2], N, 0.01, 0.01, 1.0, _soa(dA, dB, x0)[2], (0.1, 1, 0.6), 1.0,
+                                  strict_reference=False)
+        for s in range(9):
+            H = o.hat_H(N, A + dA[s], B + dB[s], Q, R, strict_reference=False)
+            ev = np.linalg.eigvalsh(0.5 * (H + H.T))
+            assert abs(float(got["min_H"][s]) - ev[0]) < 1e-11 * max(ev[0], 1e-3 * ev[-1]), (n, m, N, s)
 
 
 # ------------------------------------------------------------------------------------------------------- K5
