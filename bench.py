@@ -1,15 +1,24 @@
 #!/usr/bin/env python
-"""bench.py — headline benchmark of the lq_mpc hot path on B200 (see DESIGN.md "Measurement").
+"""bench.py — benchmark of the lq_mpc hot path on B200 (see DESIGN.md "Measurement").
 
 Metric (BASELINE.json): MPC performance evals/sec, 1 eval = one (sample, horizon) pair = Riccati gain of that
 horizon on the estimated model + closed loop on the true plant + J_inf (Lyapunov doubling) + spectral-radius
-stability check + performance ratio.  Workload: cfg-synth-4-2-10 (n=4, m=2, N=10, Q=I, R=I, unconstrained),
-1.25e7 seeded samples (dA, dB, x0) PER GPU (= BASELINE's 1e8 samples at 8 GPUs; weak scaling), followed by the
-per-column worst-case statistics (K5, one pass) and — at N>1 — the engine's only collective, one tiny NCCL
-all-gather of the per-column moments.
+stability check + performance ratio.
+
+Headline workload: cfg-synth-4-2-10 (BASELINE configs[3]: n=4, m=2, N=10, Q=I, R=I, unconstrained), 1.25e7 seeded
+samples (dA, dB, x0) PER GPU (= BASELINE's 1e8 samples at 8 GPUs; weak scaling), then the per-column worst-case
+statistics (K5, one pass) and — at N>1 — the engine's only collective, one NCCL all-gather of the column moments.
+The same JSON line carries, under "workloads", the other two BASELINE configurations measured in the same run:
+  cfg-synth-32-8-30  (configs[4]: n=32, m=8, N=30, K4 tiled kernel, 125 000 samples per GPU)
+  cfg-sweep-f        (configs[2]: the 2-state example, error-level x horizon grid N=1..50, 1e5 perturbations per level
+                      per GPU, input box active: K2a ring solves + K2b closed loops + K3 bounds + K5)
+each with its own value, ms, roofline, clocks and (N=1) CPU baseline, and under "strong_scaling" configs[3] as written
+(1e8 samples in TOTAL at every N).
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (torchrun launches it for N > 1)
   python bench.py --impl reference ...                         the CPU arm: the numpy oracle port on all host cores
+  python bench.py --workload cfg-synth-32-8-30|cfg-sweep-f     one of the other configurations as the headline line
+  python bench.py --scaling strong                             configs[3] with 1e8 samples in total as the headline line
 
 One JSON line on stdout (rank 0).
 """
@@ -26,24 +35,19 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_DIM, M_DIM, HORIZON = 4, 2, 10
-S_PER_GPU = 12_500_000
 SEED_PROBLEM, SEED_SAMPLES = 0, 1
-# BASELINE.json configs[3] is the headline (the >= 1e7 evals/s target is quoted on it); configs[4] is selectable:
+STRONG_TOTAL = 100_000_000          # BASELINE configs[3]: "10^8 sampled (dA, dB, x0) sharded across 1/2/4/8 GPUs"
 WORKLOADS = {
     "cfg-synth-4-2-10": dict(n=4, m=2, N=10, S=12_500_000, e=0.01, tiled=False, kernel="eval_kernel<4,2>"),
     "cfg-synth-32-8-30": dict(n=32, m=8, N=30, S=125_000, e=1e-3, tiled=True,
                               kernel="tiled_eval_kernel<32,8> (+ tiled_rho_kernel<32> for entries it hands over)"),
+    "cfg-sweep-f": dict(n=2, m=1, per_level=100_000, n_err=10, nmax=50, norm="f", T=30, sweep=True,
+                        kernel="bounds_kernel<2,1> (K3) + simulate_kernel<2,1> (K2b) + mpc_solve_kernel<2,1> (K2a)"),
 }
-
-
-def set_workload(name):
-    global N_DIM, M_DIM, HORIZON, S_PER_GPU, WL
-    WL = dict(WORKLOADS[name], name=name)
-    N_DIM, M_DIM, HORIZON, S_PER_GPU = WL["n"], WL["m"], WL["N"], WL["S"]
-
-
-WL = dict(WORKLOADS["cfg-synth-4-2-10"], name="cfg-synth-4-2-10")
+# ncu `sm__pipe_fp64_cycles_active` of the dominant kernel from the committed captures (profiles/README.md): what the
+# pipe actually did, next to the algorithmic fraction
+PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r01v4_k1_eval_4x2_metrics.csv", 0.636),
+                   "cfg-synth-32-8-30": ("profiles/r01k4e_k4a_tiled_eval_32x8_metrics.csv", 0.690)}
 
 
 def flops_per_eval(n, m, N, lyap_iters=8):
@@ -56,6 +60,14 @@ def flops_per_eval(n, m, N, lyap_iters=8):
 def bytes_per_eval(n, m):
     """compulsory HBM traffic of one eval: read dA, dB, x0; write J, rho, ratio, flags."""
     return (n * n + n * m + n) * 8 + 4 * 8
+
+
+def k3_flops_per_eval(n, m, N, probes=52):
+    """K3's matrix-free spectrum (csrc/gramspec.cuh): two bisection searches x `probes` probes x N elimination stages of
+    4n^3 + 4n^2 m + 3 n m^2 + m^3/3 dense flops (P B, B'Y, Cholesky, triangular solve, Y Y', two n^3 products), plus the
+    DARE (SDA, ~10 doublings of ~14 n^3) — the algorithmic count DESIGN.md states for the sweep's dominant kernel."""
+    stage = 4 * n ** 3 + 4 * n * n * m + 3 * n * m * m + m ** 3 / 3.0
+    return 2 * probes * N * stage + 10 * 14 * n ** 3
 
 
 # ---------------------------------------------------------------------------------------------------- clocks
@@ -80,19 +92,16 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append([c.strip() for c in line.split(",")])
 
-    def stop(self):
-        if self.proc:
-            self.proc.terminate()
-            try:
-                self.proc.wait(timeout=2)
-            except subprocess.TimeoutExpired:
-                self.proc.kill()
-        sm, mx, reasons = [], 0.0, set()
+    def take(self):
+        """Summary of the samples collected since the last take(); clears them (one summary per timed workload)."""
+        rows, self.rows = self.rows, []
+        sm, mx, reasons, pw = [], 0.0, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
+        for r in rows:
             try:
                 sm.append(float(r[0]))
                 mx = max(mx, float(r[1]))
+                pw.append(float(r[2]))
                 for nme, v in zip(names, r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(nme)
@@ -100,16 +109,29 @@ class ClockSampler:
                 pass
         sm.sort()
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "power_w_max": max(pw) if pw else None}
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+            self.proc = None
 
 
-# ---------------------------------------------------------------------------------------------------- CPU arm
-def _cpu_worker(args):
-    os.environ["OMP_NUM_THREADS"] = "1"
+# ---------------------------------------------------------------------------------------------------- CPU arms
+def _all_cores():
     try:                                    # the GPU arm may have bound its process to one NUMA node: the CPU arm
         os.sched_setaffinity(0, range(os.cpu_count() or 1))            # gets every core of the box
     except OSError:
         pass
+
+
+def _cpu_worker(args):
+    os.environ["OMP_NUM_THREADS"] = "1"
+    _all_cores()
     first, count, (n, m, N, e) = args
     import numpy as np  # noqa
     from oracle import np_batched as nb
@@ -121,17 +143,17 @@ def _cpu_worker(args):
     return time.perf_counter() - t, float(out["ratio"].max())
 
 
-def cpu_port_throughput(per_worker, workers=None):
+def cpu_port_throughput(wl, per_worker, workers=None):
     """The oracle port (oracle/np_batched.py) on `workers` host processes, `per_worker` samples each.
     Returns (evals/s over the wall clock of the pool, workers, samples)."""
     import multiprocessing as mp
     workers = workers or max(1, min(os.cpu_count() or 1, 64))
     ctx = mp.get_context("spawn")
-    cfg = (N_DIM, M_DIM, HORIZON, WL["e"])
-    if WL["tiled"]:
+    cfg = (wl["n"], wl["m"], wl["N"], wl["e"])
+    if wl["tiled"]:
         per_worker = max(64, per_worker // 40)                          # ~800x the flops per eval of the n=4 case
     with ctx.Pool(workers) as pool:
-        pool.map(_cpu_worker, [(0, 32 if WL["tiled"] else 256, cfg)] * workers)   # spawn + import warm-up
+        pool.map(_cpu_worker, [(0, 32 if wl["tiled"] else 256, cfg)] * workers)   # spawn + import warm-up
         t = time.perf_counter()
         pool.map(_cpu_worker, [(w * per_worker, per_worker, cfg) for w in range(workers)])
         wall = time.perf_counter() - t
@@ -139,269 +161,526 @@ def cpu_port_throughput(per_worker, workers=None):
     return total / wall, workers, total
 
 
-def run_reference(args):
+def _sweep_cpu_worker(args):
+    """The reference's PER-SAMPLE path (utils_class.py:806-859: 8 ring QPs + 30 closed-loop QPs + dlqr + energy_decreasing
+    + energy_bound per eval) restated in oracle/np_oracle.eval_one, on seeded perturbations of the 2-state example."""
+    os.environ["OMP_NUM_THREADS"] = "1"
+    _all_cores()
+    seed, count = args
+    import numpy as np
+    from oracle import np_oracle as o
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q, R = 2 * np.eye(2), np.eye(1)
+    lo, hi = np.array([-0.1]), np.array([0.1])
+    K, _ = o.dlqr(A, B, Q, R)
+    x0_vec = o.circle_generator(8, 1.5, o.local_radius(lo, hi, -K, Q), Q)
+    x_start = x0_vec[:, 1]
+    V_expert = o.mpc_solve(30, A, B, Q, R, Q, lo, hi, x_start)[1]
+    rng = np.random.default_rng(seed)
+    t = time.perf_counter()
+    done = 0
+    for c in range(count):
+        e = float(rng.choice(np.linspace(1e-3, 1e-2, 10)))
+        N = int(rng.integers(1, 51))
+        dA = rng.uniform(-e, e, size=(2, 2)) / 2.0
+        dB = rng.uniform(-e, e, size=(2, 1)) / 2.0
+        try:
+            o.eval_one(A + dA, B + dB, A, B, Q, R, lo, hi, N, 30, e, x0_vec, x_start, V_expert, (0.1, 1, 0.6))
+        except ValueError:                  # math domain error: the reference raises too (utils.py:506-507)
+            pass
+        done += 1
+    return time.perf_counter() - t, done
+
+
+def cpu_sweep_throughput(per_worker, workers=None):
+    import multiprocessing as mp
+    workers = workers or max(1, min(os.cpu_count() or 1, 64))
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(workers) as pool:
+        pool.map(_sweep_cpu_worker, [(0, 2)] * workers)
+        t = time.perf_counter()
+        pool.map(_sweep_cpu_worker, [(w + 1, per_worker) for w in range(workers)])
+        wall = time.perf_counter() - t
+    total = workers * per_worker
+    return total / wall, workers, total
+
+
+def workload_config(wl, n_gpus, scaling="weak"):
+    """`config` of the JSON line — identical in both arms (the CPU arm's remarks live outside it)."""
+    if wl.get("sweep"):
+        evals = wl["per_level"] * wl["n_err"] * wl["nmax"]
+        return {"workload": "cfg-sweep-%s: the reference's 2-state example (A=[[1,.7],[.12,.4]], B=[1,1.2]', Q=2I, R=1, "
+                            "|u|<=0.1), %d seeded perturbations per error level per GPU x %d levels x horizons 1..%d = "
+                            "%.3g evals per GPU; per eval 8 ring QPs (M_V) + a %d-step closed loop with the exact QP + "
+                            "DARE + alpha/beta/xi/eta/bound; then per-column statistics"
+                            % (wl["norm"], wl["per_level"], wl["n_err"], wl["nmax"], evals, wl["T"]),
+                "n": 2, "m": 1, "N": "1..%d" % wl["nmax"], "samples_per_gpu": wl["per_level"] * wl["n_err"],
+                "evals_per_sample": wl["nmax"], "l2": "L2 flushed by the kernels' own 200 MB+ of tables per horizon",
+                "parallelism": "perturbation-sharded x%d, one all-gather of per-column moments per horizon" % n_gpus}
+    n, m, N, S = wl["n"], wl["m"], wl["N"], wl["S"]
+    in_gb = S * (n * n + n * m + n) * 8 / 1e9
+    return {"workload": "%s: n=%d m=%d N=%d Q=I R=I unconstrained, %.3g seeded (dA,dB,x0) samples per GPU "
+                        "(%.3g total, %s scaling), J_inf + rho + ratio + flags per sample, then per-column worst-case stats"
+                        % (wl["name"], n, m, N, S, S * n_gpus, scaling),
+            "n": n, "m": m, "N": N, "samples_per_gpu": S, "evals_per_sample": 1,
+            "l2": "inputs (%.2f GB per step) exceed the 126 MB L2; no flush needed" % in_gb,
+            "parallelism": "sample-sharded x%d, one final all-gather of per-column moments (6 doubles/column)" % n_gpus}
+
+
+def run_reference(args, wl):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    per_worker = 20_000
     vals = []
-    for _ in range(args.warmup):
-        cpu_port_throughput(2_000)
     workers = total = 0
+    if wl.get("sweep"):
+        run = lambda k: cpu_sweep_throughput(k)                       # noqa: E731
+        per, per_warm = 60, 4
+        kind = ("oracle/np_oracle.eval_one: the reference's per-sample path (38 exact QPs + DARE + bound formulas per "
+                "eval), one process per host core")
+    else:
+        run = lambda k: cpu_port_throughput(wl, k)                    # noqa: E731
+        per, per_warm = 20_000, 2_000
+        kind = "oracle/np_batched.py (batched numpy/LAPACK), one process per host core"
+    for _ in range(args.warmup):
+        run(per_warm)
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        v, workers, total = cpu_port_throughput(per_worker)
+        v, workers, total = run(per)
         vals.append(v)
     wall = time.perf_counter() - t0
     value = sum(vals) / len(vals)
     line = {"impl": "reference", "metric": "mpc_evals_per_sec", "value": value, "unit": "evals/s",
             "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": 1e3 * wall / max(1, args.steps), "higher_is_better": True, "scaling": args.scaling,
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(args.gpus, note="CPU arm: bounded sample per step"),
+            "config": workload_config(wl, args.gpus, args.scaling),
+            "note": "CPU arm: each step evaluates a bounded sample of the configured workload (throughput metric)",
             "cpu_baseline": {"value": value, "unit": "evals/s", "cores": workers, "kind": "port",
-                             "sample": "%d samples per step (%d per process) of the same seeded workload; oracle/"
-                                       "np_batched.py (batched numpy/LAPACK), one process per host core" %
-                                       (total, total // max(1, workers))},
+                             "sample": "%d evals per step (%d per process) of the same seeded workload; %s"
+                                       % (total, total // max(1, workers), kind)},
             "e2e": {"value": value, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line))
     return 0
 
 
-def workload_config(n_gpus, note=None):
-    in_gb = S_PER_GPU * (N_DIM * N_DIM + N_DIM * M_DIM + N_DIM) * 8 / 1e9
-    cfg = {"workload": "%s: n=%d m=%d N=%d Q=I R=I unconstrained, %.3g seeded (dA,dB,x0) samples per GPU "
-                       "(%.3g total), J_inf + rho + ratio + flags per sample, then per-column worst-case stats"
-                       % (WL["name"], N_DIM, M_DIM, HORIZON, S_PER_GPU, S_PER_GPU * n_gpus),
-           "n": N_DIM, "m": M_DIM, "N": HORIZON, "samples_per_gpu": S_PER_GPU, "evals_per_sample": 1,
-           "l2": "inputs (%.2f GB per step) exceed the 126 MB L2; no flush needed" % in_gb,
-           "parallelism": "sample-sharded x%d, one final all-gather of per-column moments (6 doubles/column)" % n_gpus}
-    if note:
-        cfg["note"] = note
-    return cfg
-
-
 # ---------------------------------------------------------------------------------------------------- our arm
-def run_ours(args):
-    import numpy as np
-    import torch
-    import torch.distributed as dist
-    from lq_mpc_b200 import sampling as sp
-    from lq_mpc_b200.engine import Engine
-    from lq_mpc_b200.stats import column_moments_device, merge_moments
+class Ctx:
+    """Process-level plumbing shared by the measured workloads."""
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", local))
-    torch.cuda.set_device(local)
-    from lq_mpc_b200.runtime import bind_to_gpu_numa
-    numa_cpus = bind_to_gpu_numa(local)          # pinned host shards below are then first-touched on the GPU's node
-    eng = Engine(local)
-    A, B, Q, R = sp.synth_problem(N_DIM, M_DIM, seed=SEED_PROBLEM)
-    tiled = WL["tiled"]
+    def __init__(self):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if self.world > 1:
+            os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+            dist.init_process_group("nccl", rank=self.rank, world_size=self.world,
+                                    device_id=torch.device("cuda", self.local))
+        torch.cuda.set_device(self.local)
+        from lq_mpc_b200.runtime import bind_to_gpu_numa
+        self.numa_cpus = bind_to_gpu_numa(self.local)   # pinned host shards are then first-touched on the GPU's node
+        from lq_mpc_b200.engine import Engine
+        self.eng = Engine(self.local)
+        self.sampler = ClockSampler(self.local)
+        self.peaks = {}
+        try:
+            self.peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except OSError:
+            pass
+        self.peak_fp64 = self.peak_dmma = None
+
+    def barrier(self):
+        if self.world > 1:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def fp64_peaks(self):
+        """FP64 roofline denominators measured in this run (MEASURED_PEAKS.json has no FP64 figure)."""
+        if self.peak_fp64 is None:
+            self.peak_fp64 = self.eng.fp64_peak()
+            self.peak_dmma = self.eng.fp64_tensor_peak()
+        return self.peak_fp64, self.peak_dmma
+
+    def timed(self, fn, steps):
+        """`steps` calls of fn between a barrier + synchronize on both sides, CUDA events on the engine's stream;
+        returns ms per call, max over ranks."""
+        torch = self.torch
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        self.barrier()
+        e0.record()
+        out = None
+        for _ in range(steps):
+            out = fn()
+        e1.record()
+        self.barrier()
+        return self.max_over_ranks(e0.elapsed_time(e1) / steps), out
+
+
+def roofline_record(cx, wl, S, ms_kernel, tiled):
+    n, m, N = wl["n"], wl["m"], wl["N"]
+    fl, by = flops_per_eval(n, m, N), bytes_per_eval(n, m)
+    ach_tf = S * fl / (ms_kernel * 1e-3) / 1e12
+    ach_gb = S * by / (ms_kernel * 1e-3) / 1e9
+    peak_fp64, peak_dmma = cx.fp64_peaks()
+    hbm_peak = float(cx.peaks.get("hbm_gbs", 6650.0))
+    traffic = None
+    try:
+        tf_name = "k4_traffic.json" if tiled else "k1_traffic.json"
+        traffic = json.load(open(os.path.join(ROOT, "profiles", tf_name))).get("dram_bytes_per_launch")
+    except (OSError, ValueError):
+        pass
+    src, pipe = PIPE_ACTIVE_NCU.get(wl["name"], (None, None))
+    peak = max(peak_dmma, peak_fp64)
+    return {
+        # Both synthetic workloads are bound by the SM's FP64 pipe. On B200 the FP64 tensor-core MMA
+        # (mma.sync.m8n8k4.f64) executes on that same pipe (scripts/probes/fp64_pipe_probe.cu: one MMA holds it for 16
+        # cycles = 256 FMAs at the DFMA rate), so the pipe's peak is the MMA-stream figure (= 148 SMs x 64 FMA/clk); a
+        # DFMA-only stream tops out ~9 % lower. `peak` is the higher, harder one for both kernels.
+        "bound": "fp64", "bound_detail": "FP64 pipe of the SM: " + (
+            "mma.sync.m8n8k4.f64 (DMMA) products" if tiled else
+            "scalar DFMA code, no MMA issued (the FP64 tensor-core MMA runs on this same pipe; there is no tcgen05 "
+            "kind for f64)"),
+        "achieved": ach_tf, "peak": peak, "unit": "TFLOP/s", "frac": ach_tf / peak if peak else None,
+        "pipe_active_ncu": pipe, "pipe_active_ncu_source": src,
+        "traffic": traffic, "fp64_vector_peak": peak_fp64,
+        "frac_of_dfma_stream_peak": (ach_tf / peak_fp64) if peak_fp64 else None,
+        "kernel": wl["kernel"], "kernel_ms": ms_kernel,
+        "algorithmic_flops_per_eval": fl, "algorithmic_bytes_per_eval": by,
+        "peak_source": "measured in this run: mma.sync.m8n8k4.f64 stream (lqmpc_fp64_tensor_peak) and DFMA-chain "
+                       "stream (lqmpc_fp64_peak) micro-benchmarks; MEASURED_PEAKS.json has no FP64 figure",
+        "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
+                "peak_source": "MEASURED_PEAKS.json hbm_gbs" if cx.peaks else "fallback 6650"}}
+
+
+def link_ceiling(cx, h_in, d_in, d_out_bytes, steps=3):
+    """The box's host<->device copy ceiling for THIS step's traffic with every rank copying at once: plain pinned
+    cudaMemcpyAsync of the same input buffers H2D and of an output-sized buffer D2H on two streams (full duplex), no
+    kernels. `e2e` is reported as a fraction of it: what is left is pipeline overhead, not the host or the link."""
+    torch = cx.torch
+    dev_out = torch.empty(d_out_bytes // 8, dtype=torch.float64, device="cuda")
+    host_out = torch.empty(d_out_bytes // 8, dtype=torch.float64).pin_memory()
+    s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
+
+    def one():
+        with torch.cuda.stream(s_in):
+            for h, d in zip(h_in, d_in):
+                d.copy_(h, non_blocking=True)
+        with torch.cuda.stream(s_out):
+            host_out.copy_(dev_out, non_blocking=True)
+    one()
+    cx.barrier()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        one()
+    torch.cuda.synchronize()
+    dt = cx.max_over_ranks((time.perf_counter() - t0) / steps)
+    h2d = sum(h.numel() * 8 for h in h_in)
+    return {"step_s": dt, "h2d_gbs_per_gpu": h2d / dt / 1e9, "d2h_gbs_per_gpu": d_out_bytes / dt / 1e9,
+            "aggregate_gbs": (h2d + d_out_bytes) * cx.world / dt / 1e9,
+            "what": "pinned cudaMemcpyAsync of the step's inputs (H2D) and outputs (D2H), both directions at once, "
+                    "all %d ranks concurrently, no kernels" % cx.world}
+
+
+def measure_synth(cx, wl, steps, warmup, scaling="weak", full=True):
+    """One synthetic workload (K1 or K4): device-resident value, kernel-alone roofline, end-to-end through the host-buffer
+    entry point. `full=False` (sub-records) skips the nested-horizon and link-ceiling legs."""
+    import numpy as np
+    torch, dist, eng = cx.torch, cx.dist, cx.eng
+    from lq_mpc_b200 import sampling as sp
+    from lq_mpc_b200.stats import column_moments_device, merge_moments
+    world, rank = cx.world, cx.rank
+    n, m, N, S, tiled = wl["n"], wl["m"], wl["N"], wl["S"], wl["tiled"]
+    A, B, Q, R = sp.synth_problem(n, m, seed=SEED_PROBLEM)
     if tiled:
         eng.set_problem_tiled(A, B, Q, R, Q, 30)
     else:
         eng.set_problem(A, B, Q, R, Q, None, None, 30)
-    S = S_PER_GPU
-    n, m = N_DIM, M_DIM
-
     # ---- this rank's shard of the seeded workload, generated on the host into pinned buffers
     # (K1: struct-of-arrays [element][sample]; K4: array-of-matrices [sample][element], one sample contiguous for TMA)
     shp = (lambda k: (S, k)) if tiled else (lambda k: (k, S))
     hA = torch.empty(shp(n * n), dtype=torch.float64).pin_memory()
     hB = torch.empty(shp(n * m), dtype=torch.float64).pin_memory()
     hx = torch.empty(shp(n), dtype=torch.float64).pin_memory()
-    sp.synth_samples_soa(n, m, S, seed=SEED_SAMPLES, first=rank * S, e=WL["e"], aos=tiled,
+    sp.synth_samples_soa(n, m, S, seed=SEED_SAMPLES, first=rank * S, e=wl["e"], aos=tiled,
                          out=(hA.numpy(), hB.numpy(), hx.numpy()))
     dA, dB, x0 = hA.cuda(non_blocking=True), hB.cuda(non_blocking=True), hx.cuda(non_blocking=True)
     torch.cuda.synchronize()
-    evaluate = (lambda a, b, c: eng.eval_batch_tiled(a, b, c, HORIZON, HORIZON)) if tiled else \
-        (lambda a, b, c: eng.eval_batch(a, b, c, HORIZON, HORIZON))
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
+    evaluate = (lambda: eng.eval_batch_tiled(dA, dB, x0, N, N)) if tiled else (lambda: eng.eval_batch(dA, dB, x0, N, N))
 
     def step():
-        r = evaluate(dA, dB, x0)                              # K1/K4 write J, rho, ratio into one [3][S] table
+        r = evaluate()                                        # K1/K4 write J, rho, ratio into one [3][S] table
         # K5 (one pass) + the only collective (all-gather), all enqueued on the device: the [world][3][6] moments
         # stay in HBM; they are merged on the host after the timed region (the e2e leg reads results back per step)
         return r, column_moments_device(eng, r["table"])
 
-    def max_over_ranks(v):
-        if world == 1:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
-    # ---- (1) device-resident throughput: W warm-up steps, K timed steps, CUDA events, max over ranks
-    # the clock sampler (one `nvidia-smi -lms` process) starts BEFORE the warm-up and gets time to initialise (its NVML
-    # start-up takes driver locks for a few hundred ms: not at the edge of the timed region)
-    sampler = ClockSampler(local)
-    if rank == 0:
-        sampler.start()
-        time.sleep(1.0)
-    # W warm-up steps, then as many more as keep the GPU under this load for ~0.5 s (the kernel draws the board's power
-    # cap: the timed region should not start on a cold power state). The count is agreed across ranks — every step
-    # carries the all-gather, so ranks must not leave the warm-up at different steps.
-    n_warm = max(3, args.warmup)
-    for _ in range(n_warm):
-        r, st = step()      # bound exactly as in the timed loop: two result sets alternate, so the second 350 MB block
-    barrier()               # is allocated HERE (a cudaMalloc of it inside the timed region cost 6-150 ms at step 2)
-    t_w = time.perf_counter()
-    r, st = step()
-    torch.cuda.synchronize()
-    extra = int(max_over_ranks(float(min(400, int(0.5 / max(time.perf_counter() - t_w, 1e-4))))))
-    for _ in range(extra):
+    cx.sampler.take()
+    # ---- (1) the dominant kernel alone, for the roofline. Runs FIRST: it also brings the board to its loaded power
+    #      state (K1 draws the power cap), so the headline region below starts warm after exactly W warm-up steps.
+    for _ in range(3):
+        evaluate()
+    ms_kernel, _ = cx.timed(evaluate, steps)
+    # ---- (2) device-resident throughput: exactly W warm-up steps (bound like the timed loop: two result sets
+    #      alternate, so the second table is allocated here, not inside the timed region), then K timed steps
+    W = max(3, warmup)
+    for _ in range(W):
         r, st = step()
-    n_warm += 1 + extra
-    barrier()
-    if rank == 0:
-        sampler.rows.clear()                      # samples from here on: the three timed regions
     launches0 = eng.launch_count
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    trace = os.environ.get("LQMPC_BENCH_TRACE") == "1"
-    tev, thost = [], []
-    e0.record()
-    for _ in range(args.steps):
-        r, st = step()
-        if trace:                                  # development: where does a slow region lose its time?
-            ev = torch.cuda.Event(enable_timing=True)
-            ev.record()
-            tev.append(ev)
-            thost.append(time.perf_counter())
-    e1.record()
-    barrier()
-    ms_step = max_over_ranks(e0.elapsed_time(e1) / args.steps)
-    if trace and rank == 0:
-        d = [e0.elapsed_time(tev[0])] + [tev[i].elapsed_time(tev[i + 1]) for i in range(len(tev) - 1)]
-        med = sorted(d)[len(d) // 2]
-        sys.stderr.write("trace: median %.3f ms, slow steps %s, host enqueue span %.1f ms\n" % (
-            med, [(i, round(x, 1)) for i, x in enumerate(d) if x > 1.3 * med], (thost[-1] - thost[0]) * 1e3))
-    st = merge_moments(st.cpu().numpy())
+    ms_step, (r, st) = cx.timed(step, steps)
     launches = eng.launch_count - launches0
-    # ---- (2) the dominant kernel alone (K1), same data, for the roofline
-    barrier()
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    k0.record()
-    for _ in range(args.steps):
-        evaluate(dA, dB, x0)
-    k1.record()
-    barrier()
-    ms_kernel = k0.elapsed_time(k1) / args.steps
-    # ---- (2b) supplementary: every horizon 1..N emitted from ONE nested Riccati recursion per sample (the metric's
-    #      "samples x horizons" reading; not the headline, which counts one eval per sample at the quoted horizon)
+    stats = merge_moments(st.cpu().numpy())
+    # ---- (2b) supplementary: every horizon 1..N from ONE nested Riccati recursion per sample (K1 only)
     ms_nested = None
-    if not tiled:
-        nsteps = max(2, args.steps // 4)
+    if full and not tiled:
         for _ in range(2):
-            eng.eval_batch(dA, dB, x0, 1, HORIZON)
-        barrier()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record()
-        for _ in range(nsteps):
-            eng.eval_batch(dA, dB, x0, 1, HORIZON)
-        n1.record()
-        barrier()
-        ms_nested = max_over_ranks(n0.elapsed_time(n1) / nsteps)
-    # ---- (3) end to end through the host-buffer entry point: pinned host -> H2D -> K1 -> D2H, every step
+            eng.eval_batch(dA, dB, x0, 1, N)
+        ms_nested, _ = cx.timed(lambda: eng.eval_batch(dA, dB, x0, 1, N), max(2, steps // 4))
+    # ---- (3) end to end through the host-buffer entry point: pinned host -> H2D -> kernel -> D2H, every step
     outb = None
-    if tiled:       # K4: chunked H2D -> K4a + K4b -> D2H pipeline from the pinned shard (lqmpc_eval_batch_tiled_host)
+    if tiled:       # K4: chunked H2D -> K4a + K4b -> D2H pipeline (lqmpc_eval_batch_tiled_host)
         def host_step(prev):
-            return eng.eval_batch_tiled_host(hA, hB, hx, HORIZON, HORIZON, out=prev, chunk=16384)
+            return eng.eval_batch_tiled_host(hA, hB, hx, N, N, out=prev, chunk=16384)
     else:
         def host_step(prev):
-            return eng.eval_batch_host(hA, hB, hx, HORIZON, HORIZON, out=prev, chunk=1 << 19)
+            return eng.eval_batch_host(hA, hB, hx, N, N, out=prev, chunk=1 << 19)
     for _ in range(2):
         outb = host_step(outb)
-    barrier()
+    e2e_steps = max(3, min(steps, 20))
+    cx.barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(e2e_steps):
         outb = host_step(outb)
     torch.cuda.synchronize()
-    e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
-    clocks = sampler.stop() if rank == 0 else None        # sampled across all three timed regions (GPU busy throughout)
+    e2e_s = cx.max_over_ranks((time.perf_counter() - t0) / e2e_steps)
     same = bool(torch.equal(outb["J"][0, :4096], r["J"][0, :4096].cpu()))
-    peak_fp64 = eng.fp64_peak() if rank == 0 else 0.0
-    peak_dmma = eng.fp64_tensor_peak() if rank == 0 else 0.0
+    h2d_b, d2h_b = int(S * (n * n + n * m + n) * 8), int(S * (3 * 8 + 4))
+    ceiling = link_ceiling(cx, (hA, hB, hx), (dA, dB, x0), (d2h_b + 7) // 8 * 8) if full else None
+    clocks = cx.sampler.take()
     unstable = int((r["flags"] & 1).sum().item())
-    if world > 1:
-        dist.barrier()
+    # ---- (4) N > 1: the merged statistics of the TIMED data must equal a single-GPU reduction of the same samples
+    stats_check = None
+    if world > 1 and full:
+        tab = r["table"].contiguous()
+        gathered = [torch.empty_like(tab) for _ in range(world)] if rank == 0 else None
+        dist.gather(tab, gathered, dst=0)
+        if rank == 0:
+            whole = torch.cat(gathered, dim=1)
+            single = merge_moments(eng.column_moments_raw(whole).cpu().numpy()[None])
+            ok = all(np.array_equal(stats[k], single[k]) for k in ("max", "min", "count"))
+            ok = ok and bool(np.max(np.abs(stats["mean"] - single["mean"]) / np.abs(single["mean"])) < 1e-12)
+            ok = ok and bool(np.max(np.abs(stats["std"] - single["std"]) / np.abs(single["std"])) < 1e-9)
+            if not ok:
+                raise SystemExit("bench: %d-rank merged statistics differ from the single-GPU reduction" % world)
+            stats_check = "merged %d-rank column statistics == single-GPU reduction of the same %d samples " \
+                          "(max/min/count bit-equal, mean 1e-12, std 1e-9)" % (world, whole.shape[1])
+            del whole, gathered
+        cx.barrier()
+    if rank != 0:
+        return None
+    evals = S * world
+    rec = {
+        "metric": "mpc_evals_per_sec", "value": evals / (ms_step * 1e-3), "unit": "evals/s", "n_gpus": world,
+        "steps": steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(wl, world, scaling),
+        "roofline": roofline_record(cx, wl, S, ms_kernel, tiled),
+        "e2e": {"value": evals / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
+                "matches_device_path": same, "steps": e2e_steps,
+                "host_numa_binding": ("process pinned to the %d cores NVML reports local to its GPU"
+                                      % len(cx.numa_cpus)) if cx.numa_cpus else "none (NVML affinity unavailable)",
+                "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)" if not tiled
+                else "lqmpc_eval_batch_tiled_host (pinned host array-of-matrices in, J/rho/ratio/flags tables out)"},
+        "gpu_launches": int(launches),
+        "power_state": "the kernel-alone roofline leg (%d launches) ran immediately before the %d warm-up steps"
+                       % (steps + 3, W),
+        "clocks": clocks,
+        "worst_case": {"ratio_max": float(stats["max"][2]), "ratio_mean": float(stats["mean"][2]),
+                       "ratio_std": float(stats["std"][2]), "rho_max": float(stats["max"][1]), "unstable": unstable},
+    }
+    if ceiling:
+        rec["e2e"]["link_ceiling"] = ceiling
+        rec["e2e"]["frac_of_link_ceiling"] = ceiling["step_s"] / e2e_s
+    if ms_nested is not None:
+        rec["nested_horizons"] = {
+            "what": "horizons 1..%d of every sample from one nested Riccati recursion (K1 alone, device-resident)" % N,
+            "evals_per_s": S * world * N / (ms_nested * 1e-3), "ms": ms_nested}
+    if stats_check:
+        rec["stats_check"] = stats_check
+    del dA, dB, x0, hA, hB, hx, r, outb
+    torch.cuda.empty_cache()
+    return rec
 
-    if rank == 0:
-        evals = S * world
-        value = evals / (ms_step * 1e-3)
-        fl = flops_per_eval(n, m, HORIZON)
-        by = bytes_per_eval(n, m)
-        ach_tf = S * fl / (ms_kernel * 1e-3) / 1e12
-        ach_gb = S * by / (ms_kernel * 1e-3) / 1e9
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except OSError:
-            pass
-        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
-        traffic = None
-        try:
-            tf_name = "k4_traffic.json" if tiled else "k1_traffic.json"
-            traffic = json.load(open(os.path.join(ROOT, "profiles", tf_name))).get("dram_bytes_per_launch")
-            # (latest `ncu --set full` capture of eval_kernel<4,2> on this workload; see profiles/README.md)
-        except (OSError, ValueError):
-            pass
-        line = {
-            "metric": "mpc_evals_per_sec", "value": value, "unit": "evals/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "warmup_total_steps": n_warm, "ms_per_step": ms_step, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": workload_config(world),
-            "roofline": {
-                # Both workloads are bound by the SM's FP64 pipe. On B200 the FP64 tensor-core MMA (mma.sync.m8n8k4.f64)
-                # executes on that same pipe (scripts/probes/fp64_pipe_probe.cu: one MMA holds it for 16 cycles = 256
-                # FMAs at the DFMA rate), so the pipe's peak is the MMA-stream figure (= 148 SMs x 64 FMA/clk); a
-                # DFMA-only stream tops out ~9 % lower (issue / register bandwidth). `peak` is the higher, harder one for
-                # both kernels; the DFMA-stream figure and the fraction against it are reported beside it.
-                "bound": "tensor", "bound_detail": "FP64 pipe: " + (
-                    "tensor-core MMAs (DMMA)" if tiled else
-                    "scalar DFMA code, no MMA issued; the FP64 tensor-core peak is the peak of this same pipe"),
-                "achieved": ach_tf, "peak": max(peak_dmma, peak_fp64), "unit": "TFLOP/s",
-                "frac": (ach_tf / max(peak_dmma, peak_fp64)) if peak_fp64 else None, "traffic": traffic,
-                "fp64_vector_peak": peak_fp64, "frac_of_dfma_stream_peak": (ach_tf / peak_fp64) if peak_fp64 else None,
-                "kernel": WL["kernel"], "kernel_ms": ms_kernel,
-                "algorithmic_flops_per_eval": fl, "algorithmic_bytes_per_eval": by,
-                "peak_source": "measured in this run: mma.sync.m8n8k4.f64 stream (lqmpc_fp64_tensor_peak) and DFMA-chain "
-                               "stream (lqmpc_fp64_peak) micro-benchmarks; MEASURED_PEAKS.json has no FP64 figure",
-                "hbm": {"achieved": ach_gb, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gb / hbm_peak,
-                        "peak_source": "MEASURED_PEAKS.json hbm_gbs (of measured)" if peaks else "fallback 6650"}},
-            "e2e": {"value": evals / e2e_s, "unit": "evals/s",
-                    "h2d_bytes_per_step": int(S * (n * n + n * m + n) * 8),
-                    "d2h_bytes_per_step": int(S * (3 * 8 + 4)), "matches_device_path": same,
-                    "host_numa_binding": ("process pinned to the %d cores NVML reports local to its GPU" % len(numa_cpus))
-                    if numa_cpus else "none (NVML affinity unavailable)",
-                    "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)" if not tiled
-                    else "lqmpc_eval_batch_tiled_host (pinned host array-of-matrices in, J/rho/ratio/flags tables out)"},
-            "gpu_launches": int(launches),
-            "nested_horizons": None if ms_nested is None else {
-                "what": "horizons 1..%d of every sample from one nested Riccati recursion (K1 alone, device-resident)"
-                        % HORIZON, "evals_per_s": S * world * HORIZON / (ms_nested * 1e-3), "ms": ms_nested},
-            "clocks": clocks,
-            "worst_case": {"ratio_max": float(st["max"][2]), "ratio_mean": float(st["mean"][2]),
-                           "ratio_std": float(st["std"][2]), "rho_max": float(st["max"][1]), "unstable": unstable},
-        }
-        if world == 1 and not args.no_cpu_baseline:
-            v, workers, total = cpu_port_throughput(8_000)
-            line["cpu_baseline"] = {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
-                                    "sample": "%d samples of the same seeded workload (8000 per process); "
-                                              "oracle/np_batched.py, one process per host core" % total}
+
+def measure_strong(cx, steps):
+    """BASELINE configs[3] as written: 1e8 samples in TOTAL, sharded over the ranks (strong scaling). Inputs are drawn
+    on the device (seeded torch generator, U[-0.01, 0.01] / N(0, I)): this leg times the device-resident path only."""
+    torch, eng = cx.torch, cx.eng
+    from lq_mpc_b200 import sampling as sp
+    from lq_mpc_b200.stats import column_moments_device
+    wl = dict(WORKLOADS["cfg-synth-4-2-10"], name="cfg-synth-4-2-10")
+    n, m, N = wl["n"], wl["m"], wl["N"]
+    S = STRONG_TOTAL // cx.world
+    A, B, Q, R = sp.synth_problem(n, m, seed=SEED_PROBLEM)
+    eng.set_problem(A, B, Q, R, Q, None, None, 30)
+    g = torch.Generator(device="cuda").manual_seed(1000 + cx.rank)
+    dA = torch.empty((n * n, S), dtype=torch.float64, device="cuda").uniform_(-0.01, 0.01, generator=g)
+    dB = torch.empty((n * m, S), dtype=torch.float64, device="cuda").uniform_(-0.01, 0.01, generator=g)
+    x0 = torch.empty((n, S), dtype=torch.float64, device="cuda").normal_(generator=g)
+
+    def step():
+        r = eng.eval_batch(dA, dB, x0, N, N)
+        return r, column_moments_device(eng, r["table"])
+    for _ in range(3):
+        step()
+    ms, _ = cx.timed(step, steps)
+    del dA, dB, x0
+    torch.cuda.empty_cache()
+    if cx.rank != 0:
+        return None
+    return {"value": S * cx.world / (ms * 1e-3), "unit": "evals/s", "scaling": "strong", "ms_per_step": ms,
+            "steps": steps, "warmup": 3, "samples_total": S * cx.world, "samples_per_gpu": S, "n_gpus": cx.world,
+            "data": "synthetic, drawn on the device (seeded)",
+            "config": workload_config(dict(wl, S=S), cx.world, "strong")}
+
+
+def measure_sweep(cx, wl, reps=1):
+    """cfg-sweep (BASELINE configs[2]): error-level x horizon grid on the 2-state example with the input box active.
+    One 'step' = the whole sweep (n_err x nmax cells, per_level perturbations each) on device-resident grids."""
+    import numpy as np
+    torch, eng = cx.torch, cx.eng
+    from lq_mpc_b200 import sampling as sp
+    from lq_mpc_b200.stats import shard_bounds
+    from lq_mpc_b200.sweep import error_horizon_sweep
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q, R, F_u = 2 * np.eye(2), np.eye(1), np.array([[10.0], [-10.0]])
+    eng.set_problem(A, B, Q, R, Q, [-0.1], [0.1], 30)
+    error_vec = np.linspace(1e-3, 1e-2, wl["n_err"])
+    horizons = list(range(1, wl["nmax"] + 1))
+    per_total = wl["per_level"] * cx.world                      # weak scaling: per_level perturbations per GPU
+    lo, hi = shard_bounds(per_total, cx.rank, cx.world)
+    t = time.perf_counter()
+    eA, eB = sp.device_error_grids(eng, 2, 1, error_vec, per_total // 5, wl["norm"], seed=20240522, j_first=lo,
+                                   N_sys=hi - lo)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t
+    wA, wB = sp.device_error_grids(eng, 2, 1, error_vec, 400, wl["norm"])
+    cx.sampler.take()
+    error_horizon_sweep(eng, wA, wB, error_vec, [1, 7, wl["nmax"]], F_u, Q)                  # warm-up (3 horizons)
+    error_horizon_sweep(eng, eA, eB, error_vec, [wl["nmax"]], F_u, Q)
+    launches0 = eng.launch_count
+    best = None
+    for _ in range(reps):
+        cx.barrier()
+        r = error_horizon_sweep(eng, eA, eB, error_vec, horizons, F_u, Q, phase_times=True)
+        sec = cx.max_over_ranks(r["seconds"])
+        if best is None or sec < best[0]:
+            best = (sec, r)
+    launches = eng.launch_count - launches0
+    clocks = cx.sampler.take()
+    sec, r = best
+    del eA, eB
+    torch.cuda.empty_cache()
+    if cx.rank != 0:
+        return None
+    evals_gpu = wl["per_level"] * wl["n_err"] * len(horizons)
+    evals = evals_gpu * cx.world
+    n_void = float(r["n_invalid"].sum())
+    ph = r["phase_seconds"]
+    peak_fp64, peak_dmma = cx.fp64_peaks()
+    peak = max(peak_fp64, peak_dmma)
+    k3_flops = sum(k3_flops_per_eval(2, 1, N) for N in horizons) * wl["per_level"] * wl["n_err"]
+    k3_tf = k3_flops / ph["bounds"] / 1e12
+    return {
+        "metric": "mpc_evals_per_sec", "value": evals / sec, "unit": "evals/s", "n_gpus": cx.world, "steps": reps,
+        "warmup": 2, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic (K6 device sampler, Philox4x32-10, seed 20240522)",
+        "config": workload_config(wl, cx.world),
+        "evals": evals, "evals_valid_bound": evals - n_void, "evals_void_bound": n_void,
+        "valid_evals_per_s": (evals - n_void) / sec,
+        "void_note": "void = 1 - xi - eta <= 0 or a math-domain error: the reference computes (or raises on) these cells "
+                     "too; their true cost, M_V, alpha, beta, xi, eta are still evaluated and reduced",
+        "n_failed": float(r["n_failed"].sum()),
+        "phase_seconds": ph, "phase_share": {k: v / max(sum(ph.values()), 1e-12) for k, v in ph.items()},
+        "roofline": {"bound": "fp64", "bound_detail": "bounds_kernel<2,1>: matrix-free spectrum (two interleaved "
+                     "bisection recursions per thread, registers only) — FP64 pipe / dependent-chain latency",
+                     "kernel": "bounds_kernel<2,1>", "kernel_seconds_per_sweep": ph["bounds"],
+                     "achieved": k3_tf, "peak": peak, "unit": "TFLOP/s", "frac": k3_tf / peak if peak else None,
+                     "algorithmic_flops": "2 searches x 52 probes x N stages x (4n^3+4n^2m+3nm^2+m^3/3) + DARE "
+                                          "(k3_flops_per_eval), summed over N = 1..%d" % wl["nmax"],
+                     "traffic": None},
+        "gpu_launches": int(launches), "sampler_seconds": t_gen, "clocks": clocks,
+        "worst_case": {"true_ratio_max": float(np.nanmax(r["ratio_true_max"])), "V_expert": r["V_expert"]},
+    }
+
+
+def run_ours(args, wl):
+    cx = Ctx()
+    if cx.rank == 0:
+        cx.sampler.start()
+        time.sleep(1.0)      # nvidia-smi's NVML start-up takes driver locks for a few hundred ms: not at a region's edge
+    steps = args.steps
+    line = None
+    if wl.get("sweep"):
+        line = measure_sweep(cx, wl, reps=max(1, min(3, steps)))
+    elif args.scaling == "strong":
+        line = measure_strong(cx, steps)
+        if line is not None:
+            line.update({"metric": "mpc_evals_per_sec", "higher_is_better": True, "vs_baseline": None, "dtype": "f64"})
+    else:
+        line = measure_synth(cx, wl, steps, args.warmup, full=True)
+    subs = {}
+    if args.workload == "cfg-synth-4-2-10" and args.scaling == "weak" and not args.headline_only:
+        strong = measure_strong(cx, max(3, min(10, steps)))
+        k4 = dict(WORKLOADS["cfg-synth-32-8-30"], name="cfg-synth-32-8-30")
+        subs["cfg-synth-32-8-30"] = measure_synth(cx, k4, max(3, min(10, steps)), 3, full=False)
+        sw = dict(WORKLOADS["cfg-sweep-f"], name="cfg-sweep-f")
+        subs["cfg-sweep-f"] = measure_sweep(cx, sw, reps=1)
+        if cx.rank == 0:
+            line["strong_scaling"] = strong
+            line["workloads"] = subs
+    if cx.rank == 0:
+        cx.sampler.stop()
+        if cx.world == 1 and not args.no_cpu_baseline:
+            if wl.get("sweep"):
+                line["cpu_baseline"] = _sweep_cpu_record()
+            elif args.scaling == "weak":
+                line["cpu_baseline"] = _synth_cpu_record(wl, 8_000)
+            else:
+                line["cpu_baseline"] = _synth_cpu_record(dict(WORKLOADS["cfg-synth-4-2-10"]), 8_000)
+            if "cfg-synth-32-8-30" in subs:
+                subs["cfg-synth-32-8-30"]["cpu_baseline"] = _synth_cpu_record(k4, 8_000)
+            if "cfg-sweep-f" in subs:
+                subs["cfg-sweep-f"]["cpu_baseline"] = _sweep_cpu_record()
         print(json.dumps(line))
-    if world > 1:
-        dist.destroy_process_group()
+    if cx.world > 1:
+        cx.dist.barrier()
+        cx.dist.destroy_process_group()
     return 0
+
+
+def _synth_cpu_record(wl, per_worker):
+    v, workers, total = cpu_port_throughput(wl, per_worker)
+    return {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
+            "sample": "%d samples of the same seeded workload (%d per process); oracle/np_batched.py (batched "
+                      "numpy/LAPACK), one process per host core" % (total, total // workers)}
+
+
+def _sweep_cpu_record():
+    v, workers, total = cpu_sweep_throughput(24)
+    return {"value": v, "unit": "evals/s", "cores": workers, "kind": "port",
+            "sample": "%d evals (%d per process; random error level and horizon N in 1..50 of the same example); "
+                      "oracle/np_oracle.eval_one = the reference's per-sample path (utils_class.py:806-859: 8 ring QPs "
+                      "+ 30 closed-loop QPs + dlqr + energy_decreasing + energy_bound), one process per host core"
+                      % (total, total // workers)}
 
 
 def main():
@@ -411,12 +690,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--headline-only", action="store_true", help="skip the strong-scaling / cfg-5 / cfg-sweep sub-records")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--workload", default="cfg-synth-4-2-10", choices=sorted(WORKLOADS))
     args = ap.parse_args()
-    set_workload(args.workload)
+    wl = dict(WORKLOADS[args.workload], name=args.workload)
     if args.impl == "reference":
-        return run_reference(args)
-    return run_ours(args)
+        return run_reference(args, wl)
+    return run_ours(args, wl)
 
 
 if __name__ == "__main__":

@@ -38,7 +38,7 @@ def _strided_columns(v, n_err):
 def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], horizons: Sequence[int], F_u, Q,
                         N_points: int = 8, ext_radius_max: float = 1.5, p=(0.1, 1.0, 0.6), T: int = 30,
                         strict_reference: bool = True, group=None, keep_tables: bool = False,
-                        shard: Optional[tuple] = None):
+                        shard: Optional[tuple] = None, phase_times: bool = False):
     """Full error-level x horizon sweep on an engine whose TRUE problem (A, B, Q, R, box, N_opc) is already set.
 
     error_A (n,n,N_sys,n_err), error_B (n,m,N_sys,n_err): the reference's grid layout (numpy) — `shard` = (rank, world)
@@ -49,7 +49,9 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
       'ratio_true_max' / 'ratio_bound_max' (performance ratios J / V_expert, worst case per cell),
       'n_invalid' [n_err][n_horizons] (samples whose bound is void or raised in the reference),
       'n_failed' [n_err][n_horizons] (samples with an incomplete solve: QP_MAXITER / *_NOCONV / CHOL_FAIL — expected 0),
-      'evals', 'seconds' (device time of the sweep loop), and with keep_tables the raw [n_horizons][q][n_err][N_sys].
+      'evals', 'seconds' (device time of the sweep loop), and with keep_tables the raw [n_horizons][q][n_err][N_sys];
+      with phase_times 'phase_seconds' = device time per kernel family over the whole sweep (CUDA events between the
+      launches, read after the loop: no synchronisation is added).
     """
     import torch
     n_err = len(error_vec)
@@ -85,12 +87,23 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
     t0 = time.perf_counter()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
+    marks = []
+
+    def mark():
+        if phase_times:
+            ev = torch.cuda.Event(enable_timing=True)
+            ev.record()
+            marks.append(ev)
     for h, N in enumerate(horizons):
         N = int(N)
+        mark()
         rs = engine.mpc_solve_batch(dA, dB, N, pts=ring, want=("M_V", "flags"))
         mv = rs["M_V"]
+        mark()
         sim = engine.simulate_batch(dA, dB, N, T, x0_shared=x_start, want=("J_T", "flags"))
+        mark()
         b = engine.bounds_batch(dA, dB, N, e_per, e_per, mv, x_start, p, V_expert, strict_reference=strict_reference)
+        mark()
         cols = torch.cat([_strided_columns(v, n_err) for v in
                           (sim["J_T"], b["bound"], b["alpha"], b["beta"], b["xi"], b["eta"], mv)], dim=0)
         st = _stats.column_stats(engine, cols, group=group)            # [len(QUANTITIES)*n_err] columns
@@ -107,8 +120,15 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
         n_failed[:, h] = _strided_columns(fail, n_err).sum(dim=1).cpu().numpy()
         if keep_tables:
             tables.append(cols.reshape(len(QUANTITIES), n_err, N_sys).cpu().numpy())
+    mark()
     e1.record()
     torch.cuda.synchronize(engine.device)
+    phases = None
+    if phase_times:
+        phases = {"ring_solves": 0.0, "simulate": 0.0, "bounds": 0.0, "stats_and_packing": 0.0}
+        names = list(phases)
+        for i in range(len(marks) - 1):
+            phases[names[i % 4]] += marks[i].elapsed_time(marks[i + 1]) * 1e-3
     import torch.distributed as dist
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         t = torch.from_numpy(np.stack([n_invalid, n_failed])).to(engine.device)   # (column_stats merged the moments)
@@ -121,4 +141,6 @@ def error_horizon_sweep(engine, error_A, error_B, error_vec: Sequence[float], ho
                 "wall_seconds": time.perf_counter() - t0})
     if keep_tables:
         res["tables"] = np.stack(tables)
+    if phases is not None:
+        res["phase_seconds"] = phases
     return res
