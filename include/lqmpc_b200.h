@@ -80,6 +80,19 @@ int lqmpc_eval_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* 
                      int N_max, int T, double* J, double* rho, double* ratio, double* V_N, double* J_T,
                      int32_t* flags, double* K0);
 
+/* Same evaluation on SEEDED SYNTHETIC samples drawn inside the kernel (no operand traffic): global sample s in
+ * [first, first + S) draws dA, dB entrywise uniform in [-e_A, e_A) / [-e_B, e_B) and x0 ~ N(0, I) from Philox4x32-10
+ * keyed by `seed` with the counter (s, pair index) — the stream of BASELINE's synthetic configurations (SURVEY 8d.4:
+ * "Philox ... with sample index as counter so every shard size sees identical samples"), restated bit-for-bit
+ * (uniforms) in oracle/np_sampler.seeded_samples. Replaces the host-side generation + upload in front of the sweep
+ * loops (utils_class.py:802-833 on error_matrix_generator output, utils.py:826-847) for synthetic studies.
+ *   J, rho, ratio [H][S], flags [H][S] int32 : device, any may be NULL
+ *   moments [3 H][6] device or NULL : the one-pass column moments (see lqmpc_column_moments) of the [3 H][S] table
+ *     {J rows, rho rows, ratio rows}; then J/rho/ratio must be that one contiguous table, or all NULL (the tables then
+ *     live in the context's scratch and only the moments leave the call). */
+int lqmpc_eval_seeded(lqmpc_ctx* ctx, uint64_t seed, int64_t first, int64_t S, double e_A, double e_B, int N_min,
+                      int N_max, double* J, double* rho, double* ratio, int32_t* flags, double* moments);
+
 /* Same computation driven from HOST buffers (pinned or pageable): the batch is cut into chunks that are copied
  * H2D, evaluated and copied back D2H on alternating streams so copies overlap compute. All pointers are HOST
  * pointers with the same SoA layout over the full S. Synchronises before returning. This is the call `bench.py`

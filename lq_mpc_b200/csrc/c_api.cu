@@ -105,7 +105,7 @@ int pipe_abort(lqmpc_ctx* ctx, int rc) {
 
 extern "C" {
 
-int lqmpc_abi_version(void) { return 1; }
+int lqmpc_abi_version(void) { return 2; }
 
 const char* lqmpc_supported_dims(void) { return LQ_DIMS_STRING; }
 
@@ -131,6 +131,7 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
+  if (ctx->seed_buf) cudaFree(ctx->seed_buf);
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
   if (ctx->ref_x) cudaFree(ctx->ref_x);
   if (ctx->ref_u) cudaFree(ctx->ref_u);
@@ -366,6 +367,44 @@ int lqmpc_eval_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* 
   a.N_min = N_min; a.N_max = N_max; a.T = J_T ? T : 0;
   a.J = J; a.rho = rho; a.ratio = ratio; a.Vn = V_N; a.JT = J_T; a.flags = flags; a.K0 = K0;
   return lq_launch_eval(ctx, a, ctx->stream);
+}
+
+int lqmpc_eval_seeded(lqmpc_ctx* ctx, uint64_t seed, int64_t first, int64_t S, double e_A, double e_B, int N_min,
+                      int N_max, double* J, double* rho, double* ratio, int32_t* flags, double* moments) {
+  if (!ctx) return LQMPC_EINVAL;
+  if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
+  if (S < 0 || first < 0 || N_min < 1 || N_max < N_min) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/first/N_min/N_max");
+  if (S == 0) return LQMPC_OK;
+  cudaSetDevice(ctx->device);
+  const int H = N_max - N_min + 1;
+  double* tab[3] = {J, rho, ratio};
+  if (moments) {
+    // the moments are taken over ONE contiguous [3 H][S] table (J rows, rho rows, ratio rows): tables the caller did
+    // not ask for live in the context's own scratch
+    const bool contiguous = J && rho && ratio && rho == J + (int64_t)H * S && ratio == rho + (int64_t)H * S;
+    if (!contiguous) {
+      if (J || rho || ratio)
+        return lq_set_error(ctx, LQMPC_EINVAL, "with moments, pass J/rho/ratio as one contiguous [3H][S] table or all NULL");
+      const size_t need = (size_t)3 * H * S * sizeof(double);
+      if (need > ctx->seed_bytes) {
+        if (ctx->seed_buf) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->seed_buf); ctx->seed_buf = nullptr; }
+        ctx->seed_bytes = 0;
+        int rc = lq_check_cuda(ctx, cudaMalloc(&ctx->seed_buf, need), "cudaMalloc seeded tables");
+        if (rc) return rc;
+        ctx->seed_bytes = need;
+      }
+      double* b = reinterpret_cast<double*>(ctx->seed_buf);
+      tab[0] = b; tab[1] = b + (int64_t)H * S; tab[2] = b + (int64_t)2 * H * S;
+    }
+  }
+  EvalArgs a;
+  a.S = S; a.ld = S; a.dA = nullptr; a.dB = nullptr; a.x0 = nullptr;
+  a.N_min = N_min; a.N_max = N_max; a.T = 0;
+  a.J = tab[0]; a.rho = tab[1]; a.ratio = tab[2]; a.Vn = nullptr; a.JT = nullptr; a.flags = flags; a.K0 = nullptr;
+  int rc = lq_launch_eval_seeded(ctx, a, seed, first, e_A, e_B);
+  if (rc) return rc;
+  if (moments) rc = lq_launch_moments(ctx, tab[0], 3 * H, S, S, moments);
+  return rc;
 }
 
 int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const double* dB_h, const double* x0_h,

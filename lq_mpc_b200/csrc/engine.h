@@ -42,6 +42,9 @@ struct lqmpc_ctx {
   // scratch (grown on demand)
   void* ws = nullptr;
   size_t ws_bytes = 0;
+  // result tables of lqmpc_eval_seeded when the caller only wants the column moments (grown on demand)
+  void* seed_buf = nullptr;
+  size_t seed_bytes = 0;
   // host-pipeline resources
   cudaStream_t pipe_stream[2] = {nullptr, nullptr};
   cudaEvent_t pipe_done[2] = {nullptr, nullptr};
@@ -140,6 +143,7 @@ int lq_reserve_ws(lqmpc_ctx* ctx, size_t bytes);
 // launchers (one per kernel family; each switches on ctx->n, ctx->m)
 int lq_launch_prepare(lqmpc_ctx* ctx);
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
+int lq_launch_eval_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B);
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_dmma_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_mpc(lqmpc_ctx* ctx, const MpcArgs& a, bool simulate);

@@ -7,6 +7,7 @@
 #include <stdlib.h>
 
 #include "engine.h"
+#include "sampler.cuh"
 
 namespace {
 
@@ -52,6 +53,21 @@ __global__ void __launch_bounds__(128, MINB) eval_kernel(const __grid_constant__
   for (int e = 0; e < n * m; ++e) dB[e] = ld_stream(a.dB + (int64_t)e * a.ld + s);
 #pragma unroll
   for (int e = 0; e < n; ++e) x0[e] = ld_stream(a.x0 + (int64_t)e * a.ld + s);
+  DeviceSink<n, m> sink{a, s};
+  lq::eval_sample<n, m>(pb, dA, dB, x0, a.N_min, a.N_max, a.T, a.Vn != nullptr, sink);
+}
+
+// Same evaluation with the operands DRAWN IN THE KERNEL from the global sample index (sampler.cuh: seeded_sample):
+// no operand traffic at all — the fused "generate + evaluate" entry point north_star's Philox design implies.
+template <int n, int m, int MINB>
+__global__ void __launch_bounds__(128, MINB) eval_seeded_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+                                                                const __grid_constant__ EvalArgs a,
+                                                                const uint64_t seed, const int64_t first,
+                                                                const double e_A, const double e_B) {
+  const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= a.S) return;
+  double dA[n * n], dB[n * m], x0[n];
+  lq::seeded_sample<n, m>(seed, first + s, e_A, e_B, dA, dB, x0);
   DeviceSink<n, m> sink{a, s};
   lq::eval_sample<n, m>(pb, dA, dB, x0, a.N_min, a.N_max, a.T, a.Vn != nullptr, sink);
 }
@@ -105,6 +121,20 @@ int launch_eval_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
 }
 
 template <int n, int m>
+int launch_eval_seeded_t(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B) {
+  const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
+  const int threads = 128;
+  const int64_t blocks = (a.S + threads - 1) / threads;
+  if (blocks > 0x7fffffffLL) return lq_set_error(ctx, LQMPC_EINVAL, "batch too large for one launch");
+  if (a.N_min == a.N_max)
+    eval_seeded_kernel<n, m, K1Tune<n, m>::minb_single><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a, seed, first, e_A, e_B);
+  else
+    eval_seeded_kernel<n, m, K1Tune<n, m>::minb_nested><<<(unsigned)blocks, threads, 0, ctx->stream>>>(pb, a, seed, first, e_A, e_B);
+  ctx->launches++;
+  return lq_check_cuda(ctx, cudaGetLastError(), "eval_seeded_kernel launch");
+}
+
+template <int n, int m>
 int launch_prepare_t(lqmpc_ctx* ctx) {
   using P = lq::Problem<n, m>;
   if (ctx->pb_dev == nullptr) {
@@ -140,6 +170,14 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
 #define X(N_, M_) \
   if (ctx->n == N_ && ctx->m == M_) return launch_eval_t<N_, M_>(ctx, a, stream);
+  LQ_FOR_EACH_DIM(X)
+#undef X
+  return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
+}
+
+int lq_launch_eval_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B) {
+#define X(N_, M_) \
+  if (ctx->n == N_ && ctx->m == M_) return launch_eval_seeded_t<N_, M_>(ctx, a, seed, first, e_A, e_B);
   LQ_FOR_EACH_DIM(X)
 #undef X
   return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");

@@ -82,4 +82,34 @@ LQ_HD int sample_error_matrix(uint64_t seed, int which, int64_t j, int level, do
   return -kSamplerMaxAttempts;
 }
 
+// ---- seeded synthetic evaluation samples (lqmpc_eval_seeded): sample s draws its (dA, dB, x0) from Philox4x32-10 keyed
+// by the seed with the counter (s lo, s hi, pair index, 0): dA, dB entries e (2u - 1) uniform in [-e, e) (one rounding,
+// as above), x0 ~ N(0, I) by Box-Muller on the next pairs. The GLOBAL sample index is the counter, so any sharding of
+// [first, first + S) over ranks sees identical samples. Restated in oracle/np_sampler.seeded_samples:
+// the uniforms are bit-exact, the normals agree to the last digits of log / cos / sin.
+constexpr uint32_t kSeededStream = 0x53454544u;   // "SEED"
+
+template <int n, int m>
+LQ_HD void seeded_sample(uint64_t seed, int64_t s, double e_A, double e_B, double* dA, double* dB, double* x0) {
+  const uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32) ^ kSeededStream;
+  const uint32_t c0 = (uint32_t)s, c1 = (uint32_t)((uint64_t)s >> 32);
+  constexpr int nu = n * n + n * m;
+  LQ_UNROLL for (int p = 0; p < (nu + 1) / 2; ++p) {
+    const Philox4 x = philox4x32_10(c0, c1, (uint32_t)p, 0u, k0, k1);
+    const double u0 = philox_symm(x.v[0], x.v[1]), u1 = philox_symm(x.v[2], x.v[3]);
+    const int q0 = 2 * p, q1 = 2 * p + 1;
+    if (q0 < n * n) dA[q0] = e_A * u0; else dB[q0 - n * n] = e_B * u0;
+    if (q1 < nu) { if (q1 < n * n) dA[q1] = e_A * u1; else dB[q1 - n * n] = e_B * u1; }
+  }
+  LQ_UNROLL for (int p = 0; p < (n + 1) / 2; ++p) {
+    const Philox4 x = philox4x32_10(c0, c1, (uint32_t)((nu + 1) / 2 + p), 0u, k0, k1);
+    // u in (0, 1] for the logarithm, v in [0, 1) for the angle: 53-bit uniforms
+    const double u = ((double)(x.v[0] >> 5) * 67108864.0 + (double)(x.v[1] >> 6) + 1.0) * (1.0 / 9007199254740992.0);
+    const double v = ((double)(x.v[2] >> 5) * 67108864.0 + (double)(x.v[3] >> 6)) * (1.0 / 9007199254740992.0);
+    const double r = sqrt(-2.0 * log(u)), th = 6.283185307179586476925286766559 * v;
+    x0[2 * p] = r * cos(th);
+    if (2 * p + 1 < n) x0[2 * p + 1] = r * sin(th);
+  }
+}
+
 }  // namespace lq

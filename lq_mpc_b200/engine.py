@@ -43,6 +43,7 @@ ABI = {
     "lqmpc_set_problem": (_int, [_vp, _int, _int] + [_vp] * 7 + [_int]),
     "lqmpc_get_prepared": (_int, [_vp, _vp, _i64]),
     "lqmpc_eval_batch": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int] + [_vp] * 7),
+    "lqmpc_eval_seeded": (_int, [_vp, ctypes.c_uint64, _i64, _i64, ctypes.c_double, ctypes.c_double, _int, _int] + [_vp] * 5),
     "lqmpc_eval_batch_host": (_int, [_vp, _i64, _vp, _vp, _vp, _int, _int, _int, _vp, _vp, _vp, _vp, _i64]),
     "lqmpc_set_problem_tiled": (_int, [_vp, _int, _int] + [_vp] * 5 + [_int]),
     "lqmpc_get_prepared_tiled": (_int, [_vp, _vp, _i64]),
@@ -305,6 +306,30 @@ class Engine:
                                        _ptr(out.get("V_N")), _ptr(out.get("J_T")), _ptr(out.get("flags")),
                                        _ptr(out.get("K0")))
         self._check(rc, "lqmpc_eval_batch")
+        return out
+
+    @_streamed
+    def eval_seeded(self, seed: int, first: int, S: int, e_A: float, e_B: float, N_min: int, N_max: int,
+                    want=("moments",)):
+        """K1 on seeded synthetic samples drawn in the kernel (global sample indices [first, first + S)).
+        want: any of "J", "rho", "ratio", "flags" (device tensors [H][S]; J/rho/ratio are rows of one `table`) and
+        "moments" (device [3H][6]: max, min, n_finite, n_nonfinite, mean, M2 per column of {J, rho, ratio})."""
+        torch = self.torch
+        H = N_max - N_min + 1
+        out = {}
+        tables = any(k in want for k in ("J", "rho", "ratio"))
+        if tables:
+            table = torch.empty((3 * H, S), dtype=torch.float64, device=self.device)
+            out["table"] = table
+            out["J"], out["rho"], out["ratio"] = table[:H], table[H:2 * H], table[2 * H:]
+        if "flags" in want:
+            out["flags"] = torch.empty((H, S), dtype=torch.int32, device=self.device)
+        if "moments" in want:
+            out["moments"] = torch.empty((3 * H, 6), dtype=torch.float64, device=self.device)
+        rc = self.lib.lqmpc_eval_seeded(self._h, int(seed), int(first), int(S), float(e_A), float(e_B), N_min, N_max,
+                                        _ptr(out.get("J")), _ptr(out.get("rho")), _ptr(out.get("ratio")),
+                                        _ptr(out.get("flags")), _ptr(out.get("moments")))
+        self._check(rc, "lqmpc_eval_seeded")
         return out
 
     @_streamed

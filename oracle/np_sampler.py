@@ -80,3 +80,37 @@ def sample_error_grid(seed, which, rows, cols, N_sys, levels, n_boundary, norm_t
     T[proj] *= (e[proj] / nv_last[proj])[:, None]
     grid = np.ascontiguousarray(T.T).reshape(rows, cols, N_sys, n_err)
     return grid, rejected, int(proj.size)
+
+
+SEEDED_STREAM = 0x53454544
+
+
+def seeded_samples(seed, first, S, n, m, e_A, e_B):
+    """Restatement of lq::seeded_sample (csrc/sampler.cuh; entry point lqmpc_eval_seeded): global samples
+    [first, first + S) -> dA (S, n, n), dB (S, n, m) uniform in [-e, e) (bit-exact against the device), x0 (S, n)
+    ~ N(0, I) by Box-Muller (agrees with the device to the last digits of log / cos / sin)."""
+    k0 = seed & 0xFFFFFFFF
+    k1 = ((seed >> 32) & 0xFFFFFFFF) ^ SEEDED_STREAM
+    s = np.arange(first, first + S, dtype=np.uint64)
+    c0, c1 = s & _MASK, s >> np.uint64(32)
+    nu = n * n + n * m
+    flat = np.empty((S, nu))
+    for p in range((nu + 1) // 2):
+        x = philox4x32_10(c0, c1, np.uint64(p), np.uint64(0), k0, k1)
+        flat[:, 2 * p] = symm(x[0], x[1])
+        if 2 * p + 1 < nu:
+            flat[:, 2 * p + 1] = symm(x[2], x[3])
+    dA = (e_A * flat[:, :n * n]).reshape(S, n, n)
+    dB = (e_B * flat[:, n * n:]).reshape(S, n, m)
+    x0 = np.empty((S, n))
+    for p in range((n + 1) // 2):
+        x = philox4x32_10(c0, c1, np.uint64((nu + 1) // 2 + p), np.uint64(0), k0, k1)
+        u = ((x[0] >> np.uint32(5)).astype(np.float64) * 67108864.0 + (x[1] >> np.uint32(6)).astype(np.float64) + 1.0) \
+            * (1.0 / 9007199254740992.0)
+        v = ((x[2] >> np.uint32(5)).astype(np.float64) * 67108864.0 + (x[3] >> np.uint32(6)).astype(np.float64)) \
+            * (1.0 / 9007199254740992.0)
+        r, th = np.sqrt(-2.0 * np.log(u)), 6.283185307179586476925286766559 * v
+        x0[:, 2 * p] = r * np.cos(th)
+        if 2 * p + 1 < n:
+            x0[:, 2 * p + 1] = r * np.sin(th)
+    return dA, dB, x0

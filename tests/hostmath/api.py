@@ -149,3 +149,12 @@ def tridiag_extremes(d, e):
     out = np.zeros(2)
     lib().hm_tridiag_extremes(_p(d), _p(e), len(d), _p(out))
     return out[0], out[1]
+
+
+def seeded_samples(seed, first, S, n, m, e_A, e_B):
+    """lq::seeded_sample (the generator behind lqmpc_eval_seeded): dA (S,n,n), dB (S,n,m), x0 (S,n)."""
+    dA, dB, x0 = np.zeros((S, n, n)), np.zeros((S, n, m)), np.zeros((S, n))
+    rc = lib().hm_seeded_samples(n, m, ctypes.c_uint64(seed), ctypes.c_int64(first), ctypes.c_int64(S),
+                                 ctypes.c_double(e_A), ctypes.c_double(e_B), _p(dA), _p(dB), _p(x0))
+    assert rc == 0
+    return dA, dB, x0

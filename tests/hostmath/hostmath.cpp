@@ -288,6 +288,20 @@ void hm_philox4x32_10(const uint32_t* ctr, const uint32_t* key, uint32_t* out) {
   for (int i = 0; i < 4; ++i) out[i] = x.v[i];
 }
 
+// seeded synthetic evaluation samples (lqmpc_eval_seeded's generator), AoS output: dA [S][n*n], dB [S][n*m], x0 [S][n]
+int hm_seeded_samples(int n, int m, uint64_t seed, int64_t first, int64_t S, double e_A, double e_B, double* dA,
+                      double* dB, double* x0) {
+  for (int64_t s = 0; s < S; ++s) {
+    double* a = dA + s * n * n; double* b = dB + s * n * m; double* x = x0 + s * n;
+    if (n == 4 && m == 2) lq::seeded_sample<4, 2>(seed, first + s, e_A, e_B, a, b, x);
+    else if (n == 2 && m == 1) lq::seeded_sample<2, 1>(seed, first + s, e_A, e_B, a, b, x);
+    else if (n == 3 && m == 3) lq::seeded_sample<3, 3>(seed, first + s, e_A, e_B, a, b, x);
+    else if (n == 1 && m == 1) lq::seeded_sample<1, 1>(seed, first + s, e_A, e_B, a, b, x);
+    else return -1;
+  }
+  return 0;
+}
+
 // the sampler core for the shapes of the reference example (2x2, 2x1) and the synthetic one (4x4, 4x2); SoA output
 int hm_sample_error_grid(uint64_t seed, int which, int rows, int cols, int64_t N_sys, int64_t j_first, int n_err,
                          const double* levels, int64_t n_boundary, int norm_type, double* out, int64_t* stats) {

@@ -127,6 +127,42 @@ def test_k1_cfg4_vs_untouched_reference(engine, cfg4):
         assert np.max(np.abs(sim["U"].cpu().numpy()[:5, :, s].T - np.array(c["U_head"]))) < 1e-10
 
 
+def test_k1_seeded_entry_point(engine):
+    """lqmpc_eval_seeded: (dA, dB, x0) drawn INSIDE the kernel from the global sample index. The tables must equal the
+    oracle evaluated on the numpy restatement of the same Philox stream (1e-9; the uniforms are bit-exact), the fused
+    column moments must equal numpy on those tables, two shards must reproduce one batch bit for bit, and the
+    moments-only call (tables in the context's scratch) must return the same moments."""
+    import torch
+    from oracle import np_batched as nb, np_sampler as ns
+    from lq_mpc_b200 import stats
+    A, B, Q, R = nb.synth_problem(4, 2, seed=0)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    S, first = 20_001, (1 << 32) - 7000                      # the index range crosses 2^32
+    got = engine.eval_seeded(1, first, S, 0.01, 0.01, 9, 10, want=("J", "rho", "ratio", "flags", "moments"))
+    dA, dB, x0 = ns.seeded_samples(1, first, S, 4, 2, 0.01, 0.01)
+    ref = nb.eval_batch(A, B, Q, R, Q, nb.expert_matrix(A, B, Q, R, Q, 30), dA, dB, x0, 9, 10)
+    for k in ("J", "rho", "ratio"):
+        assert relerr(got[k].cpu().numpy(), ref[k]) < TOL, k
+    assert not got["flags"].cpu().numpy().any()
+    tab = got["table"].cpu().numpy()
+    st = stats.merge_moments(got["moments"].cpu().numpy()[None])
+    assert np.array_equal(st["max"], tab.max(axis=1)) and np.array_equal(st["min"], tab.min(axis=1))
+    assert relerr(st["mean"], tab.mean(axis=1)) < 1e-12 and relerr(st["std"], tab.std(axis=1)) < 1e-9
+    only = engine.eval_seeded(1, first, S, 0.01, 0.01, 9, 10, want=("moments",))
+    assert torch.equal(only["moments"], got["moments"])
+    a = engine.eval_seeded(1, first, 12_000, 0.01, 0.01, 9, 10, want=("J", "rho", "ratio"))
+    b = engine.eval_seeded(1, first + 12_000, S - 12_000, 0.01, 0.01, 9, 10, want=("J", "rho", "ratio"))
+    assert torch.equal(torch.cat([a["table"], b["table"]], dim=1), got["table"])
+    # different error levels for A and B, another shape
+    A2, B2, Q2, R2 = nb.synth_problem(2, 1, seed=0)
+    engine.set_problem(A2, B2, Q2, R2, Q2, None, None, 30)
+    g2 = engine.eval_seeded(9, 0, 3001, 0.03, 0.002, 5, 5, want=("J", "rho", "ratio"))
+    dA2, dB2, x2 = ns.seeded_samples(9, 0, 3001, 2, 1, 0.03, 0.002)
+    r2 = nb.eval_batch(A2, B2, Q2, R2, Q2, nb.expert_matrix(A2, B2, Q2, R2, Q2, 30), dA2, dB2, x2, 5, 5)
+    assert relerr(g2["J"].cpu().numpy(), r2["J"]) < TOL and relerr(g2["rho"].cpu().numpy(), r2["rho"]) < TOL
+    assert engine.eval_seeded(1, 0, 0, 0.01, 0.01, 3, 3, want=("J",))["J"].shape == (1, 0)
+
+
 def test_k1_unstable_flagged(engine):
     """An estimated model far from the plant gives an unstable closed loop: J = +inf, flag bit 0, rho >= 1."""
     A = np.array([[1.2, 0.5], [0.0, 1.1]])

@@ -61,6 +61,28 @@ def test_sampler_semantics_and_shard_invariance():
     assert abs(g[:, :, 60:, 9].mean()) < 2e-4 and g[:, :, 60:, 9].std() > 2e-3
 
 
+def test_seeded_evaluation_samples_core_matches_oracle():
+    """The generator behind lqmpc_eval_seeded (csrc/sampler.cuh: seeded_sample, compiled here with g++) vs its numpy
+    restatement: uniforms bit-exact, Box-Muller normals to rounding; N(0, I) / U[-e, e) moments; counter = global
+    sample index (a shard starting at `first` reproduces the corresponding slice)."""
+    from tests.hostmath import api as hm
+    for n, m in ((4, 2), (2, 1), (3, 3), (1, 1)):
+        dA, dB, x0 = hm.seeded_samples(77, 5, 4096, n, m, 0.01, 0.02)
+        rA, rB, rx = ns.seeded_samples(77, 5, 4096, n, m, 0.01, 0.02)
+        assert np.array_equal(dA, rA) and np.array_equal(dB, rB)
+        assert np.max(np.abs(x0 - rx)) < 1e-14
+        assert np.max(np.abs(dA)) <= 0.01 and np.max(np.abs(dB)) <= 0.02
+    a_all = ns.seeded_samples(3, 0, 3000, 4, 2, 0.01, 0.01)
+    a_mid = ns.seeded_samples(3, 1000, 500, 4, 2, 0.01, 0.01)
+    for u, v in zip(a_all, a_mid):
+        assert np.array_equal(u[1000:1500], v)
+    big = ns.seeded_samples(11, 1 << 33, 200_000, 4, 2, 0.01, 0.01)            # indices beyond 2^32
+    assert abs(big[2].mean()) < 5e-3 and abs(big[2].std() - 1.0) < 5e-3
+    assert abs(big[0].mean()) < 1e-4 and abs(big[0].std() - 0.01 / np.sqrt(3)) < 1e-4
+    other = ns.seeded_samples(12, 1 << 33, 100, 4, 2, 0.01, 0.01)
+    assert not np.array_equal(other[0], big[0][:100])
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("rows,cols,norm", [(2, 2, "f"), (2, 1, "2"), (4, 4, "2"), (3, 2, "f")])
 def test_device_sampler_matches_oracle(engine, rows, cols, norm):
