@@ -271,6 +271,101 @@ struct BoundsScalars {
   int polyP = 0;
 };
 
+// Everything of the bound computation that is scalar arithmetic on the norms / eigenvalue extremes the matrix part
+// produced (shared by the thread-per-sample kernel below and the run-time-dimension warp route, dyn.cuh).
+struct BoundsNorms {
+  double fA, fB, nK;        // ||A^||_2, ||B^||_2, ||K||_2
+  double eps_K;             // local_radius (utils.py:548-564)
+  double rho_cl;            // rho(A^ + B^ K)
+  double nPhi;              // ||Phi||_2
+  double cmax, min_H;       // lambda_max(Gamma'Gamma), lambda_min(H^)
+  double bu, bdu;           // max ||u||^2, max ||u1 - u2||^2 over the input set
+  double nx2;               // ||x||^2
+};
+
+LQ_HD int bounds_formulas(double maxQ, double minQ, double maxR, double minR, const BoundsScalars& sc,
+                          const BoundsNorms& q, double* out) {
+  int flags = 0;
+  const int N = sc.N;
+  const double fA = q.fA, fB = q.fB, nK = q.nK, eps_K = q.eps_K, rho_cl = q.rho_cl, bu = q.bu, bdu = q.bdu;
+  const double ratioQ = maxQ / minQ;
+  out[BF_BAR_U] = bu; out[BF_BAR_D_U] = bdu;
+  out[BF_NORM_A] = fA; out[BF_NORM_B] = fB; out[BF_NORM_K] = nK;
+  out[BF_EPSILON_K] = eps_K;
+  out[BF_RHO_CL] = rho_cl;
+  out[BF_NORM_PHI] = q.nPhi;
+  const double nG = sqrt(dmax(q.cmax, 0.0));
+  out[BF_NORM_GAMMA] = nG;
+  const double min_H = q.min_H;
+  out[BF_MIN_H] = min_H;
+  const double nx2 = q.nx2;
+  const double rho_K = (rho_cl + 0.4) * (rho_cl + 0.4);
+  const double C_K = (1.0 + maxR * nK * nK / minQ) * dmax(1.0, ratioQ * 1.21);
+  const double gam = C_K / (1.0 - rho_K);
+  const double rho_g = (gam - 1.0) / gam;
+  out[BF_C_K] = C_K; out[BF_RHO_K] = rho_K; out[BF_GAMMA] = gam; out[BF_RHO_GAMMA] = rho_g;
+  // ---------------- ex_stability_bounds (utils.py:567-584)
+  const double L_V = dmax(gam, sc.M_V / eps_K);
+  const double N_0 = ceil(dmax(0.0, sc.M_V / eps_K - gam));
+  out[BF_L_V] = L_V; out[BF_N_0] = N_0;
+  // ---------------- fc_omega_eta (utils.py:469-523)
+  const double fA2 = fA * fA;
+  const double G_A = (fA == 1.0) ? (double)(N - 1) : (1.0 - pow(fA, 2.0 * (N - 1))) / (1.0 - fA2);
+  const double term = 1.0 + fA2 * ratioQ;
+  const double arg1 = fA2 * ratioQ * gam;
+  if (!(arg1 > 0.0) || !(rho_g > 0.0)) flags |= FLAG_DOMAIN_ERROR;   // math.log raises ValueError in the reference
+  const double N_min = ceil(N_0 - log(arg1) / log(rho_g));
+  const double fApow = pow(fA, (double)(2 * N - 2));
+  const double rg_pow = pow(rho_g, (double)N - N_0);
+  const double w1 = maxQ * (term * fApow + G_A);
+  const double decay = maxQ * fApow * gam * rg_pow;
+  const double w05_a = maxQ * (L_V - 1.0) * G_A;
+  if (w05_a < 0.0 || decay < 0.0) flags |= FLAG_DOMAIN_ERROR;        // math.sqrt domain error
+  const double w05 = sqrt(w05_a) + 0.5 * term * sqrt(decay);
+  const double eta = (term - 1.0) * gam * rg_pow;
+  const double disc = w05 * w05 + w1 * (1.0 - eta);
+  if (disc < 0.0) flags |= FLAG_DOMAIN_ERROR;
+  const double err_th_r = (sqrt(disc) - w05) / w1;
+  out[BF_OMEGA_N1] = w1; out[BF_OMEGA_N0D5] = w05; out[BF_ETA] = eta; out[BF_ERR_TH] = err_th_r * err_th_r;
+  out[BF_N_MIN] = N_min;
+  // ---------------- fc_ec_h and xi (utils.py:526-538, utils_class.py:371)
+  const double h = sc.e_A * sc.e_A / minQ + sc.e_B * sc.e_B / minR;
+  const double xi = h * w1 + 2.0 * sqrt(h) * w05;
+  out[BF_H] = h; out[BF_XI] = xi;
+  // ---------------- error-consistent sums (utils.py:78-117, 186-223, 296-305)
+  const double nx = sqrt(nx2);
+  const double eAfA = sc.e_A + fA, eBfB = sc.e_B + fB;
+  double s_in = 0.0, s_out = 0.0, bgx = 0.0, bgu = 0.0, bgu_in = 0.0;
+  for (int i = 0; i <= N; ++i) {
+    const double fpi = pow(fA, (double)i);
+    const double gx1 = pow(eAfA, (double)i) - fpi;
+    const double gu1 = eBfB * gx1 + sc.e_B * fpi;
+    s_out += (s_in + gx1 * gx1) * (nx * nx + i * bu);
+    s_in += gu1 * gu1;
+    if (i >= 1) bgx += gx1;
+    if (i < N) { bgu_in += gu1; bgu += bgu_in; }
+  }
+  const double E_psi = maxQ * s_out;
+  const double theta_u = maxQ * (2.0 * nG * bgu + bgu * bgu);
+  const double theta_xu = maxQ * (nG * bgx + out[BF_NORM_PHI] * bgu + bgx * bgu);
+  const double bar_theta = sqrt(N * bu) * theta_u + nx * theta_xu;
+  const double cand = dmin(sqrt(N * bdu), bar_theta / min_H);
+  const double E_u = maxR * cand * cand;
+  const double E_psi_u = maxQ / maxR * (nG + bgu) * (nG + bgu) * E_u;
+  out[BF_E_PSI] = E_psi; out[BF_E_U] = E_u; out[BF_E_PSI_U] = E_psi_u;
+  out[BF_THETA_U] = theta_u; out[BF_THETA_X_U] = theta_xu;
+  // ---------------- alpha, beta (utils_class.py:329-340), J_bound (utils_class.py:858-859)
+  const double sp = sqrt(E_psi), su = sqrt(E_u), spu = sqrt(E_psi_u);
+  const double p0 = sc.p[0], p1 = sc.p[1], p2 = sc.p[2];
+  const double alpha = dmax(p0 * sp + p2 * spu + p0 * sp * p2 * spu, p1 * su);
+  const double beta = (1.0 + p0 * sp) * ((1.0 / p2) * spu + E_psi_u) + (1.0 / p1) * su + E_u + (1.0 / p0) * sp + E_psi;
+  out[BF_ALPHA] = alpha; out[BF_BETA] = beta;
+  const double den = 1.0 - xi - eta;
+  if (!(den > 0.0)) flags |= FLAG_BOUND_INVALID;
+  out[BF_BOUND] = (alpha * sc.V_expert + beta) / den;
+  return flags;
+}
+
 // Gamma[(t, r), (j, s)] for t = 0..N, j = 0..N-1 from the stored G_d = A^d B.
 template <int n, int m>
 LQ_HD double gamma_entry(const WsView& ws, const BoundsLayout<n, m>& L, int t, int r, int j, int s) {
@@ -338,40 +433,8 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
   const double rho_cl = spectral_radius<n>(Acl, &eig_ok);
   if (!eig_ok) flags |= FLAG_EIG_NOCONV;
   out[BF_RHO_CL] = rho_cl;
-  const double rho_K = (rho_cl + 0.4) * (rho_cl + 0.4);
-  const double C_K = (1.0 + maxR * nK * nK / minQ) * dmax(1.0, ratioQ * 1.21);
-  const double gam = C_K / (1.0 - rho_K);
-  const double rho_g = (gam - 1.0) / gam;
-  out[BF_C_K] = C_K; out[BF_RHO_K] = rho_K; out[BF_GAMMA] = gam; out[BF_RHO_GAMMA] = rho_g;
-  // ---------------- ex_stability_bounds (utils.py:567-584)
-  const double L_V = dmax(gam, sc.M_V / eps_K);
-  const double N_0 = ceil(dmax(0.0, sc.M_V / eps_K - gam));
-  out[BF_L_V] = L_V; out[BF_N_0] = N_0;
-  // ---------------- fc_omega_eta (utils.py:469-523)
-  const double fA2 = fA * fA;
-  const double G_A = (fA == 1.0) ? (double)(N - 1) : (1.0 - pow(fA, 2.0 * (N - 1))) / (1.0 - fA2);
-  const double term = 1.0 + fA2 * ratioQ;
-  const double arg1 = fA2 * ratioQ * gam;
-  if (!(arg1 > 0.0) || !(rho_g > 0.0)) flags |= FLAG_DOMAIN_ERROR;   // math.log raises ValueError in the reference
-  const double N_min = ceil(N_0 - log(arg1) / log(rho_g));
-  const double fApow = pow(fA, (double)(2 * N - 2));
-  const double rg_pow = pow(rho_g, (double)N - N_0);
-  const double w1 = maxQ * (term * fApow + G_A);
-  const double decay = maxQ * fApow * gam * rg_pow;
-  const double w05_a = maxQ * (L_V - 1.0) * G_A;
-  if (w05_a < 0.0 || decay < 0.0) flags |= FLAG_DOMAIN_ERROR;        // math.sqrt domain error
-  const double w05 = sqrt(w05_a) + 0.5 * term * sqrt(decay);
-  const double eta = (term - 1.0) * gam * rg_pow;
-  const double disc = w05 * w05 + w1 * (1.0 - eta);
-  if (disc < 0.0) flags |= FLAG_DOMAIN_ERROR;
-  const double err_th_r = (sqrt(disc) - w05) / w1;
-  out[BF_OMEGA_N1] = w1; out[BF_OMEGA_N0D5] = w05; out[BF_ETA] = eta; out[BF_ERR_TH] = err_th_r * err_th_r;
-  out[BF_N_MIN] = N_min;
-  // ---------------- fc_ec_h and xi (utils.py:526-538, utils_class.py:371)
-  const double h = sc.e_A * sc.e_A / minQ + sc.e_B * sc.e_B / minR;
-  const double xi = h * w1 + 2.0 * sqrt(h) * w05;
-  out[BF_H] = h; out[BF_XI] = xi;
   // ---------------- G_d = A^d B, ||Phi||_2
+  double nPhi;
   {
     double Gd[n * m], Mt[n * n], acc[n * n];
     LQ_UNROLL for (int i = 0; i < n * m; ++i) Gd[i] = Bh[i];
@@ -393,7 +456,7 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     }
     double lo, hi;
     sym_eig_minmax<n>(acc, &lo, &hi);
-    out[BF_NORM_PHI] = sqrt(dmax(hi, 0.0));
+    nPhi = sqrt(dmax(hi, 0.0));
   }
   double cmin = 0.0, cmax = 0.0, min_H;
   if (matrix_free) {
@@ -457,42 +520,13 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
     ws_tridiag_extremes(ws, L.od, L.oe, k, &min_H, &hmax);
   }
   }
-  const double nG = sqrt(dmax(cmax, 0.0));
-  out[BF_NORM_GAMMA] = nG;
-  out[BF_MIN_H] = min_H;
-  // ---------------- error-consistent sums (utils.py:78-117, 186-223, 296-305)
-  double nx2 = 0.0;
-  LQ_UNROLL for (int i = 0; i < n; ++i) nx2 = fma(x[i], x[i], nx2);
-  const double nx = sqrt(nx2);
-  const double eAfA = sc.e_A + fA, eBfB = sc.e_B + fB;
-  double s_in = 0.0, s_out = 0.0, bgx = 0.0, bgu = 0.0, bgu_in = 0.0;
-  for (int i = 0; i <= N; ++i) {
-    const double fpi = pow(fA, (double)i);
-    const double gx1 = pow(eAfA, (double)i) - fpi;
-    const double gu1 = eBfB * gx1 + sc.e_B * fpi;
-    s_out += (s_in + gx1 * gx1) * (nx * nx + i * bu);
-    s_in += gu1 * gu1;
-    if (i >= 1) bgx += gx1;
-    if (i < N) { bgu_in += gu1; bgu += bgu_in; }
-  }
-  const double E_psi = maxQ * s_out;
-  const double theta_u = maxQ * (2.0 * nG * bgu + bgu * bgu);
-  const double theta_xu = maxQ * (nG * bgx + out[BF_NORM_PHI] * bgu + bgx * bgu);
-  const double bar_theta = sqrt(N * bu) * theta_u + nx * theta_xu;
-  const double cand = dmin(sqrt(N * bdu), bar_theta / min_H);
-  const double E_u = maxR * cand * cand;
-  const double E_psi_u = maxQ / maxR * (nG + bgu) * (nG + bgu) * E_u;
-  out[BF_E_PSI] = E_psi; out[BF_E_U] = E_u; out[BF_E_PSI_U] = E_psi_u;
-  out[BF_THETA_U] = theta_u; out[BF_THETA_X_U] = theta_xu;
-  // ---------------- alpha, beta (utils_class.py:329-340), J_bound (utils_class.py:858-859)
-  const double sp = sqrt(E_psi), su = sqrt(E_u), spu = sqrt(E_psi_u);
-  const double p0 = sc.p[0], p1 = sc.p[1], p2 = sc.p[2];
-  const double alpha = dmax(p0 * sp + p2 * spu + p0 * sp * p2 * spu, p1 * su);
-  const double beta = (1.0 + p0 * sp) * ((1.0 / p2) * spu + E_psi_u) + (1.0 / p1) * su + E_u + (1.0 / p0) * sp + E_psi;
-  out[BF_ALPHA] = alpha; out[BF_BETA] = beta;
-  const double den = 1.0 - xi - eta;
-  if (!(den > 0.0)) flags |= FLAG_BOUND_INVALID;
-  out[BF_BOUND] = (alpha * sc.V_expert + beta) / den;
+  // ---------------- scalar formulas (shared with the run-time-dimension route)
+  BoundsNorms q;
+  q.fA = fA; q.fB = fB; q.nK = nK; q.eps_K = eps_K; q.rho_cl = rho_cl; q.nPhi = nPhi; q.cmax = cmax; q.min_H = min_H;
+  q.bu = bu; q.bdu = bdu;
+  q.nx2 = 0.0;
+  LQ_UNROLL for (int i = 0; i < n; ++i) q.nx2 = fma(x[i], x[i], q.nx2);
+  flags |= bounds_formulas(maxQ, minQ, maxR, minR, sc, q, out);
   LQ_UNROLL for (int i = 0; i < BF_COUNT; ++i)
     if (!(fabs(out[i]) <= 1.79e308)) flags |= FLAG_NONFINITE;
   return flags;

@@ -132,6 +132,7 @@ void lqmpc_destroy(lqmpc_ctx* ctx) {
   cudaStreamSynchronize(ctx->stream);
   if (ctx->ws) cudaFree(ctx->ws);
   if (ctx->seed_buf) cudaFree(ctx->seed_buf);
+  if (ctx->dyn_dev) cudaFree(ctx->dyn_dev);
   if (ctx->pb_dev) cudaFree(ctx->pb_dev);
   if (ctx->ref_x) cudaFree(ctx->ref_x);
   if (ctx->ref_u) cudaFree(ctx->ref_u);
@@ -171,7 +172,13 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   }
   LQ_FOR_EACH_DIM(X)
 #undef X
-  if (!found) return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m); see lqmpc_supported_dims()");
+  ctx->dyn = false;
+  if (!found) {
+    // no register-resident instantiation: the run-time-dimension route (one warp per sample, k_dyn.cu)
+    if (!lq_dyn_supported(n, m))
+      return lq_set_error(ctx, LQMPC_EINVAL, "unsupported (n, m): n <= 32 and m <= 8 are required");
+    ctx->dyn = true;
+  }
   if (ctx->ref_x) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_x); ctx->ref_x = nullptr; }
   if (ctx->ref_u) { cudaStreamSynchronize(ctx->stream); cudaFree(ctx->ref_u); ctx->ref_u = nullptr; }
   ctx->ref_ld = 0;
@@ -181,7 +188,7 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   ctx->m = m;
   ctx->N_opc = N_opc;
   ctx->has_problem = false;
-  int rc = lq_launch_prepare(ctx);
+  int rc = ctx->dyn ? lq_dyn_set_problem(ctx, A, B, Q, R, P, lo, hi) : lq_launch_prepare(ctx);
   if (rc) return rc;
   ctx->has_problem = true;
   return LQMPC_OK;
@@ -335,6 +342,7 @@ int lqmpc_get_prepared(lqmpc_ctx* ctx, double* out, int64_t capacity) {
   if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
   const int n = ctx->n;
   if (capacity < 2 * n * n + 4) return lq_set_error(ctx, LQMPC_EINVAL, "capacity too small");
+  if (ctx->dyn) return lq_dyn_get_prepared(ctx, out);
   bool done = false;
 #define X(N_, M_)                                                                       \
   if (!done && ctx->n == N_ && ctx->m == M_) {                                          \
@@ -366,7 +374,7 @@ int lqmpc_eval_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* 
   a.S = S; a.ld = S; a.dA = dA; a.dB = dB; a.x0 = x0;
   a.N_min = N_min; a.N_max = N_max; a.T = J_T ? T : 0;
   a.J = J; a.rho = rho; a.ratio = ratio; a.Vn = V_N; a.JT = J_T; a.flags = flags; a.K0 = K0;
-  return lq_launch_eval(ctx, a, ctx->stream);
+  return ctx->dyn ? lq_dyn_eval(ctx, a, ctx->stream) : lq_launch_eval(ctx, a, ctx->stream);
 }
 
 int lqmpc_eval_seeded(lqmpc_ctx* ctx, uint64_t seed, int64_t first, int64_t S, double e_A, double e_B, int N_min,
@@ -374,6 +382,7 @@ int lqmpc_eval_seeded(lqmpc_ctx* ctx, uint64_t seed, int64_t first, int64_t S, d
   if (!ctx) return LQMPC_EINVAL;
   if (!ctx->has_problem) return lq_set_error(ctx, LQMPC_ESTATE, "problem not set");
   if (S < 0 || first < 0 || N_min < 1 || N_max < N_min) return lq_set_error(ctx, LQMPC_EINVAL, "bad S/first/N_min/N_max");
+  if (ctx->dyn) return lq_set_error(ctx, LQMPC_EINVAL, "lqmpc_eval_seeded needs a compiled (n, m) pair; see lqmpc_supported_dims()");
   if (S == 0) return LQMPC_OK;
   cudaSetDevice(ctx->device);
   const int H = N_max - N_min + 1;
@@ -460,7 +469,7 @@ int lqmpc_eval_batch_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, const d
     a.N_min = N_min; a.N_max = N_max; a.T = 0;
     a.J = J_h ? d_J : nullptr; a.rho = rho_h ? d_rho : nullptr; a.ratio = ratio_h ? d_ratio : nullptr;
     a.Vn = nullptr; a.JT = nullptr; a.flags = flags_h ? d_flags : nullptr; a.K0 = nullptr;
-    rc = lq_launch_eval(ctx, a, st);
+    rc = ctx->dyn ? lq_dyn_eval(ctx, a, st) : lq_launch_eval(ctx, a, st);
     if (rc) return pipe_abort(ctx, rc);
     if (J_h) {
       rc = lq_check_cuda(ctx, cudaMemcpy2DAsync(J_h + s0, sp, d_J, dp, w, (size_t)H, cudaMemcpyDeviceToHost, st),
@@ -526,6 +535,8 @@ int lqmpc_set_input_polytope(lqmpc_ctx* ctx, int p, const double* F_host) {
   // validate first: a rejected call leaves the installed polytope (or the box) as it was
   const bool clear = (p <= 0 || !F_host);
   if (!clear) {
+    if (ctx->dyn)
+      return lq_set_error(ctx, LQMPC_EINVAL, "general input polytopes need a compiled (n, m) pair; see lqmpc_supported_dims()");
     if (p > lq::kPolyMaxRows) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: at most 12 rows");
     for (int e = 0; e < p * ctx->m; ++e)
       if (!(fabs(F_host[e]) <= 1.79e308)) return lq_set_error(ctx, LQMPC_EINVAL, "input polytope: non-finite entry");
@@ -556,7 +567,7 @@ int lqmpc_mpc_solve_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const dou
   MpcArgs a{};
   a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.T = 0; a.npts = npts; a.pts = pts; a.x0 = x0;
   a.V = V; a.u0 = u0; a.M_V = M_V; a.flags = flags;
-  return lq_launch_mpc(ctx, a, false);
+  return ctx->dyn ? lq_dyn_mpc(ctx, a, false) : lq_launch_mpc(ctx, a, false);
 }
 
 int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, int N, int T,
@@ -572,7 +583,7 @@ int lqmpc_simulate_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const doub
   MpcArgs a{};
   a.S = S; a.dA = dA; a.dB = dB; a.N = N; a.T = T; a.npts = 1; a.pts = x0_shared; a.x0 = x0;
   a.J_T = J_T; a.X = X; a.U = U; a.flags = flags; a.n_active = n_active;
-  return lq_launch_mpc(ctx, a, true);
+  return ctx->dyn ? lq_dyn_mpc(ctx, a, true) : lq_launch_mpc(ctx, a, true);
 }
 
 int lqmpc_bounds_fields(void) { return (int)lq::BF_COUNT; }
@@ -603,7 +614,7 @@ int lqmpc_bounds_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double
       return lq_set_error(ctx, LQMPC_EINVAL, "with an input polytope installed bar_u / bar_d_u must be supplied (>= 0)");
     a.polyF = ctx->poly_dev; a.polyP = ctx->poly_p;
   }
-  return lq_launch_bounds(ctx, a);
+  return ctx->dyn ? lq_dyn_bounds(ctx, a) : lq_launch_bounds(ctx, a);
 }
 
 int lqmpc_dlqr_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K_out, double* P_out,
@@ -613,7 +624,8 @@ int lqmpc_dlqr_batch(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* 
   if (S < 0) return lq_set_error(ctx, LQMPC_EINVAL, "bad S");
   if (S == 0) return LQMPC_OK;
   cudaSetDevice(ctx->device);
-  return lq_launch_dlqr(ctx, S, dA, dB, K_out, P_out, flags);
+  return ctx->dyn ? lq_dyn_dlqr(ctx, S, dA, dB, K_out, P_out, flags)
+                  : lq_launch_dlqr(ctx, S, dA, dB, K_out, P_out, flags);
 }
 
 int lqmpc_column_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* stats) {

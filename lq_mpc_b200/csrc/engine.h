@@ -4,6 +4,7 @@
 #include <stdint.h>
 
 #include <string>
+#include <vector>
 
 #include "../../include/lqmpc_b200.h"
 #include "riccati.cuh"
@@ -27,6 +28,10 @@ struct lqmpc_ctx {
   void* pb_dev = nullptr;
   std::string err;
   int64_t launches = 0;
+  // run-time-dimension route (k_dyn.cu): (n, m) without a register-resident instantiation
+  bool dyn = false;
+  void* dyn_dev = nullptr;              // device problem buffer (layout: k_dyn.cu DynLayout)
+  std::vector<double> dyn_host;         // host mirror after the device preparation
   // tiled (large-n) problem: device doubles A | B | Q | R | Pt | Pexp, see k_tiled.cu
   int tn = 0, tm = 0;
   bool has_tiled = false;
@@ -153,6 +158,14 @@ int lq_launch_stats(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, in
 int lq_launch_moments(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, double* out);
 int lq_launch_sqdev(lqmpc_ctx* ctx, const double* table, int cols, int64_t S, int64_t ld, const double* mean,
                     double* out);
+bool lq_dyn_supported(int n, int m);
+int lq_dyn_set_problem(lqmpc_ctx* ctx, const double* A, const double* B, const double* Q, const double* R,
+                       const double* P, const double* lo, const double* hi);
+int lq_dyn_get_prepared(lqmpc_ctx* ctx, double* out);
+int lq_dyn_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
+int lq_dyn_mpc(lqmpc_ctx* ctx, MpcArgs a, bool simulate);
+int lq_dyn_bounds(lqmpc_ctx* ctx, const BoundsArgs& a);
+int lq_dyn_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, double* K, double* P, int32_t* flags);
 bool lq_tiled_supported(int n, int m);
 size_t lq_tiled_pb_doubles(int n, int m);
 int lq_launch_tiled(lqmpc_ctx* ctx, const TiledEval& t);

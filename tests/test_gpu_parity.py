@@ -1016,10 +1016,190 @@ def test_errors_are_loud(engine):
     from lq_mpc_b200.engine import EngineError
     from lq_mpc_b200.utils_class import LQ_MPC_Controller
     with pytest.raises(EngineError):
-        engine.set_problem(np.eye(5), np.ones((5, 1)), np.eye(5), np.eye(1))        # (5,1) is not compiled
+        engine.set_problem(np.eye(33), np.ones((33, 1)), np.eye(33), np.eye(1))     # n > 32: no route at all
+    with pytest.raises(EngineError):
+        engine.set_problem(np.eye(5), np.ones((5, 9)), np.eye(5), np.eye(9))        # m > 8
+    engine.set_problem(np.eye(5), np.ones((5, 1)), np.eye(5), np.eye(1))            # run-time-dimension route
+    with pytest.raises(EngineError):
+        engine.set_input_polytope(np.array([[1.0], [-1.0], [0.5]]))                 # polytopes need a compiled pair
+    with pytest.raises(EngineError):
+        engine.eval_seeded(1, 0, 10, 0.01, 0.01, 3, 3)                              # so does the seeded entry point
     with pytest.raises(EngineError):
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
                           np.array([[1.0, 1.0]])).solve(np.ones(2), None, None)     # F_u with 2 columns, B with 1
     with pytest.raises(EngineError):                                                  # reference window shorter than N
         LQ_MPC_Controller(3, np.eye(2), np.ones((2, 1)), np.eye(2), np.eye(1), np.eye(2),
                           np.array([[10.0], [-10.0]])).solve(np.ones(2), np.ones((2, 2)), np.zeros((1, 2)))
+
+
+# ------------------------------------------------------------------------------- run-time-dimension route (any n, m)
+DYN_DIMS = [(5, 1), (5, 2), (7, 3), (9, 2), (12, 4), (16, 4), (24, 6), (32, 8), (6, 4), (8, 4)]
+
+
+@pytest.mark.parametrize("n,m", DYN_DIMS)
+def test_dyn_k1_matches_oracle(engine, n, m):
+    """(n, m) pairs WITHOUT a register-resident instantiation go through the warp-per-sample route (csrc/dyn.cuh,
+    k_dyn.cu): LQ_MPC_Controller / LQ_RDP_Calculator take any (n, m) (utils_class.py:23-46, 293-306). K1 vs the
+    batched oracle: nested horizons, gains, V_N, finite-T cost, flags; at n = 32, m = 8 also vs the tiled kernel (K4)."""
+    from oracle import np_batched as nb
+    assert (n, m) not in engine.supported_dims()
+    A, B, Q, R = nb.synth_problem(n, m, seed=0)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    S = 203
+    e = 0.02 if n <= 16 else 2e-3
+    dA, dB, x0 = nb.synth_samples(n, m, S, seed=1, e=e)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    assert relerr(engine.prepared()["Pexp"], Pexp) < 1e-11
+    N1 = 9 if n <= 16 else 5
+    ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, N1 - 2, N1, T=12, want_K=True)
+    got = engine.eval_batch(*_soa(dA, dB, x0), N1 - 2, N1, T=12, want=("J", "rho", "ratio", "flags", "V_N", "J_T", "K0"))
+    g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
+    assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"]) and not np.any(g["flags"] & ~1)
+    for k, kr in (("rho", "rho"), ("V_N", "Vn"), ("J_T", "JT"), ("J", "J"), ("ratio", "ratio")):
+        assert relerr(g[k], ref[kr]) < TOL, k
+    K = g["K0"].reshape(3, m, n, S).transpose(0, 3, 1, 2)
+    assert np.max(np.abs(K - ref["K0"])) < 1e-10 * max(1.0, np.max(np.abs(ref["K0"])))
+    if (n, m) == (32, 8):
+        engine.set_problem_tiled(A, B, Q, R, Q, 30)
+        t = engine.eval_batch_tiled(dA, dB, x0, N1, N1)
+        assert relerr(t["J"].cpu().numpy()[0], g["J"][2]) < TOL and relerr(t["rho"].cpu().numpy()[0], g["rho"][2]) < TOL
+    # host-buffer pipeline on the same route
+    import torch
+    h = [torch.from_numpy(a).pin_memory() for a in _soa(dA, dB, x0)]
+    hp = engine.eval_batch_host(h[0], h[1], h[2], N1, N1, chunk=64)
+    assert np.array_equal(hp["J"].numpy()[0], g["J"][2]) and np.array_equal(hp["flags"].numpy()[0], g["flags"][2])
+
+
+@pytest.mark.parametrize("n,m", [(5, 1), (5, 2), (7, 3), (12, 4), (16, 4), (32, 8)])
+def test_dyn_k2_box_qp_vs_dense_oracle(engine, n, m):
+    """Exact input-box QP and closed loop on the run-time-dimension route vs the dense Cholesky + BVLS oracle; includes
+    BASELINE cfg 5's shape (n = 32, m = 8) with the box active, which round 1 could not evaluate."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(100 + n)
+    N = 6 if n <= 16 else 4
+    A = rng.normal(size=(n, n)); A *= 1.05 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+    Q, R = np.eye(n), 0.5 * np.eye(m)
+    lo, hi = -0.3 * np.ones(m), 0.25 * np.ones(m)
+    engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+    S = 40
+    x0 = rng.normal(size=(n, S)) * 0.6
+    dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
+    got = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+    V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
+    assert not np.any(fl & ~2)
+    n_act = 0
+    for s in range(0, S, 3):
+        Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+        ur, Vr, act = o.mpc_solve(N, Ah, Bh, Q, R, Q, lo, hi, x0[:, s])
+        n_act += int(act)
+        assert abs(V[0, s] - Vr) < TOL * abs(Vr) and np.max(np.abs(u0[0, :, s] - ur)) < 1e-9, (n, m, s)
+        assert bool(fl[0, s] & 2) == act
+    assert n_act > 3
+    ring = rng.normal(size=(4, n)) * 0.5
+    mv = engine.mpc_solve_batch(dA, dB, N, pts=ring)
+    Vp = mv["V"].cpu().numpy()
+    assert np.array_equal(mv["M_V"].cpu().numpy(), Vp.max(axis=0))
+    s = 1
+    for p in range(4):
+        Vr = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi, ring[p])[1]
+        assert abs(Vp[p, s] - Vr) < TOL * abs(Vr)
+    T = 6
+    sim = engine.simulate_batch(dA, dB, N, T, x0=x0, want=("J_T", "X", "U", "flags", "n_active"))
+    for s in range(0, S, 13):
+        so = o.simulate(T, N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi, x0[:, s], A, B)
+        assert abs(float(sim["J_T"][s]) - so["J_T"]) < TOL * so["J_T"]
+        assert np.max(np.abs(sim["U"].cpu().numpy()[:, :, s].T - so["U"])) < 1e-9
+        assert np.max(np.abs(sim["X"].cpu().numpy()[:, :, s].T - so["X"])) < 1e-9
+        assert int(sim["n_active"][s]) == so["n_active"]
+    if n == 5:                                                       # non-zero references on this route as well
+        xr, ur = rng.normal(size=(n, N)) * 0.2, rng.normal(size=(m, N)) * 0.1
+        with engine.references(xr, ur):
+            trk = engine.mpc_solve_batch(dA, dB, N, x0=x0)
+        for s in range(0, S, 7):
+            u_o, V_o, _ = o.mpc_solve(N, A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m), Q, R, Q, lo, hi,
+                                      x0[:, s], x_ref=xr, u_ref=ur)
+            assert abs(float(trk["V"][0, s]) - V_o) < TOL * abs(V_o)
+            assert np.max(np.abs(trk["u0"].cpu().numpy()[0, :, s] - u_o)) < 1e-9
+
+
+@pytest.mark.parametrize("n,m", [(5, 1), (5, 2), (7, 3), (12, 4), (16, 4), (32, 8)])
+def test_dyn_k3_bounds_and_dlqr_vs_oracle(engine, n, m):
+    """dlqr (DARE by doubling), norms, matrix-free Gram spectrum and the bound formulas on the run-time-dimension route
+    vs the per-sample oracle — energy_bound / energy_decreasing at n = 16 and n = 32 (BASELINE cfg 5's shape)."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(200 + n)
+    N = 7 if n <= 16 else 5
+    A = rng.normal(size=(n, n)); A *= 0.5 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+    Q, R = 2.0 * np.eye(n), np.eye(m)
+    lo, hi = -0.2 * np.ones(m), 0.3 * np.ones(m)
+    engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+    pr = engine.prepared()
+    assert relerr(pr["Qinv"], np.linalg.inv(Q)) < 1e-12 and abs(pr["maxQ"] - 2.0) < 1e-12 and abs(pr["minR"] - 1.0) < 1e-12
+    S = 7
+    dA = rng.uniform(-0.005, 0.005, size=(n * n, S)); dB = rng.uniform(-0.005, 0.005, size=(n * m, S))
+    d = engine.dlqr_batch(dA, dB)
+    e = rng.uniform(1e-4, 5e-3, size=S); MV = rng.uniform(0.05, 1.0, size=S)
+    x = rng.normal(size=(n, S)) * 0.2
+    p = np.array([0.1, 1, 0.6])
+    got = engine.bounds_batch(dA, dB, N, e, e, MV, x, p, 0.37, want_K=True, want_P=True)
+    g = {k: v.cpu().numpy() for k, v in got.items()}
+    for s in range(S):
+        Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+        K, P = o.dlqr(Ah, Bh, Q, R)
+        assert np.max(np.abs(d["K"].cpu().numpy()[:, s].reshape(m, n) - K)) < 1e-9 * max(1, np.max(np.abs(K)))
+        assert relerr(d["P"].cpu().numpy()[:, s].reshape(n, n), P) < 1e-9
+        assert np.max(np.abs(g["K"][:, s].reshape(m, n) + K)) < 1e-9 * max(1, np.max(np.abs(K)))
+        bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, e[s], e[s], x[:, s], p)
+        for f in ("alpha", "beta", "E_psi", "E_u", "E_psi_u", "min_H", "norm_Gamma", "theta_u", "theta_x_u"):
+            assert abs(g[f][s] - bnd[f]) <= TOL * abs(bnd[f]), (n, m, f)
+        try:
+            dec = o.energy_decreasing(Ah, Bh, Q, R, lo, hi, N, e[s], e[s], -K, MV[s])
+        except ValueError:
+            assert g["flags"][s] & 512
+            continue
+        for f in ("xi", "eta", "C_K", "rho_K", "gamma", "rho_gamma", "L_V", "N_0", "omega_N1", "omega_N0d5",
+                  "err_th", "N_min", "h", "epsilon_K"):
+            assert abs(g[f][s] - dec[f]) <= TOL * abs(dec[f]), (n, m, f)
+    # general (non-scalar) weights in the time-major convention, and a supplied shared gain
+    Mq, Mr = rng.normal(size=(n, n)), rng.normal(size=(m, m))
+    Q2, R2 = Mq @ Mq.T / n + np.eye(n), Mr @ Mr.T / m + np.eye(m)
+    engine.set_problem(A, B, Q2, R2, Q2, lo, hi, 10)
+    Ksh = -o.dlqr(A, B, Q2, R2)[0]
+    g2 = engine.bounds_batch(dA, dB, N, 1e-3, 1e-3, 0.3, x[:, 0], p, 0.2, K=Ksh, strict_reference=False)
+    for s in range(0, S, 3):
+        Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
+        bnd = o.energy_bound(Ah, Bh, Q2, R2, lo, hi, N, 1e-3, 1e-3, x[:, 0], p, strict_reference=False)
+        for f in ("alpha", "beta", "min_H", "norm_Gamma"):
+            assert abs(float(g2[f][s]) - bnd[f]) <= TOL * abs(bnd[f]), (n, m, f)
+
+
+def test_dyn_dropin_classes_with_five_states():
+    """The drop-in classes on a 5-state, 2-input plant (no compiled pair): solve / simulate / energy_bound vs the oracle."""
+    from oracle import np_oracle as o
+    from lq_mpc_b200.control import dlqr
+    from lq_mpc_b200.utils_class import LQ_MPC_Controller, LQ_MPC_Simulator, LQ_RDP_Calculator
+    rng = np.random.default_rng(3)
+    n, m, N, T = 5, 2, 6, 8
+    A = rng.normal(size=(n, n)); A *= 0.6 / np.max(np.abs(np.linalg.eigvals(A))); B = rng.normal(size=(n, m))
+    Q, R = 1.5 * np.eye(n), np.eye(m)
+    ub = 0.2
+    F_u = np.vstack((np.eye(m) / ub, -np.eye(m) / ub))
+    lo, hi = -ub * np.ones(m), ub * np.ones(m)
+    x0 = rng.normal(size=n) * 0.8
+    sol = LQ_MPC_Controller(N, A, B, Q, R, Q, F_u).solve(x0, np.zeros((n, N)), np.zeros((m, N)))
+    ur, Vr, act = o.mpc_solve(N, A, B, Q, R, Q, lo, hi, x0)
+    assert act and abs(sol["V_N"] - Vr) < TOL * Vr and np.max(np.abs(sol["u_0"] - ur)) < 1e-9
+    At = A + rng.uniform(-0.01, 0.01, size=(n, n))
+    sim = LQ_MPC_Simulator(T, N, A, B, Q, R, Q, F_u).simulate(x0, At, B, np.zeros((n, N)), np.zeros((m, N)))
+    so = o.simulate(T, N, A, B, Q, R, Q, lo, hi, x0, At, B)
+    assert abs(sim["J_T"] - so["J_T"]) < TOL * so["J_T"] and np.max(np.abs(sim["U"] - so["U"])) < 1e-9
+    K, P, _ = dlqr(A, B, Q, R)
+    Ko, Po = o.dlqr(A, B, Q, R)
+    assert relerr(K, Ko) < 1e-9 and relerr(P, Po) < 1e-9
+    calc = LQ_RDP_Calculator(A, B, Q, R, F_u)
+    bnd = calc.energy_bound(N, 5e-3, 5e-3, x0, np.array([0.1, 1, 0.6]))
+    bo = o.energy_bound(A, B, Q, R, lo, hi, N, 5e-3, 5e-3, x0, (0.1, 1, 0.6))
+    assert abs(bnd["alpha"] - bo["alpha"]) < TOL * bo["alpha"] and abs(bnd["beta"] - bo["beta"]) < TOL * bo["beta"]
+    dec = calc.energy_decreasing(N, 5e-3, 5e-3, -K, 0.4)
+    do = o.energy_decreasing(A, B, Q, R, lo, hi, N, 5e-3, 5e-3, -Ko, 0.4)
+    assert abs(dec["xi"] - do["xi"]) < TOL * do["xi"] and abs(dec["eta"] - do["eta"]) < TOL * abs(do["eta"])
