@@ -12,7 +12,7 @@ using lqd::DynPb;
 using lqd::QpWs;
 using namespace lqd;
 
-constexpr int kWarpsPerCta = 4;
+constexpr int kMaxWarpsPerCta = 4;   // the launcher picks 4, 2 or 1 warps per CTA by the size of the per-warp arena
 
 // device problem buffer (doubles): A | B | Q | R | Pt | Pexp | Qinv | ulo | uhi | maxQ minQ maxR minR has_bounds qr_scalar
 struct DynLayout {
@@ -116,12 +116,13 @@ __global__ void __launch_bounds__(32) dyn_prepare_kernel(double* buf, int n, int
 }
 
 // ---------------------------------------------------------------------------------------------------- K1
-__global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_eval_kernel(const DynPb pb, const EvalArgs a) {
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32) dyn_eval_kernel(const DynPb pb, const EvalArgs a) {
   const int lane = threadIdx.x & 31, n = pb.n, m = pb.m;
   Arena ar;
   ar.carve(warp_arena(7, n, m), n, m, 7);
-  const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t s = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); s < a.S; s += nw) {
+  const int wpc = blockDim.x >> 5;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+  for (int64_t s = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); s < a.S; s += nw) {
     load_model(lane, ar, pb, a.dA, a.dB, a.ld, s);
     for (int i = lane; i < n; i += 32) ar.x[i] = a.x0[(int64_t)i * a.ld + s];
     lqd::wcopy(lane, n, n, pb.Pt, n, ar.big[1], ar.ld);
@@ -153,11 +154,12 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_eval_kernel(const DynPb
 }
 
 // ---------------------------------------------------------------------------------------------------- K2
-__global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_mpc_kernel(const DynPb pb, const MpcArgs a, const int simulate) {
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32) dyn_mpc_kernel(const DynPb pb, const MpcArgs a, const int simulate) {
   const int lane = threadIdx.x & 31, n = pb.n, m = pb.m;
   Arena ar;
   ar.carve(warp_arena(6, n, m), n, m, 6);
-  const int64_t wid = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * kWarpsPerCta;
+  const int wpc = blockDim.x >> 5;
+  const int64_t wid = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5), nw = (int64_t)gridDim.x * wpc;
   QpWs ws;
   ws.carve(a.ws + (size_t)wid * QpWs::doubles(n, m, a.N), n, m, a.N);
   lq::Refs rf;
@@ -220,14 +222,15 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_mpc_kernel(const DynPb 
 }
 
 // ---------------------------------------------------------------------------------------------------- K3 / dlqr
-__global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_bounds_kernel(const DynPb pb, const BoundsArgs a,
+__global__ void __launch_bounds__(kMaxWarpsPerCta * 32) dyn_bounds_kernel(const DynPb pb, const BoundsArgs a,
                                                                        const int dlqr_only, double* K_dlqr,
                                                                        double* P_dlqr, int32_t* f_dlqr, int64_t S) {
   const int lane = threadIdx.x & 31, n = pb.n, m = pb.m;
   Arena ar;
   ar.carve(warp_arena(8, n, m), n, m, 8);
-  const int64_t nw = (int64_t)gridDim.x * kWarpsPerCta;
-  for (int64_t s = (int64_t)blockIdx.x * kWarpsPerCta + (threadIdx.x >> 5); s < S; s += nw) {
+  const int wpc = blockDim.x >> 5;
+  const int64_t nw = (int64_t)gridDim.x * wpc;
+  for (int64_t s = (int64_t)blockIdx.x * wpc + (threadIdx.x >> 5); s < S; s += nw) {
     load_model(lane, ar, pb, a.dA, a.dB, S, s);
     int flags = 0;
     const bool own_gain = dlqr_only || (!a.K_in && !a.K_shared);
@@ -278,18 +281,26 @@ __global__ void __launch_bounds__(kWarpsPerCta * 32) dyn_bounds_kernel(const Dyn
   }
 }
 
-int grid_for(lqmpc_ctx* ctx, const void* kern, size_t smem, int64_t S, int* blocks_out) {
+// CTA shape and grid of a warp-per-sample kernel whose per-warp arena takes `per_warp` bytes of shared memory: the most
+// warps per CTA (4, 2, 1) that fit, then as many CTAs as the SMs hold.
+int grid_for(lqmpc_ctx* ctx, const void* kern, size_t per_warp, int64_t S, int* blocks_out, int* warps_out) {
   int sms = 148;
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
+  int w = kMaxWarpsPerCta;
+  while (w > 1 && (size_t)w * per_warp > (size_t)200 * 1024) w >>= 1;
+  const size_t smem = (size_t)w * per_warp;
+  if (smem > (size_t)220 * 1024)
+    return lq_set_error(ctx, LQMPC_EINVAL, "run-time-dimension route: shared memory arena does not fit");
   cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int per_sm = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kWarpsPerCta * 32, smem);
-  if (per_sm < 1) return lq_set_error(ctx, LQMPC_EINVAL, "run-time-dimension route: shared memory arena does not fit");
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, w * 32, smem);
+  if (per_sm < 1) return lq_set_error(ctx, LQMPC_EINVAL, "run-time-dimension route: kernel does not fit an SM");
   int64_t blocks = (int64_t)sms * per_sm;
-  const int64_t want = (S + kWarpsPerCta - 1) / kWarpsPerCta;
+  const int64_t want = (S + w - 1) / w;
   if (blocks > want) blocks = want;
   if (blocks < 1) blocks = 1;
   *blocks_out = (int)blocks;
+  *warps_out = w;
   return LQMPC_OK;
 }
 
@@ -347,11 +358,11 @@ int lq_dyn_get_prepared(lqmpc_ctx* ctx, double* out) {
 
 int lq_dyn_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
   const DynPb pb = make_pb(ctx);
-  const size_t smem = kWarpsPerCta * Arena::doubles(pb.n, pb.m, 7) * sizeof(double);
-  int blocks;
-  int rc = grid_for(ctx, (const void*)dyn_eval_kernel, smem, a.S, &blocks);
+  const size_t per = Arena::doubles(pb.n, pb.m, 7) * sizeof(double);
+  int blocks, w;
+  int rc = grid_for(ctx, (const void*)dyn_eval_kernel, per, a.S, &blocks, &w);
   if (rc) return rc;
-  dyn_eval_kernel<<<blocks, kWarpsPerCta * 32, smem, stream>>>(pb, a);
+  dyn_eval_kernel<<<blocks, w * 32, w * per, stream>>>(pb, a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "dyn_eval_kernel launch");
 }
@@ -360,17 +371,17 @@ int lq_dyn_mpc(lqmpc_ctx* ctx, MpcArgs a, bool sim) {
   if (ctx->poly_p > 0)
     return lq_set_error(ctx, LQMPC_EINVAL, "general input polytopes need a compiled (n, m) pair; see lqmpc_supported_dims()");
   const DynPb pb = make_pb(ctx);
-  const size_t smem = kWarpsPerCta * Arena::doubles(pb.n, pb.m, 6) * sizeof(double);
-  int blocks;
-  int rc = grid_for(ctx, (const void*)dyn_mpc_kernel, smem, a.S, &blocks);
+  const size_t per_arena = Arena::doubles(pb.n, pb.m, 6) * sizeof(double);
+  int blocks, w;
+  int rc = grid_for(ctx, (const void*)dyn_mpc_kernel, per_arena, a.S, &blocks, &w);
   if (rc) return rc;
   const size_t per = QpWs::doubles(pb.n, pb.m, a.N);
-  rc = lq_reserve_ws(ctx, per * (size_t)blocks * kWarpsPerCta * sizeof(double));
+  rc = lq_reserve_ws(ctx, per * (size_t)blocks * w * sizeof(double));
   if (rc) return rc;
   a.ws = reinterpret_cast<double*>(ctx->ws);
   if (ctx->ref_ld >= a.N) { a.xr = ctx->ref_x; a.ur = ctx->ref_u; a.ref_ld = ctx->ref_ld; }
   else if (ctx->ref_ld > 0) return lq_set_error(ctx, LQMPC_EINVAL, "references hold fewer than N columns");
-  dyn_mpc_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(pb, a, sim ? 1 : 0);
+  dyn_mpc_kernel<<<blocks, w * 32, w * per_arena, ctx->stream>>>(pb, a, sim ? 1 : 0);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "dyn_mpc_kernel launch");
 }
@@ -382,11 +393,11 @@ int lq_dyn_bounds(lqmpc_ctx* ctx, const BoundsArgs& a) {
                                            "(pass strict_reference = 0 for the time-major weights)");
   if (a.polyP > 0)
     return lq_set_error(ctx, LQMPC_EINVAL, "general input polytopes need a compiled (n, m) pair");
-  const size_t smem = kWarpsPerCta * Arena::doubles(pb.n, pb.m, 8) * sizeof(double);
-  int blocks;
-  int rc = grid_for(ctx, (const void*)dyn_bounds_kernel, smem, a.S, &blocks);
+  const size_t per = Arena::doubles(pb.n, pb.m, 8) * sizeof(double);
+  int blocks, w;
+  int rc = grid_for(ctx, (const void*)dyn_bounds_kernel, per, a.S, &blocks, &w);
   if (rc) return rc;
-  dyn_bounds_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(pb, a, 0, nullptr, nullptr, nullptr, a.S);
+  dyn_bounds_kernel<<<blocks, w * 32, w * per, ctx->stream>>>(pb, a, 0, nullptr, nullptr, nullptr, a.S);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "dyn_bounds_kernel launch");
 }
@@ -395,11 +406,11 @@ int lq_dyn_dlqr(lqmpc_ctx* ctx, int64_t S, const double* dA, const double* dB, d
   const DynPb pb = make_pb(ctx);
   BoundsArgs a{};
   a.S = S; a.dA = dA; a.dB = dB;
-  const size_t smem = kWarpsPerCta * Arena::doubles(pb.n, pb.m, 8) * sizeof(double);
-  int blocks;
-  int rc = grid_for(ctx, (const void*)dyn_bounds_kernel, smem, S, &blocks);
+  const size_t per = Arena::doubles(pb.n, pb.m, 8) * sizeof(double);
+  int blocks, w;
+  int rc = grid_for(ctx, (const void*)dyn_bounds_kernel, per, S, &blocks, &w);
   if (rc) return rc;
-  dyn_bounds_kernel<<<blocks, kWarpsPerCta * 32, smem, ctx->stream>>>(pb, a, 1, K, P, flags, S);
+  dyn_bounds_kernel<<<blocks, w * 32, w * per, ctx->stream>>>(pb, a, 1, K, P, flags, S);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "dyn_bounds_kernel (dlqr) launch");
 }
