@@ -1082,7 +1082,7 @@ def test_dyn_k2_box_qp_vs_dense_oracle(engine, n, m):
     lo, hi = -0.3 * np.ones(m), 0.25 * np.ones(m)
     engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
     S = 40
-    x0 = rng.normal(size=(n, S)) * 0.6
+    x0 = rng.normal(size=(n, S)) * (0.6 if n <= 16 else 1.5)
     dA = rng.uniform(-0.01, 0.01, size=(n * n, S)); dB = rng.uniform(-0.01, 0.01, size=(n * m, S))
     got = engine.mpc_solve_batch(dA, dB, N, x0=x0)
     V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
@@ -1147,7 +1147,7 @@ def test_dyn_k3_bounds_and_dlqr_vs_oracle(engine, n, m):
         Ah, Bh = A + dA[:, s].reshape(n, n), B + dB[:, s].reshape(n, m)
         K, P = o.dlqr(Ah, Bh, Q, R)
         assert np.max(np.abs(d["K"].cpu().numpy()[:, s].reshape(m, n) - K)) < 1e-9 * max(1, np.max(np.abs(K)))
-        assert relerr(d["P"].cpu().numpy()[:, s].reshape(n, n), P) < 1e-9
+        assert np.max(np.abs(d["P"].cpu().numpy()[:, s].reshape(n, n) - P)) < 1e-9 * np.max(np.abs(P))     # normwise
         assert np.max(np.abs(g["K"][:, s].reshape(m, n) + K)) < 1e-9 * max(1, np.max(np.abs(K)))
         bnd = o.energy_bound(Ah, Bh, Q, R, lo, hi, N, e[s], e[s], x[:, s], p)
         for f in ("alpha", "beta", "E_psi", "E_u", "E_psi_u", "min_H", "norm_Gamma", "theta_u", "theta_x_u"):
