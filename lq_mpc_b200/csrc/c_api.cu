@@ -1,5 +1,6 @@
 // c_api.cu — the extern "C" boundary declared in include/lqmpc_b200.h.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <new>
@@ -173,6 +174,7 @@ int lqmpc_set_problem(lqmpc_ctx* ctx, int n, int m, const double* A, const doubl
   LQ_FOR_EACH_DIM(X)
 #undef X
   ctx->dyn = false;
+  if (found && getenv("LQMPC_FORCE_DYN") != nullptr && lq_dyn_supported(n, m)) found = false;   // A/B measurements
   if (!found) {
     // no register-resident instantiation: the run-time-dimension route (one warp per sample, k_dyn.cu)
     if (!lq_dyn_supported(n, m))
