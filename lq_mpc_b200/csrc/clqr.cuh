@@ -53,12 +53,28 @@ struct Mask128 {   // (name kept from the 128-bit first version)
   }
   LQ_HD void set(int b) { put(b, true); }
   LQ_HD void clear(int b) { put(b, false); }
+  LQ_HD static int top64(uint64_t w) {
+#if defined(__CUDA_ARCH__)
+    return 63 - __clzll((long long)w);
+#else
+    return 63 - __builtin_clzll(w);
+#endif
+  }
+  // index of the highest set bit, -1 when empty
+  LQ_HD int top_bit() const {
+    if (w3) return 192 + top64(w3);
+    if (w2) return 128 + top64(w2);
+    if (w1) return 64 + top64(w1);
+    if (w0) return top64(w0);
+    return -1;
+  }
 };
 
 template <int n, int m>
 struct ClqrLayout {
   int N;
-  int64_t oKu, oKc, okc, oz, ozs, oxs, total;
+  int64_t oKu, oKc, okc, oz, ozs, oxs, oP, total;
+  static constexpr int np = n * (n + 1) / 2;      // packed upper triangle of a symmetric n x n matrix
   LQ_HD explicit ClqrLayout(int N_) : N(N_) {
     oKu = 0;
     oKc = oKu + (int64_t)N * m * n;
@@ -66,7 +82,8 @@ struct ClqrLayout {
     oz = okc + (int64_t)N * m;
     ozs = oz + (int64_t)N * m;
     oxs = ozs + (int64_t)N * m;
-    total = oxs + (int64_t)(N + 1) * n;
+    oP = oxs + (int64_t)(N + 1) * n;              // unconstrained cost-to-go S_k of every stage (packed), k = 0..N-1
+    total = oP + (int64_t)N * np;
   }
 };
 
@@ -97,6 +114,12 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
     riccati_gain<n, m>(st, pl.Ah, K);
     LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oKu + (int64_t)k * (m * n) + e] = K[e];
     riccati_update<n, m>(st, pl.Ah, pb.Q, P);
+    // S_k: where a constrained sweep may start when every clamped input sits at an earlier stage (clqr_backward)
+    {
+      int e = 0;
+      LQ_UNROLL for (int i = 0; i < n; ++i)
+        LQ_UNROLL for (int j = i; j < n; ++j) { ws[L.oP + (int64_t)k * L.np + e] = P[i * n + j]; ++e; }
+    }
   }
   LQ_UNROLL for (int i = 0; i < n * n; ++i) pl.P0[i] = P[i];
   return flags;
@@ -113,20 +136,35 @@ LQ_HD void step_model(const double* A, const double* B, const double* x, const d
 }
 
 // Backward affine Riccati sweep for the working set (fixed, athi): stores K_k (m x n) and k_k (m).
+// `klast` (regulation only, i.e. no references): the highest stage that holds a clamped input. Stages beyond it are
+// unconstrained with a purely quadratic cost-to-go, so their law IS the unconstrained one (ws.Ku, zero offset) and the
+// sweep starts at klast from the stored S_{klast+1} — O(klast) stages instead of N per active-set iteration (in the
+// sweeps of utils_class.py:802-833 the inputs saturate at the first steps only). Pass N - 1 for a full sweep.
 template <int n, int m>
 LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const Mask128& fixed, const Mask128& athi,
-                         const WsView& ws, const Refs& rf = Refs()) {
+                         const WsView& ws, const Refs& rf = Refs(), int klast = -2) {
   const ClqrLayout<n, m> L(N);
+  if (klast < -1 || klast > N - 1) klast = N - 1;
   // cost-to-go INCLUDING the state's own stage term: Phi_k(x) = x'S x + 2 s'x + const; Phi_N = (x - r_{N-1})'P(x - r_{N-1})
   double S[n * n], s[n];
-  LQ_UNROLL for (int i = 0; i < n * n; ++i) S[i] = pb.Pt[i];
-  LQ_UNROLL for (int i = 0; i < n; ++i) {
-    double acc = 0.0;
-    LQ_UNROLL for (int j = 0; j < n; ++j) acc = fma(-pb.Pt[i * n + j], rf.x(j, N - 1), acc);
-    s[i] = acc;
+  if (klast == N - 1) {
+    LQ_UNROLL for (int i = 0; i < n * n; ++i) S[i] = pb.Pt[i];
+    LQ_UNROLL for (int i = 0; i < n; ++i) {
+      double acc = 0.0;
+      LQ_UNROLL for (int j = 0; j < n; ++j) acc = fma(-pb.Pt[i * n + j], rf.x(j, N - 1), acc);
+      s[i] = acc;
+    }
+  } else {
+    int e = 0;
+    LQ_UNROLL for (int i = 0; i < n; ++i)
+      LQ_UNROLL for (int j = i; j < n; ++j) {
+        const double v = ws[L.oP + (int64_t)(klast + 1) * L.np + e];
+        S[i * n + j] = v; S[j * n + i] = v; ++e;
+      }
+    LQ_UNROLL for (int i = 0; i < n; ++i) s[i] = 0.0;
   }
   bool ok = true;
-  for (int k = N - 1; k >= 0; --k) {
+  for (int k = klast; k >= 0; --k) {
     double SB[n * m], G[m * m], Hx[m * (n + 1)];
     mm<n, n, m>(S, pl.Bh, SB);
     LQ_UNROLL for (int i = 0; i < m; ++i)
@@ -280,7 +318,10 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   const int maxit = 8 * N * m + 32;
   bool done = false;
   for (int it = 0; it < maxit && !done; ++it) {
-    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf)) flags |= FLAG_CHOL_FAIL;
+    // regulation: stages beyond the last clamped one keep the unconstrained law — the sweep covers 0..klast only
+    const int top = fixed.top_bit();
+    const int klast = trk ? N - 1 : (top < 0 ? -1 : top / m);
+    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)) flags |= FLAG_CHOL_FAIL;
     // forward sweep: candidate z* (stored in zs), trajectory in xs, largest feasible step along z* - z
     double alpha = 1.0;
     int block = -1;
@@ -288,10 +329,12 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = x0[i]; ws[L.oxs + i] = x0[i]; }
     for (int k = 0; k < N; ++k) {
       double K[m * n];
-      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKc + (int64_t)k * (m * n) + e];
+      const bool tail = (k > klast);                       // unconstrained law (zero offset) beyond klast
+      const int64_t og = tail ? L.oKu : L.oKc;
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[og + (int64_t)k * (m * n) + e];
       mv<m, n>(K, x, u);
       LQ_UNROLL for (int j = 0; j < m; ++j) {
-        u[j] += ws[L.okc + (int64_t)k * m + j];
+        if (!tail) u[j] += ws[L.okc + (int64_t)k * m + j];
         const int bit = k * m + j;
         const bool isfx = fixed.test(bit);
         if (isfx) u[j] = athi.test(bit) ? pb.uhi[j] : pb.ulo[j];

@@ -724,7 +724,7 @@ __device__ __forceinline__ void dyn_gram_spectrum(int lane, Arena& ar, const Dyn
       for (int s = 1; s <= N && ok; ++s) ok = dyn_gs_stage(lane, ar, 1, pb.Q, false, pb.R, -x, 1.0, s == N) && ok;
       if (ok) loH = x; else hiH = x;
       const double mid = 0.5 * (loH + hiH);
-      liveH = (hiH - loH > 4.5e-16 * hiH) && (mid > loH) && (mid < hiH);
+      liveH = (hiH - loH > lq::kGramSpectrumTol * hiH) && (mid > loH) && (mid < hiH);
     }
     if (liveC) {
       const double x = 0.5 * (loC + hiC);
@@ -734,7 +734,7 @@ __device__ __forceinline__ void dyn_gram_spectrum(int lane, Arena& ar, const Dyn
       for (int s = 1; s <= N && ok; ++s) ok = dyn_gs_stage(lane, ar, 2, nullptr, true, nullptr, x, -1.0, s == N) && ok;
       if (ok) hiC = x; else loC = x;
       const double mid = 0.5 * (loC + hiC);
-      liveC = (hiC - loC > 4.5e-16 * hiC) && (mid > loC) && (mid < hiC);
+      liveC = (hiC - loC > lq::kGramSpectrumTol * hiC) && (mid > loC) && (mid < hiC);
     }
   }
   *min_H = 0.5 * (loH + hiH);
