@@ -253,6 +253,11 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, c
 }
 
 // Exact constrained solve from state x0. Returns flags; writes u0[m] and V (= optimum + x0'Qx0).
+// Pass structure (every pass is a sequential N-stage chain on strided scratch, so passes are what the solve costs):
+//   one clipped rollout of the unconstrained law (feasible => optimal, done) doubles as the feasible start;
+//   per active-set iteration: a backward sweep over the stages up to the last clamped one, ONE forward sweep that
+//   also accumulates the objective of its candidate, and a costate sweep over the clamped stages only — the tail
+//   beyond them is unconstrained with cost-to-go x'S x, so its costate is 2 S x without a sweep.
 template <int n, int m>
 LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const double* x0, const WsView& ws,
                      double* u0, double* V, const Refs& rf = Refs()) {
@@ -260,25 +265,30 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   double x[n], xn[n], u[m];
   const bool trk = rf.any();
   int flags = 0;
-  // ---- 1. unconstrained plan; feasible => optimal. With references the plan is affine: gains AND offsets come from
-  //         the affine sweep with an empty working set (stored where the constrained sweeps store theirs).
+  // ---- 1. unconstrained plan, clipped into the box as it is rolled out: no clip => it is the QP minimiser. With
+  //         references the plan is affine: gains AND offsets come from the affine sweep with an empty working set.
   if (trk && !clqr_backward<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf)) flags |= FLAG_CHOL_FAIL;
   const int64_t oK = trk ? L.oKc : L.oKu;
+  Mask128 fixed, athi;
   bool feas = true;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
-  double cost_u = quad<n>(x0, pb.Q, x0);
+  const double c0 = quad<n>(x0, pb.Q, x0);
+  double cost_u = c0;
   for (int k = 0; k < N; ++k) {
     double K[m * n];
     LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
     mv<m, n>(K, x, u);
     LQ_UNROLL for (int j = 0; j < m; ++j) {
       if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
-      if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) feas = false;
       if (k == 0) u0[j] = u[j];
+      if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) feas = false;
+      const int bit = k * m + j;
+      if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed.set(bit); athi.set(bit); }
+      else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed.set(bit); }
+      ws[L.oz + (int64_t)k * m + j] = u[j];
     }
-    if (!feas) break;
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
-    if (trk) {
+    if (trk && feas) {
       double du[m], dx[n];
       LQ_UNROLL for (int j = 0; j < m; ++j) du[j] = u[j] - rf.u(j, k);
       LQ_UNROLL for (int i = 0; i < n; ++i) dx[i] = xn[i] - rf.x(i, k);
@@ -297,36 +307,24 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     *V = NAN;
     return flags | FLAG_QP_MAXITER;
   }
-  // ---- 2. feasible start: saturated rollout of the unconstrained gains; clipped components enter the working set
-  Mask128 fixed, athi;
-  LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
-  for (int k = 0; k < N; ++k) {
-    double K[m * n];
-    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
-    mv<m, n>(K, x, u);
-    LQ_UNROLL for (int j = 0; j < m; ++j) {
-      if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
-      const int bit = k * m + j;
-      if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed.set(bit); athi.set(bit); }
-      else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed.set(bit); }
-      ws[L.oz + (int64_t)k * m + j] = u[j];
-    }
-    step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
-    LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
-  }
-  // ---- 3. primal active-set iterations
+  // ---- 2. primal active-set iterations from the clipped plan (z in ws[oz..], candidate z* in ws[ozs..]; the two
+  //         regions swap roles on a full step instead of being copied)
+  int64_t oz = L.oz, ozs = L.ozs;
   const int maxit = 8 * N * m + 32;
   bool done = false;
+  double cost = 0.0;
   for (int it = 0; it < maxit && !done; ++it) {
     // regulation: stages beyond the last clamped one keep the unconstrained law — the sweep covers 0..klast only
     const int top = fixed.top_bit();
     const int klast = trk ? N - 1 : (top < 0 ? -1 : top / m);
     if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)) flags |= FLAG_CHOL_FAIL;
-    // forward sweep: candidate z* (stored in zs), trajectory in xs, largest feasible step along z* - z
+    // forward sweep: candidate z*, its trajectory (kept up to stage klast + 1: all the costate sweep reads), its
+    // objective, and the largest feasible step along z* - z
     double alpha = 1.0;
     int block = -1;
     bool block_hi = false;
     LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = x0[i]; ws[L.oxs + i] = x0[i]; }
+    cost = c0;
     for (int k = 0; k < N; ++k) {
       double K[m * n];
       const bool tail = (k > klast);                       // unconstrained law (zero offset) beyond klast
@@ -338,9 +336,9 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
         const int bit = k * m + j;
         const bool isfx = fixed.test(bit);
         if (isfx) u[j] = athi.test(bit) ? pb.uhi[j] : pb.ulo[j];
-        ws[L.ozs + (int64_t)k * m + j] = u[j];
+        ws[ozs + (int64_t)k * m + j] = u[j];
         if (!isfx) {
-          const double zc = ws[L.oz + (int64_t)k * m + j];
+          const double zc = ws[oz + (int64_t)k * m + j];
           if (u[j] > pb.uhi[j]) {
             const double a = (pb.uhi[j] - zc) / (u[j] - zc);
             if (a < alpha) { alpha = a; block = k * m + j; block_hi = true; }
@@ -351,35 +349,57 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
         }
       }
       step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
-      LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = xn[i]; ws[L.oxs + (int64_t)(k + 1) * n + i] = xn[i]; }
+      {
+        double du[m], dx[n];
+        LQ_UNROLL for (int j = 0; j < m; ++j) du[j] = u[j] - rf.u(j, k);
+        LQ_UNROLL for (int i = 0; i < n; ++i) dx[i] = xn[i] - rf.x(i, k);
+        cost += quad<m>(du, pb.R, du);
+        cost += (k == N - 1) ? quad<n>(dx, pb.Pt, dx) : quad<n>(dx, pb.Q, dx);
+      }
+      LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
+      if (k <= klast || k == N - 1) {
+        LQ_UNROLL for (int i = 0; i < n; ++i) ws[L.oxs + (int64_t)(k + 1) * n + i] = xn[i];
+      }
     }
     if (block >= 0) {
       // partial step to the blocking bound, which joins the working set
       if (alpha < 0.0) alpha = 0.0;
       for (int e = 0; e < N * m; ++e) {
-        const double zc = ws[L.oz + e];
-        ws[L.oz + e] = fma(alpha, ws[L.ozs + e] - zc, zc);
+        const double zc = ws[oz + e];
+        ws[oz + e] = fma(alpha, ws[ozs + e] - zc, zc);
       }
       const int j = block % m;
-      ws[L.oz + block] = block_hi ? pb.uhi[j] : pb.ulo[j];
+      ws[oz + block] = block_hi ? pb.uhi[j] : pb.ulo[j];
       fixed.set(block);
       if (block_hi) athi.set(block); else athi.clear(block);
       continue;
     }
-    // full step: z = z*; multipliers from the costate sweep over the stored trajectory
-    for (int e = 0; e < N * m; ++e) ws[L.oz + e] = ws[L.ozs + e];
+    // full step: z = z* (swap the regions); multipliers of the clamped inputs from the costate sweep
+    { const int64_t t = oz; oz = ozs; ozs = t; }
     double lam[n];
-    {
+    if (klast == N - 1) {
       double xe[n];
       LQ_UNROLL for (int i = 0; i < n; ++i) xe[i] = ws[L.oxs + (int64_t)N * n + i] - rf.x(i, N - 1);
       mv<n, n>(pb.Pt, xe, lam);
       LQ_UNROLL for (int i = 0; i < n; ++i) lam[i] *= 2.0;
+    } else {
+      // unconstrained tail: cost-to-go x' S_{klast+1} x, hence the costate 2 S x at stage klast + 1
+      double Sk[n * n], xe[n];
+      int e = 0;
+      LQ_UNROLL for (int i = 0; i < n; ++i)
+        LQ_UNROLL for (int j = i; j < n; ++j) {
+          const double v = ws[L.oP + (int64_t)(klast + 1) * L.np + e];
+          Sk[i * n + j] = v; Sk[j * n + i] = v; ++e;
+        }
+      LQ_UNROLL for (int i = 0; i < n; ++i) xe[i] = ws[L.oxs + (int64_t)(klast + 1) * n + i];
+      mv<n, n>(Sk, xe, lam);
+      LQ_UNROLL for (int i = 0; i < n; ++i) lam[i] *= 2.0;
     }
     double worst = 0.0;
     int rel = -1;
-    for (int k = N - 1; k >= 0; --k) {
+    for (int k = klast; k >= 0; --k) {
       double uk[m], g1[m], g2[m];
-      LQ_UNROLL for (int j = 0; j < m; ++j) uk[j] = ws[L.oz + (int64_t)k * m + j] - rf.u(j, k);
+      LQ_UNROLL for (int j = 0; j < m; ++j) uk[j] = ws[oz + (int64_t)k * m + j] - rf.u(j, k);
       mv<m, m>(pb.R, uk, g1);
       LQ_UNROLL for (int j = 0; j < m; ++j) {
         double acc = 0.0;
@@ -408,13 +428,18 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     if (rel < 0) done = true;
     else fixed.clear(rel);
   }
-  if (!done) flags |= FLAG_QP_MAXITER;
-  // ---- 4. objective along z
+  if (done) {                                              // `cost` is the objective of the last candidate = z
+    LQ_UNROLL for (int j = 0; j < m; ++j) u0[j] = ws[oz + j];
+    *V = cost;
+    return flags;
+  }
+  flags |= FLAG_QP_MAXITER;
+  // ---- 3. iteration budget exhausted: objective along the current (feasible, not proven optimal) z
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
-  double cost = quad<n>(x0, pb.Q, x0);
+  cost = c0;
   for (int k = 0; k < N; ++k) {
     LQ_UNROLL for (int j = 0; j < m; ++j) {
-      u[j] = ws[L.oz + (int64_t)k * m + j];
+      u[j] = ws[oz + (int64_t)k * m + j];
       if (k == 0) u0[j] = u[j];
     }
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
