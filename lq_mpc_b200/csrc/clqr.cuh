@@ -278,6 +278,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     double K[m * n];
     LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
     mv<m, n>(K, x, u);
+    const bool was_feas = feas;
     LQ_UNROLL for (int j = 0; j < m; ++j) {
       if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
       if (k == 0) u0[j] = u[j];
@@ -285,7 +286,26 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       const int bit = k * m + j;
       if (u[j] >= pb.uhi[j]) { u[j] = pb.uhi[j]; fixed.set(bit); athi.set(bit); }
       else if (u[j] <= pb.ulo[j]) { u[j] = pb.ulo[j]; fixed.set(bit); }
-      ws[L.oz + (int64_t)k * m + j] = u[j];
+    }
+    // the plan is only WRITTEN (as the active-set start) once it has left the box: a feasible solve — the closed loop's
+    // usual case — stores nothing. The stages before the first violation are replayed (normally there are none).
+    if (was_feas && !feas && k > 0) {
+      double xr[n], xq[n], ur[m];
+      LQ_UNROLL for (int i = 0; i < n; ++i) xr[i] = x0[i];
+      for (int kk = 0; kk < k; ++kk) {
+        double Kr[m * n];
+        LQ_UNROLL for (int e = 0; e < m * n; ++e) Kr[e] = ws[oK + (int64_t)kk * (m * n) + e];
+        mv<m, n>(Kr, xr, ur);
+        LQ_UNROLL for (int j = 0; j < m; ++j) {
+          if (trk) ur[j] += ws[L.okc + (int64_t)kk * m + j];
+          ws[L.oz + (int64_t)kk * m + j] = ur[j];
+        }
+        step_model<n, m>(pl.Ah, pl.Bh, xr, ur, xq);
+        LQ_UNROLL for (int i = 0; i < n; ++i) xr[i] = xq[i];
+      }
+    }
+    if (!feas) {
+      LQ_UNROLL for (int j = 0; j < m; ++j) ws[L.oz + (int64_t)k * m + j] = u[j];
     }
     step_model<n, m>(pl.Ah, pl.Bh, x, u, xn);
     if (trk && feas) {
