@@ -27,33 +27,69 @@
 
 namespace lq {
 
-// One elimination stage. G = Rd + sigma B'PB (Rd already carries the shift), Cholesky test, and unless `last`
+// Square-root-free factorisation test of a small symmetric matrix: G = L D L' (unit lower L left below the diagonal),
+// reciprocals of the pivots in dinv (MUFU.RCP64H + 2 Newton steps instead of the ~30-instruction FP64 rsqrt of a
+// Cholesky: ncu showed 8 % of the kernel's instructions there). Returns "every pivot is positive"; a non-positive or
+// NaN pivot is replaced by 1 so that nothing downstream overflows (the probe has failed anyway).
+template <int m>
+LQ_HD bool ldl_pos(double* G, double* dinv) {
+  bool ok = true;
+  double dv[m];
+  LQ_UNROLL for (int j = 0; j < m; ++j) {
+    double w[m];
+    double d = G[j * m + j];
+    LQ_UNROLL for (int k = 0; k < j; ++k) {
+      w[k] = G[j * m + k] * dv[k];
+      d = fma(-G[j * m + k], w[k], d);
+    }
+    const bool pos = (d > 0.0) && (d < 1.7e308);
+    ok = ok && pos;
+    d = pos ? d : 1.0;
+    dv[j] = d;
+    dinv[j] = rcp(d);
+    LQ_UNROLL for (int i = j + 1; i < m; ++i) {
+      double s = G[i * m + j];
+      LQ_UNROLL for (int k = 0; k < j; ++k) s = fma(-G[i * m + k], w[k], s);
+      G[i * m + j] = s * dinv[j];
+    }
+  }
+  return ok;
+}
+
+// One elimination stage. G = Rd + sigma B'PB (Rd already carries the shift), positivity test, and unless `last`
 // P <- Qw + A' (P - sigma (P B) G^-1 (P B)') A. Returns "G is positive definite".
 template <int n, int m>
 LQ_HD bool gs_stage(const double* Ah, const double* Bh, const double* Qw, const double* Rd, double sigma, bool last,
                     double* P) {
-  double Y[n * m], L[m * m], Li[m];
+  double Y[n * m], L[m * m], Di[m];
   mm<n, n, m>(P, Bh, Y);
   LQ_UNROLL for (int i = 0; i < m; ++i)
     LQ_UNROLL for (int j = 0; j <= i; ++j) {
       double acc = 0.0;
       LQ_UNROLL for (int k = 0; k < n; ++k) acc = fma(Bh[k * m + i], Y[k * m + j], acc);
-      const double g = fma(sigma, acc, Rd[i * m + j]);
-      L[i * m + j] = g;
-      L[j * m + i] = g;
+      L[i * m + j] = fma(sigma, acc, Rd[i * m + j]);
     }
-  const bool ok = chol_inv<m>(L, Li);
+  const bool ok = ldl_pos<m>(L, Di);
   if (last) return ok;
-  solve_right_lt_inv<n, m>(L, Li, Y);             // Y = P B L^-T
-  double Mx[n * n], MA[n * n];
+  // Z = P B L^-T (unit triangular: no divisions), then P - sigma Z D^-1 Z'
   LQ_UNROLL for (int i = 0; i < n; ++i)
+    LQ_UNROLL for (int j = 1; j < m; ++j) {
+      double s = Y[i * m + j];
+      LQ_UNROLL for (int k = 0; k < j; ++k) s = fma(-Y[i * m + k], L[j * m + k], s);
+      Y[i * m + j] = s;
+    }
+  double Mx[n * n], MA[n * n];
+  LQ_UNROLL for (int i = 0; i < n; ++i) {
+    double yd[m];
+    LQ_UNROLL for (int k = 0; k < m; ++k) yd[k] = Y[i * m + k] * Di[k];
     LQ_UNROLL for (int j = i; j < n; ++j) {
       double acc = 0.0;
-      LQ_UNROLL for (int k = 0; k < m; ++k) acc = fma(Y[i * m + k], Y[j * m + k], acc);
+      LQ_UNROLL for (int k = 0; k < m; ++k) acc = fma(yd[k], Y[j * m + k], acc);
       const double v = fma(-sigma, acc, P[i * n + j]);
       Mx[i * n + j] = v;
       Mx[j * n + i] = v;
     }
+  }
   mm<n, n, n>(Mx, Ah, MA);
   sym_add_mtm<n, n>(Qw, Ah, MA, P);
   return ok;
@@ -118,6 +154,10 @@ LQ_HD GramSpectrum gram_spectrum(const double* Ah, const double* Bh, const doubl
   GramSpectrum out;
   bool liveH = (hiH > loH), liveC = (hiC > loC) && (hiC == hiC) && (hiC < 1.7e308);
   if (!(hiC == hiC) || !(hiC < 1.7e308)) { loC = hiC = sumF * sumF; }      // overflow / NaN operands: propagate
+  // Plain bisection on the two predicates. (Safeguarded regula falsi on the last pivot — a smooth monotone function
+  // of the shift whose zero is the eigenvalue — was measured on the host harness: 14-32 probes per sample on average
+  // instead of 43, but its slow tail, samples whose next pole sits within ~1e-6 of the root, puts the MAXIMUM over the
+  // 32 samples of a warp at 33-48 probes: no gain in SIMT, so the simpler search stays.)
   int pass = 0;
   for (; pass < 128 && (liveH || liveC); ++pass) {
     const double xH = 0.5 * (loH + hiH), xC = 0.5 * (loC + hiC);

@@ -214,6 +214,7 @@ struct TiledArgs {
   double* rho;
   double* ratio;
   int rho_qr;            // 1: leave every spectral radius to k4b
+  int rho_sub;           // 1: try the dominant-subspace early exit during the squarings (default)
 };
 
 template <int n, int m>
@@ -538,7 +539,67 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
         double lacc = 0.0, wgt = __hiloint2double((1023 - nsq) << 20, 0), est1 = 0.0;
         bool fail = false, zero = false;
         int kk = nsq;
+        // Early exit through the dominant invariant subspace. A_cl^(2^kk) v lies (to (|lambda_3| / |lambda_1|)^(2^kk)) in
+        // the span of the dominant eigenvector, or of the dominant complex / +- pair; three Krylov vectors x1 = N v,
+        // x2 = A_cl x1, x3 = A_cl x2 of the TRUE closed loop then obey x2 = lambda x1 or x3 = alpha x2 + beta x1 up to
+        // that term, and rho follows from lambda or from the roots of z^2 - alpha z - beta. Accepted only on a relative
+        // residual <= 1e-13 with well separated x1, x2 (sin^2 of their angle >= 1e-3 in the pair case: the 2 x 2 solve
+        // then amplifies the residual by < 1e3); otherwise the squarings go on towards the two-estimate test below.
+        // The residual is measured on A_cl itself, so rounding accumulated in the repeated squarings cannot fake it.
+        bool sub_ok = false;
+        auto try_subspace = [&](const double* Mm) {
+          double* x1 = PB; double* x2 = PB + 32; double* x3 = PB + 64; double* uu = PB + 96;   // PB, Z are idle here
+          auto apply = [&](const double* xin, double* xout) {                                   // xout = (A + B K) xin
+            if (tid < M8) {
+              double acc = 0.0;
+              for (int j = 0; j < n; ++j) acc = fma(Kg[tid * LD + j], xin[j], acc);
+              uu[tid] = acc;
+            }
+            __syncthreads();
+            if (tid < n) {
+              double acc = 0.0;
+              for (int j = 0; j < n; ++j) acc = fma(__ldg(gA + tid * n + j), xin[j], acc);
+              for (int q = 0; q < m; ++q) acc = fma(__ldg(gB + tid * m + q), uu[q], acc);
+              xout[tid] = acc;
+            }
+            __syncthreads();
+          };
+          if (tid < n) {
+            double acc = 0.0;
+            for (int j = 0; j < n; ++j) acc = fma(Mm[tid * LD + j], 1.0 + 0.381966011250105 * (double)((7 * j + 3) % 11), acc);
+            x1[tid] = acc;
+          }
+          __syncthreads();
+          apply(x1, x2);
+          apply(x2, x3);
+          if (w == 0) {
+            const double a1 = (lane < n) ? x1[lane] : 0.0, a2 = (lane < n) ? x2[lane] : 0.0, a3 = (lane < n) ? x3[lane] : 0.0;
+            const double g11 = warp_sum(a1 * a1), g12 = warp_sum(a1 * a2), g22 = warp_sum(a2 * a2);
+            const double b1 = warp_sum(a1 * a3), b2 = warp_sum(a2 * a3), cc = warp_sum(a3 * a3);
+            if (lane == 0) { uu[0] = g11; uu[1] = g12; uu[2] = g22; uu[3] = b1; uu[4] = b2; uu[5] = cc; }
+          }
+          __syncthreads();
+          const double g11 = uu[0], g12 = uu[1], g22 = uu[2], b1 = uu[3], b2 = uu[4], cc = uu[5];
+          __syncthreads();
+          if (!(g11 > 0.0) || !(g22 > 0.0) || !(cc > 0.0) || !(g11 < 1e300) || !(g22 < 1e300) || !(cc < 1e300)) return;
+          const double lam = g12 / g11;
+          const double r2 = g22 - lam * g12;                        // ||x2 - lam x1||^2
+          if (r2 <= 1e-26 * g22) { rho = fabs(lam); sub_ok = true; return; }
+          const double det = g11 * g22 - g12 * g12;
+          if (!(det >= 1e-3 * g11 * g22)) return;
+          const double be = (g22 * b1 - g12 * b2) / det, al = (g11 * b2 - g12 * b1) / det;
+          const double res2 = cc - be * b1 - al * b2;               // ||x3 - al x2 - be x1||^2
+          if (!(res2 <= 1e-26 * cc)) return;
+          const double disc = al * al + 4.0 * be;
+          rho = (disc < 0.0) ? sqrt(-be) : 0.5 * (fabs(al) + sqrt(disc));
+          sub_ok = true;
+        };
         for (; kk < kRhoK2; ++kk) {
+          if (!hi_nonfinite(mh) && (mh >> 20) != 0 && kk >= nsq + 2 && kk <= 28 && ((kk - nsq) & 1) == 0 &&
+              a.rho_sub) {
+            try_subspace(Mc);
+            if (sub_ok) break;
+          }
           if (hi_nonfinite(mh)) { fail = true; break; }
           if ((mh >> 20) == 0) {                             // a vanishing power: A_cl^(2^kk) = 0 (or subnormal).
             zero = (kk <= 6);                                // Nilpotent (rho = 0) if that early; later it is underflow
@@ -568,7 +629,9 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           mh = lh;
           double* t = Mc; Mc = Xc; Xc = t;
         }
-        if (!fail) {
+        if (sub_ok) {
+          accepted = true;
+        } else if (!fail) {
           if (zero) {
             accepted = true;
           } else if (hi_nonfinite(mh) || (mh >> 20) == 0) {
@@ -855,6 +918,7 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
   // spectral radius: repeated squaring inside k4a with the QR kernel as fallback (default), LQMPC_K4_RHO=qr: QR for all
   const char* rhov = getenv("LQMPC_K4_RHO");
   const int rho_qr = (rhov && rhov[0] == 'q') ? 1 : 0;
+  const int rho_sub = (rhov && rhov[0] == 's') ? 0 : 1;     // LQMPC_K4_RHO=sq: squarings with the two-estimate test only
   auto r_J = [](const TiledEval& tt, int64_t s0) { return tt.J ? tt.J + s0 : nullptr; };
   auto r_rho = [](const TiledEval& tt, int64_t s0) { return tt.rho ? tt.rho + s0 : nullptr; };
   auto r_ratio = [](const TiledEval& tt, int64_t s0) { return tt.ratio ? tt.ratio + s0 : nullptr; };
@@ -905,6 +969,7 @@ int launch_tiled_t(lqmpc_ctx* ctx, const TiledEval& t) {
     a.Pout = t.Pout;
     a.J = r_J(t, s0); a.rho = r_rho(t, s0); a.ratio = r_ratio(t, s0);
     a.rho_qr = rho_qr;
+    a.rho_sub = rho_sub;
     int64_t blocks = (int64_t)sms * per_sm;
     if (blocks > cs) blocks = cs;
     kern<<<(unsigned)blocks, kT, smem, ctx->stream>>>(a, nbig);

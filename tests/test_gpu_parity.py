@@ -964,6 +964,28 @@ def test_k4_spectral_radius_by_squaring_and_qr_fallback(engine, monkeypatch):
     assert relerr(sq["rho"].cpu().numpy(), qr["rho"].cpu().numpy()) < 1e-10
     assert np.array_equal(sq["flags"].cpu().numpy(), qr["flags"].cpu().numpy())
     assert np.array_equal(sq["J"].cpu().numpy(), qr["J"].cpu().numpy())
+    # default: the dominant-subspace early exit (three Krylov vectors of the true closed loop, residual <= 1e-13) in
+    # front of the two-estimate test — same answers, and on spectra it must NOT decide (a +- pair of equal modulus
+    # next to a complex pair of the same modulus: rank 4) the later stages still deliver
+    monkeypatch.delenv("LQMPC_K4_RHO")
+    sub = engine.eval_batch_tiled(dA, dB, x0, 30, 30)
+    assert relerr(sub["rho"].cpu().numpy(), qr["rho"].cpu().numpy()) < 1e-10
+    assert np.array_equal(sub["flags"].cpu().numpy(), qr["flags"].cpu().numpy())
+    assert np.array_equal(sub["J"].cpu().numpy(), qr["J"].cpu().numpy())
+    dA2, dB2, x2 = nb.synth_samples(n, m, 600, seed=9, e=0.2)           # far perturbations: unstable loops included
+    monkeypatch.setenv("LQMPC_K4_RHO", "qr")
+    qr2 = engine.eval_batch_tiled(dA2, dB2, x2, 30, 30)
+    monkeypatch.delenv("LQMPC_K4_RHO")
+    sub2 = engine.eval_batch_tiled(dA2, dB2, x2, 30, 30)
+    assert relerr(sub2["rho"].cpu().numpy(), qr2["rho"].cpu().numpy()) < 1e-10
+    assert np.array_equal(sub2["flags"].cpu().numpy(), qr2["flags"].cpu().numpy())
+    blocks = [np.array([[0.0, 0.8], [-0.8, 0.0]]), np.diag([0.8, -0.8])] + [np.array([[0.3]])] * (n - 4)
+    import scipy.linalg as sla
+    Tm = rng.normal(size=(n, n)) + 3 * np.eye(n)
+    A4 = Tm @ sla.block_diag(*blocks) @ np.linalg.inv(Tm)
+    engine.set_problem_tiled(A4, np.zeros((n, m)), np.eye(n), np.eye(m), np.eye(n), 30)
+    r4 = engine.eval_batch_tiled(np.zeros((5, n, n)), np.zeros((5, n, m)), rng.normal(size=(5, n)), 6, 6)
+    assert np.max(np.abs(r4["rho"].cpu().numpy() - 0.8)) < 1e-10 and not np.any(r4["flags"].cpu().numpy())
 
 
 # --------------------------------------------------------------------------------------------- sweep driver (cfg 2)
