@@ -582,14 +582,23 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           const double g11 = uu[0], g12 = uu[1], g22 = uu[2], b1 = uu[3], b2 = uu[4], cc = uu[5];
           __syncthreads();
           if (!(g11 > 0.0) || !(g22 > 0.0) || !(cc > 0.0) || !(g11 < 1e300) || !(g22 < 1e300) || !(cc < 1e300)) return;
+          // candidates from the Gram entries; the RESIDUALS are formed explicitly (a Gram-based residual such as
+          // g22 - g12^2 / g11 cancels to ~1e-16 g22, i.e. cannot see relative residuals below 1e-8)
           const double lam = g12 / g11;
-          const double r2 = g22 - lam * g12;                        // ||x2 - lam x1||^2
-          if (r2 <= 1e-26 * g22) { rho = fabs(lam); sub_ok = true; return; }
           const double det = g11 * g22 - g12 * g12;
-          if (!(det >= 1e-3 * g11 * g22)) return;
-          const double be = (g22 * b1 - g12 * b2) / det, al = (g11 * b2 - g12 * b1) / det;
-          const double res2 = cc - be * b1 - al * b2;               // ||x3 - al x2 - be x1||^2
-          if (!(res2 <= 1e-26 * cc)) return;
+          const bool pair_ok = (det >= 1e-3 * g11 * g22);
+          const double be = pair_ok ? (g22 * b1 - g12 * b2) / det : 0.0, al = pair_ok ? (g11 * b2 - g12 * b1) / det : 0.0;
+          if (w == 0) {
+            const double a1 = (lane < n) ? x1[lane] : 0.0, a2 = (lane < n) ? x2[lane] : 0.0, a3 = (lane < n) ? x3[lane] : 0.0;
+            const double e1 = a2 - lam * a1, e2 = a3 - al * a2 - be * a1;
+            const double r1 = warp_sum(e1 * e1), r2 = warp_sum(e2 * e2);
+            if (lane == 0) { uu[6] = r1; uu[7] = r2; }
+          }
+          __syncthreads();
+          const double r1 = uu[6], r2 = uu[7];
+          __syncthreads();
+          if (r1 <= 1e-26 * g22) { rho = fabs(lam); sub_ok = true; return; }      // ||x2 - lam x1|| <= 1e-13 ||x2||
+          if (!pair_ok || !(r2 <= 1e-26 * cc)) return;                          // ||x3 - al x2 - be x1|| <= 1e-13 ||x3||
           const double disc = al * al + 4.0 * be;
           rho = (disc < 0.0) ? sqrt(-be) : 0.5 * (fabs(al) + sqrt(disc));
           sub_ok = true;
