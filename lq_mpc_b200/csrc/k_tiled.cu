@@ -546,7 +546,12 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
         // residual <= 1e-13 with well separated x1, x2 (sin^2 of their angle >= 1e-3 in the pair case: the 2 x 2 solve
         // then amplifies the residual by < 1e3); otherwise the squarings go on towards the two-estimate test below.
         // The residual is measured on A_cl itself, so rounding accumulated in the repeated squarings cannot fake it.
-        bool sub_ok = false;
+        // A small residual alone does not bound the eigenvalue error of a NON-NORMAL matrix (defective spectra: error ~
+        // residual^(1/d) — a 16 x 16 Jordan block passed the residual test 1.6e-7 off), so, as for the norm estimates
+        // below, two successive candidates (powers 2^kk and 2^(kk+2)) must also agree to 2e-11: slow, polynomial
+        // convergence shows up as disagreement and falls through to the later stages.
+        bool sub_ok = false, sub_cand = false;
+        double rho_cand = 0.0;
         auto try_subspace = [&](const double* Mm) {
           double* x1 = PB; double* x2 = PB + 32; double* x3 = PB + 64; double* uu = PB + 96;   // PB, Z are idle here
           auto apply = [&](const double* xin, double* xout) {                                   // xout = (A + B K) xin
@@ -581,7 +586,10 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           __syncthreads();
           const double g11 = uu[0], g12 = uu[1], g22 = uu[2], b1 = uu[3], b2 = uu[4], cc = uu[5];
           __syncthreads();
-          if (!(g11 > 0.0) || !(g22 > 0.0) || !(cc > 0.0) || !(g11 < 1e300) || !(g22 < 1e300) || !(cc < 1e300)) return;
+          if (!(g11 > 0.0) || !(g22 > 0.0) || !(cc > 0.0) || !(g11 < 1e300) || !(g22 < 1e300) || !(cc < 1e300)) {
+            sub_cand = false;
+            return;
+          }
           // candidates from the Gram entries; the RESIDUALS are formed explicitly (a Gram-based residual such as
           // g22 - g12^2 / g11 cancels to ~1e-16 g22, i.e. cannot see relative residuals below 1e-8)
           const double lam = g12 / g11;
@@ -597,11 +605,17 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           __syncthreads();
           const double r1 = uu[6], r2 = uu[7];
           __syncthreads();
-          if (r1 <= 1e-26 * g22) { rho = fabs(lam); sub_ok = true; return; }      // ||x2 - lam x1|| <= 1e-13 ||x2||
-          if (!pair_ok || !(r2 <= 1e-26 * cc)) return;                          // ||x3 - al x2 - be x1|| <= 1e-13 ||x3||
-          const double disc = al * al + 4.0 * be;
-          rho = (disc < 0.0) ? sqrt(-be) : 0.5 * (fabs(al) + sqrt(disc));
-          sub_ok = true;
+          double cand;
+          if (r1 <= 1e-26 * g22) {                                              // ||x2 - lam x1|| <= 1e-13 ||x2||
+            cand = fabs(lam);
+          } else {
+            if (!pair_ok || !(r2 <= 1e-26 * cc)) { sub_cand = false; return; } // ||x3 - al x2 - be x1|| <= 1e-13 ||x3||
+            const double disc = al * al + 4.0 * be;
+            cand = (disc < 0.0) ? sqrt(-be) : 0.5 * (fabs(al) + sqrt(disc));
+          }
+          if (sub_cand && fabs(cand - rho_cand) <= 2e-11 * cand) { rho = cand; sub_ok = true; return; }
+          sub_cand = true;
+          rho_cand = cand;
         };
         for (; kk < kRhoK2; ++kk) {
           if (!hi_nonfinite(mh) && (mh >> 20) != 0 && kk >= nsq + 2 && kk <= 28 && ((kk - nsq) & 1) == 0 &&
