@@ -46,8 +46,9 @@ WORKLOADS = {
 }
 # ncu `sm__pipe_fp64_cycles_active` of the dominant kernel from the committed captures (profiles/README.md): what the
 # pipe actually did, next to the algorithmic fraction
-PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r01v4_k1_eval_4x2_metrics.csv", 0.636),
-                   "cfg-synth-32-8-30": ("profiles/r01k4e_k4a_tiled_eval_32x8_metrics.csv", 0.690)}
+PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 0.636),
+                   "cfg-synth-32-8-30": ("profiles/r02_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.576),
+                   "cfg-sweep-f": ("profiles/r02b_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
 
 
 def flops_per_eval(n, m, N, lyap_iters=8):
@@ -203,6 +204,13 @@ def cpu_sweep_throughput(per_worker, workers=None):
         wall = time.perf_counter() - t
     total = workers * per_worker
     return total / wall, workers, total
+
+
+def _json_field(rel, key):
+    try:
+        return json.load(open(os.path.join(ROOT, rel))).get(key)
+    except (OSError, ValueError):
+        return None
 
 
 def workload_config(wl, n_gpus, scaling="weak"):
@@ -639,7 +647,11 @@ def measure_sweep(cx, wl, reps=1):
                      "achieved": k3_tf, "peak": peak, "unit": "TFLOP/s", "frac": k3_tf / peak if peak else None,
                      "algorithmic_flops": "2 searches x 52 probes x N stages x (4n^3+4n^2m+3nm^2+m^3/3) + DARE "
                                           "(k3_flops_per_eval), summed over N = 1..%d" % wl["nmax"],
-                     "traffic": None},
+                     "pipe_active_ncu": PIPE_ACTIVE_NCU["cfg-sweep-f"][1],
+                     "pipe_active_ncu_source": PIPE_ACTIVE_NCU["cfg-sweep-f"][0],
+                     "traffic": _json_field("profiles/r02b_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
+                     "traffic_note": "ncu capture of ONE bounds_kernel launch (N = 50, 1e6 samples): operands + outputs "
+                                     "(6 + 31 doubles per sample), no scratch"},
         "gpu_launches": int(launches), "sampler_seconds": t_gen, "clocks": clocks,
         "worst_case": {"true_ratio_max": float(np.nanmax(r["ratio_true_max"])), "V_expert": r["V_expert"]},
     }
