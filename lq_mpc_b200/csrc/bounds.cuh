@@ -236,6 +236,12 @@ LQ_HD_NOINLINE void ws_tridiag_extremes(const WsView& ws, int64_t od, int64_t oe
 }
 
 template <int n, int m>
+LQ_HD_NOINLINE_T GramSpectrum gram_spectrum_call(const double* Ah, const double* Bh, const double* Q, const double* R,
+                                                 double minR, int N) {
+  return gram_spectrum<n, m>(Ah, Bh, Q, R, minR, N);
+}
+
+template <int n, int m>
 struct BoundsLayout {
   int N, k;
   int64_t oG, oC, od, oe, total;
@@ -461,7 +467,9 @@ LQ_HD int bounds_sample(const Problem<n, m>& pb, const double* Ah, const double*
   double cmin = 0.0, cmax = 0.0, min_H;
   if (matrix_free) {
     // ---------------- matrix-free: bisection on the N-stage elimination (gramspec.cuh); Q, R enter stage-wise
-    const GramSpectrum gs = gram_spectrum<n, m>(Ah, Bh, pb.Q, pb.R, minR, N);
+    // (n >= 5: a separate, non-inlined function — inlined into this body the register allocator gave up at n = 8)
+    const GramSpectrum gs = (n <= 4) ? gram_spectrum<n, m>(Ah, Bh, pb.Q, pb.R, minR, N)
+                                     : gram_spectrum_call<n, m>(Ah, Bh, pb.Q, pb.R, minR, N);
     cmax = gs.cmax;
     min_H = gs.min_H;
   } else {

@@ -252,6 +252,14 @@ LQ_HD bool clqr_backward(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, c
   return ok;
 }
 
+// n >= 5: the sweep as a separate, non-inlined function (inlined into the solver the register allocator gives up at
+// n = 8: 32 registers and 55 kB of spills per thread).
+template <int n, int m>
+LQ_HD_NOINLINE_T bool clqr_backward_call(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const Mask128& fixed,
+                                         const Mask128& athi, const WsView& ws, const Refs& rf, int klast) {
+  return clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast);
+}
+
 // Exact constrained solve from state x0. Returns flags; writes u0[m] and V (= optimum + x0'Qx0).
 // Pass structure (every pass is a sequential N-stage chain on strided scratch, so passes are what the solve costs):
 //   one clipped rollout of the unconstrained law (feasible => optimal, done) doubles as the feasible start;
@@ -267,7 +275,9 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   int flags = 0;
   // ---- 1. unconstrained plan, clipped into the box as it is rolled out: no clip => it is the QP minimiser. With
   //         references the plan is affine: gains AND offsets come from the affine sweep with an empty working set.
-  if (trk && !clqr_backward<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf)) flags |= FLAG_CHOL_FAIL;
+  if (trk && !((n <= 4) ? clqr_backward<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf, N - 1)
+                        : clqr_backward_call<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf, N - 1)))
+    flags |= FLAG_CHOL_FAIL;
   const int64_t oK = trk ? L.oKc : L.oKu;
   Mask128 fixed, athi;
   bool feas = true;
@@ -337,7 +347,9 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     // regulation: stages beyond the last clamped one keep the unconstrained law — the sweep covers 0..klast only
     const int top = fixed.top_bit();
     const int klast = trk ? N - 1 : (top < 0 ? -1 : top / m);
-    if (!clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)) flags |= FLAG_CHOL_FAIL;
+    if (!((n <= 4) ? clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)
+                   : clqr_backward_call<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)))
+      flags |= FLAG_CHOL_FAIL;
     // forward sweep: candidate z*, its trajectory (kept up to stage klast + 1: all the costate sweep reads), its
     // objective, and the largest feasible step along z* - z
     double alpha = 1.0;

@@ -169,11 +169,16 @@ LQ_HD GramSpectrum gram_spectrum(const double* Ah, const double* Bh, const doubl
       }
     LQ_UNROLL for (int e = 0; e < n * n; ++e) { PH[e] = Q[e]; PC[e] = eye[e]; }
     bool okH = true, okC = true;
-    for (int s = 1; s <= N; ++s) {
-      const bool last = (s == N);
-      okH = gs_stage<n, m>(Ah, Bh, Q, RdH, 1.0, last, PH) && okH;
-      okC = gs_stage<n, m>(Ah, Bh, eye, RdC, -1.0, last, PC) && okC;
-      if (!okH && !okC) break;          // both probes already decided
+    if (n <= 4) {                         // two independent recursions interleaved: instruction-level parallelism
+      for (int s = 1; s <= N; ++s) {
+        const bool last = (s == N);
+        okH = gs_stage<n, m>(Ah, Bh, Q, RdH, 1.0, last, PH) && okH;
+        okC = gs_stage<n, m>(Ah, Bh, eye, RdC, -1.0, last, PC) && okC;
+        if (!okH && !okC) break;          // both probes already decided
+      }
+    } else {                              // n >= 5: one recursion at a time (an n x n block is 2 n^2 registers)
+      for (int s = 1; s <= N && okH; ++s) okH = gs_stage<n, m>(Ah, Bh, Q, RdH, 1.0, s == N, PH);
+      for (int s = 1; s <= N && okC; ++s) okC = gs_stage<n, m>(Ah, Bh, eye, RdC, -1.0, s == N, PC);
     }
     if (liveH) {
       if (okH) loH = xH; else hiH = xH;

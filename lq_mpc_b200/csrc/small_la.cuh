@@ -14,10 +14,12 @@
 #if defined(__CUDACC__)
 #define LQ_HD __host__ __device__ __forceinline__
 #define LQ_HD_NOINLINE static __host__ __device__ __noinline__
+#define LQ_HD_NOINLINE_T __host__ __device__ __noinline__
 #define LQ_UNROLL _Pragma("unroll")
 #else
 #define LQ_HD inline
 #define LQ_HD_NOINLINE static
+#define LQ_HD_NOINLINE_T
 #define LQ_UNROLL
 #endif
 
