@@ -170,14 +170,6 @@ LQ_HD void closed_loop_eval(const Problem<n, m>& pb, const double* K, const doub
   }
 }
 
-// n >= 5: the closed-loop part (spectral radius by Hessenberg + QR, Lyapunov doubling) as a separate, non-inlined
-// function, so that its n x n temporaries are allocated apart from the Riccati loop's.
-template <int n, int m>
-LQ_HD_NOINLINE_T void closed_loop_eval_call(const Problem<n, m>& pb, const double* K, const double* x0, int T,
-                                            double* J_inf, double* rho_out, double* J_T, int* flags) {
-  closed_loop_eval<n, m>(pb, K, x0, T, J_inf, rho_out, J_T, flags);
-}
-
 // Full per-sample evaluation over the nested horizons N_min..N_max. `sink(h, ...)` receives column h = N - N_min.
 template <int n, int m, class Sink>
 LQ_HD void eval_sample(const Problem<n, m>& pb, const double* dA, const double* dB, const double* x0,
@@ -198,8 +190,7 @@ LQ_HD void eval_sample(const Problem<n, m>& pb, const double* dA, const double* 
     if (emit) {
       int flags = sticky;
       double J, rho, JT = 0.0;
-      if (n <= 4) closed_loop_eval<n, m>(pb, K, x0, T, &J, &rho, &JT, &flags);
-      else closed_loop_eval_call<n, m>(pb, K, x0, T, &J, &rho, &JT, &flags);
+      closed_loop_eval<n, m>(pb, K, x0, T, &J, &rho, &JT, &flags);
       const double vn = want_vn ? quad<n>(x0, P, x0) : 0.0;
       sink(k - N_min, J, rho, J / v_exp, vn, JT, flags, K);
     }
