@@ -73,7 +73,7 @@ struct Mask128 {   // (name kept from the 128-bit first version)
 template <int n, int m>
 struct ClqrLayout {
   int N;
-  int64_t oKu, oKc, okc, oz, ozs, oxs, oP, total;
+  int64_t oKu, oKc, okc, oz, ozs, oxs, oP, oGc, total;
   static constexpr int np = n * (n + 1) / 2;      // packed upper triangle of a symmetric n x n matrix
   LQ_HD explicit ClqrLayout(int N_) : N(N_) {
     oKu = 0;
@@ -83,7 +83,8 @@ struct ClqrLayout {
     ozs = oz + (int64_t)N * m;
     oxs = ozs + (int64_t)N * m;
     oP = oxs + (int64_t)(N + 1) * n;              // unconstrained cost-to-go S_k of every stage (packed), k = 0..N-1
-    total = oP + (int64_t)N * np;
+    oGc = oP + (int64_t)N * np;                   // composite rows g_k = K_k Phi_k: planned input u_k = g_k x_0
+    total = oGc + (int64_t)N * m * n;
   }
 };
 
@@ -122,6 +123,30 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
     }
   }
   LQ_UNROLL for (int i = 0; i < n * n; ++i) pl.P0[i] = P[i];
+  // Composite rows of the unconstrained plan: x_k = Phi_k x_0 with Phi_{k+1} = (A^ + B^ K_k) Phi_k, so the planned input
+  // is u_k = (K_k Phi_k) x_0 =: g_k x_0. The feasibility test of a solve then is N INDEPENDENT dot products instead of an
+  // N-stage dependent rollout (the closed loop's usual, feasible step is bound by exactly that chain's latency).
+  {
+    double Phi[n * n];
+    LQ_UNROLL for (int i = 0; i < n; ++i)
+      LQ_UNROLL for (int j = 0; j < n; ++j) Phi[i * n + j] = (i == j) ? 1.0 : 0.0;
+    for (int k = 0; k < N; ++k) {
+      double K[m * n], g[m * n], Acl[n * n], Pn[n * n];
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+      mm<m, n, n>(K, Phi, g);
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oGc + (int64_t)k * (m * n) + e] = g[e];
+      if (k + 1 < N) {
+        LQ_UNROLL for (int i = 0; i < n; ++i)
+          LQ_UNROLL for (int j = 0; j < n; ++j) {
+            double acc = pl.Ah[i * n + j];
+            LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(pl.Bh[i * m + r], K[r * n + j], acc);
+            Acl[i * n + j] = acc;
+          }
+        mm<n, n, n>(Acl, Phi, Pn);
+        LQ_UNROLL for (int i = 0; i < n * n; ++i) Phi[i] = Pn[i];
+      }
+    }
+  }
   return flags;
 }
 
@@ -279,6 +304,28 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
                         : clqr_backward_call<n, m>(pb, pl, N, Mask128(), Mask128(), ws, rf, N - 1)))
     flags |= FLAG_CHOL_FAIL;
   const int64_t oK = trk ? L.oKc : L.oKu;
+  if (!trk) {
+    // ---- 0. regulation: the whole unconstrained plan is linear in x0 (u_k = g_k x0): test it without rolling it out
+    bool inside = true;
+    for (int k0 = 0; k0 < N && inside; k0 += 4) {          // four stages per exit test: their loads are independent
+      LQ_UNROLL for (int kk = 0; kk < 4; ++kk) {
+        const int k = k0 + kk;
+        if (k < N) {
+          double g[m * n];
+          LQ_UNROLL for (int e = 0; e < m * n; ++e) g[e] = ws[L.oGc + (int64_t)k * (m * n) + e];
+          mv<m, n>(g, x0, u);
+          LQ_UNROLL for (int j = 0; j < m; ++j) {
+            if (k == 0) u0[j] = u[j];
+            if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) inside = false;
+          }
+        }
+      }
+    }
+    if (inside) {
+      *V = quad<n>(x0, pl.P0, x0);
+      return flags;
+    }
+  }
   Mask128 fixed, athi;
   bool feas = true;
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
