@@ -73,7 +73,7 @@ struct Mask128 {   // (name kept from the 128-bit first version)
 template <int n, int m>
 struct ClqrLayout {
   int N;
-  int64_t oKu, oKc, okc, oz, ozs, oxs, oP, oGc, total;
+  int64_t oKu, oKc, okc, oz, ozs, oxs, oP, total;
   static constexpr int np = n * (n + 1) / 2;      // packed upper triangle of a symmetric n x n matrix
   LQ_HD explicit ClqrLayout(int N_) : N(N_) {
     oKu = 0;
@@ -83,8 +83,7 @@ struct ClqrLayout {
     ozs = oz + (int64_t)N * m;
     oxs = ozs + (int64_t)N * m;
     oP = oxs + (int64_t)(N + 1) * n;              // unconstrained cost-to-go S_k of every stage (packed), k = 0..N-1
-    oGc = oP + (int64_t)N * np;                   // composite rows g_k = K_k Phi_k: planned input u_k = g_k x_0
-    total = oGc + (int64_t)N * m * n;
+    total = oP + (int64_t)N * np;
   }
 };
 
@@ -98,6 +97,7 @@ template <int n, int m>
 struct Plan {
   double Ah[n * n], Bh[n * m];
   double P0[n * n];  // unconstrained horizon-N cost-to-go: V_N = x0' P0 x0 when no bound is active
+  double cstar;      // feasibility certificate: x0' P0 x0 <= cstar  =>  the whole unconstrained plan stays inside the box
 };
 
 // Unconstrained Riccati sweep; stores the gains K_k (u_k = K_k x_k) for k = 0..N-1 in the workspace.
@@ -123,29 +123,59 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
     }
   }
   LQ_UNROLL for (int i = 0; i < n * n; ++i) pl.P0[i] = P[i];
-  // Composite rows of the unconstrained plan: x_k = Phi_k x_0 with Phi_{k+1} = (A^ + B^ K_k) Phi_k, so the planned input
-  // is u_k = (K_k Phi_k) x_0 =: g_k x_0. The feasibility test of a solve then is N INDEPENDENT dot products instead of an
-  // N-stage dependent rollout (the closed loop's usual, feasible step is bound by exactly that chain's latency).
-  {
-    double Phi[n * n];
-    LQ_UNROLL for (int i = 0; i < n; ++i)
-      LQ_UNROLL for (int j = 0; j < n; ++j) Phi[i * n + j] = (i == j) ? 1.0 : 0.0;
-    for (int k = 0; k < N; ++k) {
-      double K[m * n], g[m * n], Acl[n * n], Pn[n * n];
-      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
-      mm<m, n, n>(K, Phi, g);
-      LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oGc + (int64_t)k * (m * n) + e] = g[e];
-      if (k + 1 < N) {
-        LQ_UNROLL for (int i = 0; i < n; ++i)
-          LQ_UNROLL for (int j = 0; j < n; ++j) {
-            double acc = pl.Ah[i * n + j];
-            LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(pl.Bh[i * m + r], K[r * n + j], acc);
-            Acl[i * n + j] = acc;
-          }
-        mm<n, n, n>(Acl, Phi, Pn);
-        LQ_UNROLL for (int i = 0; i < n * n; ++i) Phi[i] = Pn[i];
-      }
+  // Feasibility certificate of the unconstrained plan. x_k = Phi_k x_0 with Phi_{k+1} = (A^ + B^ K_k) Phi_k, so the
+  // planned input is u_k = (K_k Phi_k) x_0 =: g_k x_0 and, by Cauchy-Schwarz in the P0 metric,
+  //     |u_{k,j}| <= sqrt(g_{k,j} P0^-1 g_{k,j}') sqrt(x_0' P0 x_0).
+  // Hence x_0' P0 x_0 <= cstar := min_{k,j} b_j^2 / (g_{k,j} P0^-1 g_{k,j}'), b_j = min(-lo_j, hi_j), guarantees that no
+  // planned input leaves the box: the solve returns the unconstrained answer from ONE quadratic form (which it needs
+  // anyway: it is V_N) instead of an N-stage rollout. Sufficient, not necessary — outside the ellipsoid the rollout
+  // decides as before, so nothing is approximated. In the closed loops of the sweeps the state enters the ellipsoid
+  // after the first few steps. (1 - 1e-9 margin against rounding in cstar itself.)
+  pl.cstar = -1.0;
+  if (pb.has_bounds) {
+    double Lc[n * n], Lci[n];
+    LQ_UNROLL for (int i = 0; i < n * n; ++i) Lc[i] = P[i];
+    bool okc = chol_inv<n>(Lc, Lci);
+    double bmin2[m];
+    LQ_UNROLL for (int j = 0; j < m; ++j) {
+      const double b = dmin(-pb.ulo[j], pb.uhi[j]);
+      okc = okc && (b > 0.0);
+      bmin2[j] = b * b;
     }
+    if (okc) {
+      double cs = HUGE_VAL;
+      double Phi[n * n];
+      LQ_UNROLL for (int i = 0; i < n; ++i)
+        LQ_UNROLL for (int j = 0; j < n; ++j) Phi[i * n + j] = (i == j) ? 1.0 : 0.0;
+      for (int k = 0; k < N; ++k) {
+        double K[m * n], g[m * n], Acl[n * n], Pn[n * n];
+        LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+        mm<m, n, n>(K, Phi, g);
+        LQ_UNROLL for (int j = 0; j < m; ++j) {             // y = L^-1 g_j' (forward substitution), q = y'y = g_j P0^-1 g_j'
+          double y[n], q = 0.0;
+          LQ_UNROLL for (int i = 0; i < n; ++i) {
+            double acc = g[j * n + i];
+            LQ_UNROLL for (int r = 0; r < i; ++r) acc = fma(-Lc[i * n + r], y[r], acc);
+            y[i] = acc * Lci[i];
+            q = fma(y[i], y[i], q);
+          }
+          if (bmin2[j] < 1e300 && q > 0.0) cs = dmin(cs, bmin2[j] / q);
+        }
+        if (k + 1 < N) {
+          LQ_UNROLL for (int i = 0; i < n; ++i)
+            LQ_UNROLL for (int j = 0; j < n; ++j) {
+              double acc = pl.Ah[i * n + j];
+              LQ_UNROLL for (int r = 0; r < m; ++r) acc = fma(pl.Bh[i * m + r], K[r * n + j], acc);
+              Acl[i * n + j] = acc;
+            }
+          mm<n, n, n>(Acl, Phi, Pn);
+          LQ_UNROLL for (int i = 0; i < n * n; ++i) Phi[i] = Pn[i];
+        }
+      }
+      if (cs == cs) pl.cstar = cs * (1.0 - 1e-9);
+    }
+  } else {
+    pl.cstar = HUGE_VAL;             // no input bounds at all: every plan is feasible
   }
   return flags;
 }
@@ -305,24 +335,13 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     flags |= FLAG_CHOL_FAIL;
   const int64_t oK = trk ? L.oKc : L.oKu;
   if (!trk) {
-    // ---- 0. regulation: the whole unconstrained plan is linear in x0 (u_k = g_k x0): test it without rolling it out
-    bool inside = true;
-    for (int k0 = 0; k0 < N && inside; k0 += 4) {          // four stages per exit test: their loads are independent
-      LQ_UNROLL for (int kk = 0; kk < 4; ++kk) {
-        const int k = k0 + kk;
-        if (k < N) {
-          double g[m * n];
-          LQ_UNROLL for (int e = 0; e < m * n; ++e) g[e] = ws[L.oGc + (int64_t)k * (m * n) + e];
-          mv<m, n>(g, x0, u);
-          LQ_UNROLL for (int j = 0; j < m; ++j) {
-            if (k == 0) u0[j] = u[j];
-            if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) inside = false;
-          }
-        }
-      }
-    }
-    if (inside) {
-      *V = quad<n>(x0, pl.P0, x0);
+    // ---- 0. regulation: inside the certificate ellipsoid the unconstrained plan is feasible, hence optimal
+    const double V0 = quad<n>(x0, pl.P0, x0);
+    if (V0 <= pl.cstar) {
+      double K[m * n];
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + e];
+      mv<m, n>(K, x0, u0);
+      *V = V0;
       return flags;
     }
   }
