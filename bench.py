@@ -48,7 +48,7 @@ WORKLOADS = {
 # pipe actually did, next to the algorithmic fraction
 PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 0.636),
                    "cfg-synth-32-8-30": ("profiles/r02_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.576),
-                   "cfg-sweep-f": ("profiles/r02b_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
+                   "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
 
 
 def flops_per_eval(n, m, N, lyap_iters=8):
@@ -63,8 +63,8 @@ def bytes_per_eval(n, m):
     return (n * n + n * m + n) * 8 + 4 * 8
 
 
-def k3_flops_per_eval(n, m, N, probes=52):
-    """K3's matrix-free spectrum (csrc/gramspec.cuh): two bisection searches x `probes` probes x N elimination stages of
+def k3_flops_per_eval(n, m, N, probes=43):
+    """K3's matrix-free spectrum (csrc/gramspec.cuh): two bisection searches x `probes` probes (a ~6-bit bracket narrowed to 2^-42) x N elimination stages of
     4n^3 + 4n^2 m + 3 n m^2 + m^3/3 dense flops (P B, B'Y, Cholesky, triangular solve, Y Y', two n^3 products), plus the
     DARE (SDA, ~10 doublings of ~14 n^3) — the algorithmic count DESIGN.md states for the sweep's dominant kernel."""
     stage = 4 * n ** 3 + 4 * n * n * m + 3 * n * m * m + m ** 3 / 3.0
@@ -645,11 +645,11 @@ def measure_sweep(cx, wl, reps=1):
                      "bisection recursions per thread, registers only) — FP64 pipe / dependent-chain latency",
                      "kernel": "bounds_kernel<2,1>", "kernel_seconds_per_sweep": ph["bounds"],
                      "achieved": k3_tf, "peak": peak, "unit": "TFLOP/s", "frac": k3_tf / peak if peak else None,
-                     "algorithmic_flops": "2 searches x 52 probes x N stages x (4n^3+4n^2m+3nm^2+m^3/3) + DARE "
+                     "algorithmic_flops": "2 searches x 43 probes x N stages x (4n^3+4n^2m+3nm^2+m^3/3) + DARE "
                                           "(k3_flops_per_eval), summed over N = 1..%d" % wl["nmax"],
                      "pipe_active_ncu": PIPE_ACTIVE_NCU["cfg-sweep-f"][1],
                      "pipe_active_ncu_source": PIPE_ACTIVE_NCU["cfg-sweep-f"][0],
-                     "traffic": _json_field("profiles/r02b_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
+                     "traffic": _json_field("profiles/r02c_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
                      "traffic_note": "ncu capture of ONE bounds_kernel launch (N = 50, 1e6 samples): operands + outputs "
                                      "(6 + 31 doubles per sample), no scratch"},
         "gpu_launches": int(launches), "sampler_seconds": t_gen, "clocks": clocks,
