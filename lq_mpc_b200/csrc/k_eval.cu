@@ -168,6 +168,10 @@ __global__ void __launch_bounds__(256) dfma_kernel(double* out, int iters, doubl
 }  // namespace
 
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
+  if (lq_group_supported(ctx->n, ctx->m)) {   // n = 6, 8: lane-group kernel (k_group.cu); LQMPC_K1_GROUP=0: thread/sample
+    const char* v = getenv("LQMPC_K1_GROUP");
+    if (!(v && v[0] == '0')) return lq_launch_eval_group(ctx, a, stream);
+  }
 #define X(N_, M_) \
   if (ctx->n == N_ && ctx->m == M_) return launch_eval_t<N_, M_>(ctx, a, stream);
   LQ_FOR_EACH_DIM(X)

@@ -69,6 +69,103 @@ def test_k1_matches_oracle(engine, n, m, e):
     assert not np.any(g["flags"] & ~1)
 
 
+@pytest.mark.parametrize("n,m,variant", [(8, 2, ""), (8, 2, "2"), (8, 2, "4"), (8, 2, "0"), (6, 2, ""), (6, 2, "0")])
+def test_k1_lane_group_builds_agree_with_thread_route_and_oracle(engine, n, m, variant, monkeypatch):
+    """n = 6, 8: the lane-group kernel (k_group.cu; default), its two other register / lane splits and the
+    thread-per-sample instantiation (LQMPC_K1_GROUP=0) against the oracle — one horizon per sample (the build whose
+    cost-to-go dies before the closed-loop phase) and nested horizons (the build that parks it in shared memory),
+    a ragged batch (tail groups), large perturbations (unstable closed loops) included."""
+    from oracle import np_batched as nb
+    if variant:
+        monkeypatch.setenv("LQMPC_K1_GROUP", variant)
+    else:
+        monkeypatch.delenv("LQMPC_K1_GROUP", raising=False)
+    A, B, Q, R = nb.synth_problem(n, m, seed=2)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    Pexp = nb.expert_matrix(A, B, Q, R, Q, 30)
+    for S, e, (N_min, N_max) in ((1031, 0.05, (7, 7)), (517, 0.4, (1, 5)), (3, 0.02, (1, 1))):
+        dA, dB, x0 = nb.synth_samples(n, m, S, seed=11 + S, e=e)
+        ref = nb.eval_batch(A, B, Q, R, Q, Pexp, dA, dB, x0, N_min, N_max, T=0, want_K=True)
+        want = ("J", "rho", "ratio", "flags", "K0") + (("V_N",) if N_min != N_max else ())
+        got = engine.eval_batch(*_soa(dA, dB, x0), N_min, N_max, want=want)
+        g = {k: v.cpu().numpy() for k, v in got.items() if hasattr(v, "cpu")}
+        assert np.array_equal((g["flags"] & 1) != 0, ref["unstable"]), (S, e)
+        assert not np.any(g["flags"] & ~1)
+        assert relerr(g["rho"], ref["rho"]) < TOL
+        if "V_N" in g:
+            assert relerr(g["V_N"], ref["Vn"]) < TOL
+        _k1_arbitrate(A, B, Q, R, dA, dB, x0, N_min, g["J"], ref["J"], ref["rho"])
+        assert np.array_equal(np.isfinite(g["J"]), np.isfinite(ref["J"]))
+        H = N_max - N_min + 1
+        K = g["K0"].reshape(H, m, n, S).transpose(0, 3, 1, 2)
+        assert np.max(np.abs(K - ref["K0"])) < 1e-10 * max(1.0, np.max(np.abs(ref["K0"])))
+
+
+def test_k1_lane_group_spectral_radius_on_hard_spectra(engine):
+    """The lane-group kernel takes rho from repeated squaring with a dominant-pair early acceptance (k_group.cu). With
+    a vanishing input matrix the closed loop IS the plant, so prescribed spectra reach that code: a dominant real
+    eigenvalue, a +- pair, a complex pair, three eigenvalues of (nearly) equal modulus, a defective (Jordan) dominant
+    eigenvalue, a nilpotent plant. Compared with numpy's eigenvalues; where the two differ by more than 1e-9 the
+    dominant eigenvalue is ill-conditioned and both must lie within its condition bound of the 50-digit value."""
+    import mpmath as mp
+    rng = np.random.default_rng(77)
+    n, m = 8, 2
+
+    def from_spec(spec, V):
+        D = np.zeros((n, n)); i = 0
+        for sp_ in spec:
+            if sp_[0] == "c":
+                a, b = sp_[1] * np.cos(sp_[2]), sp_[1] * np.sin(sp_[2])
+                D[i:i + 2, i:i + 2] = [[a, b], [-b, a]]; i += 2
+            elif sp_[0] == "j":                        # Jordan block of size 3
+                for q in range(3):
+                    D[i + q, i + q] = sp_[1]
+                D[i, i + 1] = D[i + 1, i + 2] = 1.0; i += 3
+            else:
+                D[i, i] = sp_[1]; i += 1
+        while i < n:
+            D[i, i] = rng.uniform(-0.4, 0.4) * abs(spec[0][1]); i += 1
+        return V @ D @ np.linalg.inv(V)
+
+    mats = []
+    for t in range(60):
+        V = rng.standard_normal((n, n))
+        r0 = rng.uniform(0.3, 1.3)
+        gap = 10.0 ** rng.uniform(-12, -1)
+        th, th2 = rng.uniform(0.05, 3.0, 2)
+        kind = t % 6
+        if kind == 0: spec = [("r", r0)]
+        elif kind == 1: spec = [("r", r0), ("r", -r0 * (1 - gap))]
+        elif kind == 2: spec = [("c", r0, th)]
+        elif kind == 3: spec = [("c", r0, th), ("r", r0 * (1 - gap)), ("c", r0 * (1 - 3 * gap), th2)]
+        elif kind == 4: spec = [("j", r0)]
+        else: spec = [("r", r0), ("r", r0 * (1 - gap)), ("r", -r0 * (1 - 2 * gap))]
+        mats.append(from_spec(spec, V))
+    N8 = np.zeros((n, n)); N8[np.arange(n - 1), np.arange(1, n)] = rng.uniform(0.5, 2.0, n - 1)
+    mats.append(N8)                                     # nilpotent: rho = 0
+    mats.append(np.zeros((n, n)))
+    mp.mp.dps = 50
+    n_arb = 0
+    for M in mats:
+        B = np.zeros((n, m)); B[0, 0] = B[1, 1] = 1e-200          # K = O(1e-200): A + B K == A in double
+        engine.set_problem(M, B, np.eye(n), np.eye(m), np.eye(n), None, None, 1)
+        z = np.zeros((1, n, n)), np.zeros((1, n, m)), np.ones((1, n))
+        got = engine.eval_batch(*_soa(*z), 1, 1, want=("rho", "flags"))
+        rho = float(got["rho"].cpu().numpy()[0, 0])
+        ref = float(np.max(np.abs(np.linalg.eigvals(M))))
+        if abs(rho - ref) <= TOL * max(ref, 1e-300) or (ref < 1e-12 and rho < 1e-12):
+            continue
+        n_arb += 1
+        ev = mp.eig(mp.matrix(M.tolist()), left=False, right=False)
+        truth = float(max(abs(x) for x in ev))
+        w, vl, vr = __import__("scipy.linalg", fromlist=["eig"]).eig(M, left=True)
+        j = int(np.argmax(np.abs(w)))
+        kappa = np.linalg.norm(vl[:, j]) * np.linalg.norm(vr[:, j]) / abs(np.vdot(vl[:, j], vr[:, j]))
+        bound = max(TOL, 64 * np.finfo(float).eps * kappa * np.linalg.norm(M, 2) / truth)
+        assert abs(rho - truth) <= bound * truth, (rho, truth, ref, kappa)
+    assert n_arb <= 25
+
+
 def test_k1_per_sample_oracle_and_edges(engine):
     """Independent per-sample oracle (scipy Lyapunov/eig) + edge cases: S=1, S=0, N=1, nested == single horizon."""
     from oracle import np_batched as nb, np_oracle as o
