@@ -15,8 +15,10 @@
 //     symmetric) do not. The Cholesky is replicated in the registers of every lane of the chain warp (no shuffles,
 //     no shared-memory round trips on the serial stretch). Lyapunov doubling accumulates M'(S M) straight into S from the GEMM
 //     epilogue. The spectral radius comes from the SAME squarings carried on with exact power-of-two rescaling:
-//     rho = lim ||A_cl^(2^k)||^(1/2^k), 40 squarings, accepted when the k = 34 and k = 40 estimates agree to 5e-10
-//     (then the error is ~1e-11 or better); anything else is left to k4b.
+//     rho = lim ||A_cl^(2^k)||^(1/2^k). A sample whose dominant eigenvalue is real, a +- pair or a complex pair is
+//     accepted after typically 9-14 squarings from the traces of two successive powers (roots of z^2 - t z + d,
+//     reproduced by two successive squarings); the others run 40 squarings and are accepted when the k = 34 and
+//     k = 40 norm estimates agree to 5e-10 (then the error is ~1e-11 or better); anything else is left to k4b.
 //   * k4b `tiled_rho_kernel<n>`: ONE WARP PER PENDING SAMPLE: Householder -> Hessenberg and the Francis double-shift
 //     QR iteration run warp-synchronously on a shared-memory copy of A_cl (lane = row or column of the 3-row/3-column
 //     reflector updates), scalars replicated across lanes. Only samples k4a did not accept (LQMPC_K4_RHO=qr: all).
@@ -115,6 +117,19 @@ __device__ __forceinline__ void block_max2_u32(unsigned& a, unsigned& b, unsigne
   a = ta; b = tb;
 }
 
+// max of `a` and sum of `t` over the block behind ONE barrier (same slot discipline as block_max2_u32)
+__device__ __forceinline__ void block_max_u32_sum(unsigned& a, double& t, unsigned* uslot, double* dslot) {
+  a = __reduce_max_sync(0xffffffffu, a);
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) { uslot[threadIdx.x >> 5] = a; dslot[threadIdx.x >> 5] = t; }
+  __syncthreads();
+  unsigned ta = uslot[0];
+  double tt = dslot[0];
+#pragma unroll
+  for (int w = 1; w < kT / 32; ++w) { ta = max(ta, uslot[w]); tt += dslot[w]; }
+  a = ta; t = tt;
+}
+
 // ------------------------------------------------------------------------------------------------ warp-level MMA
 // Every matrix product of the Riccati step and of the Lyapunov doubling goes through ONE routine: a warp accumulates an
 // (8 MT) x (8 NT) block of C = A B as m8n8k4 FP64 tensor-core MMAs (DM = true: mma.sync -> DMMA), operands read
@@ -195,6 +210,8 @@ __device__ __forceinline__ void gemm_nn(const double* __restrict__ A, const doub
 
 // ------------------------------------------------------------------------------------------------ k4a
 constexpr int kRhoK1 = 34, kRhoK2 = 40;          // squarings behind the two spectral-radius estimates
+constexpr double kRhoEta = 1e-9;                  // dominant-pair early acceptance: consistency of successive candidates
+constexpr double kRhoMinRoot = 0.02;              //   ... and the smallest root / max|X| ratio a candidate may have
 constexpr int kFlagRhoPending = 1 << 30;          // internal: k4b still owes this entry its QR iteration
 
 struct TiledArgs {
@@ -228,7 +245,7 @@ struct K4Smem {
   static constexpr int LD = n + 4, NN = n * LD, LS = 12, M8 = 8;
   static constexpr int oBh = 0, oPB = oBh + n * LS, oZ = oPB + n * LS, oKg = oZ + n * LS, oRK = oKg + M8 * LD,
                        oG = oRK + M8 * LD, oRs = oG + M8 * LS, oxs = oRs + M8 * LS, ored = oxs + n,
-                       obar = ored + 4 * (kT / 32), total = obar + 2;
+                       obar = ored + 6 * (kT / 32), total = obar + 2;
   static_assert(M8 * LD >= n * m, "dB lands dense in the RK area");
   static_assert((oxs % 2) == 0 && (oRK % 2) == 0 && (oG % 2) == 0, "TMA destinations / 16-byte loads must be aligned");
 };
@@ -279,7 +296,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
   double* G = sk + L::oG;               // 8 x 8 (ld 12)
   double* Rs = sk + L::oRs;             // 8 x 8 (ld 12): R padded with the identity
   double* xs = sk + L::oxs;             // n
-  double* red = sk + L::ored;           // 4 * (kT/32): two slots for block_sum/block_max2, two for the squarings
+  double* red = sk + L::ored;           // 6 * (kT/32): two slots for block_sum/block_max2, two (as unsigned) + two for the squarings
   uint64_t* bar = reinterpret_cast<uint64_t*>(sk + L::obar);
   int* cflag = reinterpret_cast<int*>(bar + 1);
 
@@ -539,90 +556,26 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
         double lacc = 0.0, wgt = __hiloint2double((1023 - nsq) << 20, 0), est1 = 0.0;
         bool fail = false, zero = false;
         int kk = nsq;
-        // Early exit through the dominant invariant subspace. A_cl^(2^kk) v lies (to (|lambda_3| / |lambda_1|)^(2^kk)) in
-        // the span of the dominant eigenvector, or of the dominant complex / +- pair; three Krylov vectors x1 = N v,
-        // x2 = A_cl x1, x3 = A_cl x2 of the TRUE closed loop then obey x2 = lambda x1 or x3 = alpha x2 + beta x1 up to
-        // that term, and rho follows from lambda or from the roots of z^2 - alpha z - beta. Accepted only on a relative
-        // residual <= 1e-13 with well separated x1, x2 (sin^2 of their angle >= 1e-3 in the pair case: the 2 x 2 solve
-        // then amplifies the residual by < 1e3); otherwise the squarings go on towards the two-estimate test below.
-        // The residual is measured on A_cl itself, so rounding accumulated in the repeated squarings cannot fake it.
-        // A small residual alone does not bound the eigenvalue error of a NON-NORMAL matrix (defective spectra: error ~
-        // residual^(1/d) — a 16 x 16 Jordan block passed the residual test 1.6e-7 off), so, as for the norm estimates
-        // below, two successive candidates (powers 2^kk and 2^(kk+2)) must also agree to 2e-11: slow, polynomial
-        // convergence shows up as disagreement and falls through to the later stages.
-        bool sub_ok = false, sub_cand = false;
-        double rho_cand = 0.0;
-        auto try_subspace = [&](const double* Mm) {
-          double* x1 = PB; double* x2 = PB + 32; double* x3 = PB + 64; double* uu = PB + 96;   // PB, Z are idle here
-          auto apply = [&](const double* xin, double* xout) {                                   // xout = (A + B K) xin
-            if (tid < M8) {
-              double acc = 0.0;
-              for (int j = 0; j < n; ++j) acc = fma(Kg[tid * LD + j], xin[j], acc);
-              uu[tid] = acc;
-            }
-            __syncthreads();
-            if (tid < n) {
-              double acc = 0.0;
-              for (int j = 0; j < n; ++j) acc = fma(__ldg(gA + tid * n + j), xin[j], acc);
-              for (int q = 0; q < m; ++q) acc = fma(__ldg(gB + tid * m + q), uu[q], acc);
-              xout[tid] = acc;
-            }
-            __syncthreads();
-          };
-          if (tid < n) {
-            double acc = 0.0;
-            for (int j = 0; j < n; ++j) acc = fma(Mm[tid * LD + j], 1.0 + 0.381966011250105 * (double)((7 * j + 3) % 11), acc);
-            x1[tid] = acc;
-          }
-          __syncthreads();
-          apply(x1, x2);
-          apply(x2, x3);
-          if (w == 0) {
-            const double a1 = (lane < n) ? x1[lane] : 0.0, a2 = (lane < n) ? x2[lane] : 0.0, a3 = (lane < n) ? x3[lane] : 0.0;
-            const double g11 = warp_sum(a1 * a1), g12 = warp_sum(a1 * a2), g22 = warp_sum(a2 * a2);
-            const double b1 = warp_sum(a1 * a3), b2 = warp_sum(a2 * a3), cc = warp_sum(a3 * a3);
-            if (lane == 0) { uu[0] = g11; uu[1] = g12; uu[2] = g22; uu[3] = b1; uu[4] = b2; uu[5] = cc; }
-          }
-          __syncthreads();
-          const double g11 = uu[0], g12 = uu[1], g22 = uu[2], b1 = uu[3], b2 = uu[4], cc = uu[5];
-          __syncthreads();
-          if (!(g11 > 0.0) || !(g22 > 0.0) || !(cc > 0.0) || !(g11 < 1e300) || !(g22 < 1e300) || !(cc < 1e300)) {
-            sub_cand = false;
-            return;
-          }
-          // candidates from the Gram entries; the RESIDUALS are formed explicitly (a Gram-based residual such as
-          // g22 - g12^2 / g11 cancels to ~1e-16 g22, i.e. cannot see relative residuals below 1e-8)
-          const double lam = g12 / g11;
-          const double det = g11 * g22 - g12 * g12;
-          const bool pair_ok = (det >= 1e-3 * g11 * g22);
-          const double be = pair_ok ? (g22 * b1 - g12 * b2) / det : 0.0, al = pair_ok ? (g11 * b2 - g12 * b1) / det : 0.0;
-          if (w == 0) {
-            const double a1 = (lane < n) ? x1[lane] : 0.0, a2 = (lane < n) ? x2[lane] : 0.0, a3 = (lane < n) ? x3[lane] : 0.0;
-            const double e1 = a2 - lam * a1, e2 = a3 - al * a2 - be * a1;
-            const double r1 = warp_sum(e1 * e1), r2 = warp_sum(e2 * e2);
-            if (lane == 0) { uu[6] = r1; uu[7] = r2; }
-          }
-          __syncthreads();
-          const double r1 = uu[6], r2 = uu[7];
-          __syncthreads();
-          double cand;
-          if (r1 <= 1e-26 * g22) {                                              // ||x2 - lam x1|| <= 1e-13 ||x2||
-            cand = fabs(lam);
-          } else {
-            if (!pair_ok || !(r2 <= 1e-26 * cc)) { sub_cand = false; return; } // ||x3 - al x2 - be x1|| <= 1e-13 ||x3||
-            const double disc = al * al + 4.0 * be;
-            cand = (disc < 0.0) ? sqrt(-be) : 0.5 * (fabs(al) + sqrt(disc));
-          }
-          if (sub_cand && fabs(cand - rho_cand) <= 2e-11 * cand) { rho = cand; sub_ok = true; return; }
-          sub_cand = true;
-          rho_cand = cand;
-        };
+        // Early acceptance through the two dominant eigenvalues (the rule of k_group.cu, where it is derived and
+        // its tolerances are explained). With X = 2^-e N_k (max|X| in [1, 2)) and N_(k+1) = X^2: t = tr X, t' = tr X^2,
+        // d = (t^2 - t') / 2. When one real eigenvalue, a +- pair or a complex pair dominates, the p-th powers
+        // (p = 2^k) of the dominant eigenvalues are the roots of z^2 - t z + d up to (|lambda_3| / |lambda_1|)^p, so
+        // rho^p = sqrt(d) (complex roots) or the larger root modulus. A candidate must not be tiny against max|X|
+        // (ill-conditioned or defective dominant eigenvalues leave rounding noise in the traces) nor nearly double,
+        // and is ACCEPTED when two successive squarings reproduce it, r_k 2^(e_k) = r_(k-1)^2 to kRhoEta; everything
+        // else runs on to the norm-based two-estimate test below (and to the QR kernel when that fails too).
+        // Replaces round 2's Krylov-vector subspace test, which needed 3 extra mat-vecs per probe and still ran
+        // ~30 squarings on most samples; this one costs one trace per squaring and typically stops after 9-14.
+        bool sub_ok = false;
+        double tr_cur = 0.0, rr_prev = 0.0;
+        int streak = -1;
+        {
+          double tq = 0.0;
+          for (int e = tid; e < n; e += kT) tq += Mc[e * LD + e];
+          tr_cur = block_sum(tq, red);
+        }
+        double* dsl = red + 4 * (kT / 32);
         for (; kk < kRhoK2; ++kk) {
-          if (!hi_nonfinite(mh) && (mh >> 20) != 0 && kk >= nsq + 2 && kk <= 28 && ((kk - nsq) & 1) == 0 &&
-              a.rho_sub) {
-            try_subspace(Mc);
-            if (sub_ok) break;
-          }
           if (hi_nonfinite(mh)) { fail = true; break; }
           if ((mh >> 20) == 0) {                             // a vanishing power: A_cl^(2^kk) = 0 (or subnormal).
             zero = (kk <= 6);                                // Nilpotent (rho = 0) if that early; later it is underflow
@@ -636,6 +589,7 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
           // range (a product of two unnormalised operands would underflow the small entries that carry rho)
           const double s2 = __hiloint2double((1023 - 2 * e) << 20, 0);
           unsigned lh = 0;
+          double trn = 0.0;
           {
             const int r0 = (w >> 1) * HB, c0 = (w & 1) * HB;
             double c[T][T][2];
@@ -644,13 +598,34 @@ __global__ void __launch_bounds__(kT, MB) tiled_eval_kernel(const TiledArgs a, c
             warp_mma_store<T, T>(r0, c0, c, [&](int i, int j, double v) {
               Xc[i * LD + j] = v;
               lh = max(lh, hi_abs(v));
+              if (i == j) trn += v;
             });
           }
           lacc = fma(wgt, (double)e, lacc);
+          block_max_u32_sum(lh, trn, ru + (rp & 1) * (2 * (kT / 32)), dsl + (rp & 1) * (kT / 32));
+          ++rp;
+          if (a.rho_sub) {
+            const double sc = __hiloint2double((1023 - e) << 20, 0);
+            const double tau = tr_cur * sc, t2 = tau * tau;
+            const double d = 0.5 * (t2 - trn), disc = fma(2.0, trn, -t2);
+            const double rr = (disc < 0.0) ? sqrt(d) : 0.5 * (fabs(tau) + sqrt(disc));
+            if ((rr > kRhoMinRoot) && (rr < 1e300) && !(fabs(disc) < 1e-4 * t2)) {
+              const bool same = (streak >= 0) && fabs(rr - rr_prev * rr_prev * sc) <= kRhoEta * rr;
+              if (same && streak >= 1 && kRhoEta * wgt <= 2e-10) {
+                rho = exp(fma(lacc, 0.6931471805599453, wgt * log(rr)));
+                sub_ok = true;
+              }
+              streak = same ? streak + 1 : 0;
+              rr_prev = rr;
+            } else {
+              streak = -1;
+            }
+          }
+          tr_cur = trn;
           wgt *= 0.5;
-          block_max2_u32(lh, dm, ru + (rp++ & 1) * (2 * (kT / 32)));
           mh = lh;
           double* t = Mc; Mc = Xc; Xc = t;
+          if (sub_ok) break;
         }
         if (sub_ok) {
           accepted = true;
