@@ -47,7 +47,7 @@ WORKLOADS = {
 # ncu `sm__pipe_fp64_cycles_active` of the dominant kernel from the committed captures (profiles/README.md): what the
 # pipe actually did, next to the algorithmic fraction
 PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 0.636),
-                   "cfg-synth-32-8-30": ("profiles/r02_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.576),
+                   "cfg-synth-32-8-30": ("profiles/r02d_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.656),
                    "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
 
 
