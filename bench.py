@@ -13,11 +13,12 @@ The same JSON line carries, under "workloads", the other two BASELINE configurat
   cfg-sweep-f        (configs[2]: the 2-state example, error-level x horizon grid N=1..50, 1e5 perturbations per level
                       per GPU, input box active: K2a ring solves + K2b closed loops + K3 bounds + K5)
 each with its own value, ms, roofline, clocks and (N=1) CPU baseline, and under "strong_scaling" configs[3] as written
-(1e8 samples in TOTAL at every N).
+(1e8 samples in TOTAL at every N). A fourth sub-record, "probe-8-2-10", is NOT a BASELINE configuration: n=8, m=2,
+N=10 on the lane-group K1 (the top of north_star's "n <= 8" range), 2e6 samples per GPU, same legs.
 
   python bench.py [--gpus N] [--steps K] [--warmup W]          our arm  (torchrun launches it for N > 1)
   python bench.py --impl reference ...                         the CPU arm: the numpy oracle port on all host cores
-  python bench.py --workload cfg-synth-32-8-30|cfg-sweep-f     one of the other configurations as the headline line
+  python bench.py --workload cfg-synth-32-8-30|cfg-sweep-f|probe-8-2-10   one of the others as the headline line
   python bench.py --scaling strong                             configs[3] with 1e8 samples in total as the headline line
 
 One JSON line on stdout (rank 0).
@@ -43,12 +44,15 @@ WORKLOADS = {
                               kernel="tiled_eval_kernel<32,8> (+ tiled_rho_kernel<32> for entries it hands over)"),
     "cfg-sweep-f": dict(n=2, m=1, per_level=100_000, n_err=10, nmax=50, norm="f", T=30, sweep=True,
                         kernel="bounds_kernel<2,1> (K3) + simulate_kernel<2,1> (K2b) + mpc_solve_kernel<2,1> (K2a)"),
+    # not a BASELINE configuration: the top of north_star's "n <= 8" range, on the lane-group K1 (k_group.cu)
+    "probe-8-2-10": dict(n=8, m=2, N=10, S=2_000_000, e=0.01, tiled=False, kernel="group_eval_kernel<8,2,4> (lane groups)"),
 }
 # ncu `sm__pipe_fp64_cycles_active` of the dominant kernel from the committed captures (profiles/README.md): what the
 # pipe actually did, next to the algorithmic fraction
 PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 0.636),
                    "cfg-synth-32-8-30": ("profiles/r02d_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.656),
-                   "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741)}
+                   "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741),
+                   "probe-8-2-10": ("profiles/r02d_k1_group_eval_8x2_metrics.csv", 0.333)}
 
 
 POWER_WARM_S = 0.75          # see measure_synth step (0)
@@ -361,8 +365,9 @@ def roofline_record(cx, wl, S, ms_kernel, tiled):
     hbm_peak = float(cx.peaks.get("hbm_gbs", 6650.0))
     traffic = None
     try:
-        tf_name = "k4_traffic.json" if tiled else "k1_traffic.json"
-        traffic = json.load(open(os.path.join(ROOT, "profiles", tf_name))).get("dram_bytes_per_launch")
+        tf_name = "k4_traffic.json" if tiled else ("k1_traffic.json" if n == 4 else None)   # captures of THESE shapes
+        if tf_name:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", tf_name))).get("dram_bytes_per_launch")
     except (OSError, ValueError):
         pass
     src, pipe = PIPE_ACTIVE_NCU.get(wl["name"], (None, None))
@@ -744,6 +749,8 @@ def run_ours(args, wl):
         subs["cfg-synth-32-8-30"] = measure_synth(cx, k4, max(3, min(10, steps)), 3, full=False)
         sw = dict(WORKLOADS["cfg-sweep-f"], name="cfg-sweep-f")
         subs["cfg-sweep-f"] = measure_sweep(cx, sw, reps=1)
+        p8 = dict(WORKLOADS["probe-8-2-10"], name="probe-8-2-10")
+        subs["probe-8-2-10"] = measure_synth(cx, p8, max(3, min(10, steps)), 3, full=False)
         if cx.rank == 0:
             line["strong_scaling"] = strong
             line["workloads"] = subs
