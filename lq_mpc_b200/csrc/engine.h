@@ -150,6 +150,7 @@ int lq_launch_prepare(lqmpc_ctx* ctx);
 int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
 bool lq_group_supported(int n, int m);
 int lq_launch_eval_group(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream);
+int lq_launch_eval_group_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B);
 int lq_launch_eval_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B);
 int lq_launch_fp64_peak(lqmpc_ctx* ctx, double* tflops);
 int lq_launch_dmma_peak(lqmpc_ctx* ctx, double* tflops);

@@ -180,6 +180,10 @@ int lq_launch_eval(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
 }
 
 int lq_launch_eval_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B) {
+  if (lq_group_supported(ctx->n, ctx->m)) {
+    const char* v = getenv("LQMPC_K1_GROUP");
+    if (!(v && v[0] == '0')) return lq_launch_eval_group_seeded(ctx, a, seed, first, e_A, e_B);
+  }
 #define X(N_, M_) \
   if (ctx->n == N_ && ctx->m == M_) return launch_eval_seeded_t<N_, M_>(ctx, a, seed, first, e_A, e_B);
   LQ_FOR_EACH_DIM(X)

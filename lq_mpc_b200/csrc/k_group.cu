@@ -25,6 +25,7 @@
 #include <stdlib.h>
 
 #include "engine.h"
+#include "sampler.cuh"
 
 namespace {
 
@@ -543,9 +544,18 @@ __device__ __forceinline__ void closed_loop_emit(const lq::Problem<n, m>& pb, co
 
 // NESTED = false: one horizon per sample and no V_N — the cost-to-go dies before the closed-loop phase;
 // NESTED = true: horizons N_min..N_max (or V_N wanted) — it waits in the arena while the closed loop is evaluated.
-template <int n, int m, int L, bool NESTED, int MINB>
+// lqmpc_eval_seeded on lane groups: the operands are not read but drawn in the kernel (sampler.cuh: seeded_sample — the
+// stream is addressed by (global sample index, pair index), so every lane draws exactly its own rows)
+struct SeedArgs {
+  uint64_t seed;
+  int64_t first;
+  double e_A, e_B;
+};
+
+template <int n, int m, int L, bool NESTED, int MINB, bool SEEDED>
 __global__ void __launch_bounds__((GroupLayout<n, m, L, NESTED>::kThreads), MINB)
-    group_eval_kernel(const __grid_constant__ lq::Problem<n, m> pb, const __grid_constant__ EvalArgs a) {
+    group_eval_kernel(const __grid_constant__ lq::Problem<n, m> pb, const __grid_constant__ EvalArgs a,
+                      const __grid_constant__ SeedArgs sd) {
   using Lay = GroupLayout<n, m, L, NESTED>;
   constexpr int R = Lay::R;
   extern __shared__ __align__(16) double sm[];
@@ -572,22 +582,60 @@ __global__ void __launch_bounds__((GroupLayout<n, m, L, NESTED>::kThreads), MINB
 
   // ---- operands: every lane fetches its own rows of A^ = A + dA, B^ = B + dB and its entries of x0
   double Bhr[R][m], P[R][n];
+  if (SEEDED) {
+    static_assert(!SEEDED || ((R * n) % 2 == 0 && (R * m) % 2 == 0 && (n * n) % 2 == 0), "seeded draw: whole pairs per lane");
+    const uint32_t k0 = (uint32_t)sd.seed, k1 = (uint32_t)(sd.seed >> 32) ^ lq::kSeededStream;
+    const int64_t gs = sd.first + s;
+    const uint32_t c0 = (uint32_t)gs, c1 = (uint32_t)((uint64_t)gs >> 32);
+    constexpr int nu = n * n + n * m;
 #pragma unroll
-  for (int r = 0; r < R; ++r) {
-#pragma unroll
-    for (int j = 0; j < n; ++j) {
-      const int e = (row0 + r) * n + j;
-      g.Ah[e] = g.cA[e] + ldg_stream(a.dA + (int64_t)e * a.ld + s);
-      P[r][j] = pb.Pt[e];
+    for (int q = 0; q < R * n; q += 2) {                 // own rows of dA: elements row0 n + q, + 1
+      const int e = row0 * n + q;
+      const lq::Philox4 x = lq::philox4x32_10(c0, c1, (uint32_t)(e >> 1), 0u, k0, k1);
+      g.Ah[e] = g.cA[e] + sd.e_A * lq::philox_symm(x.v[0], x.v[1]);
+      g.Ah[e + 1] = g.cA[e + 1] + sd.e_A * lq::philox_symm(x.v[2], x.v[3]);
     }
 #pragma unroll
-    for (int j = 0; j < m; ++j) {
-      const int e = (row0 + r) * m + j;
-      const double v = g.cB[e] + ldg_stream(a.dB + (int64_t)e * a.ld + s);
-      Bhr[r][j] = v;
-      g.Bh[e] = v;
+    for (int q = 0; q < R * m; q += 2) {                 // own rows of dB: elements n n + row0 m + q, + 1
+      const int e = row0 * m + q;
+      const lq::Philox4 x = lq::philox4x32_10(c0, c1, (uint32_t)((n * n + e) >> 1), 0u, k0, k1);
+      const double v0 = g.cB[e] + sd.e_B * lq::philox_symm(x.v[0], x.v[1]);
+      const double v1 = g.cB[e + 1] + sd.e_B * lq::philox_symm(x.v[2], x.v[3]);
+      Bhr[q / m][q % m] = v0;
+      Bhr[(q + 1) / m][(q + 1) % m] = v1;
+      g.Bh[e] = v0;
+      g.Bh[e + 1] = v1;
     }
-    g.Xs[row0 + r] = ldg_stream(a.x0 + (int64_t)(row0 + r) * a.ld + s);
+    for (int pp = row0 >> 1; pp <= (row0 + R - 1) >> 1; ++pp) {      // own entries of x0 (Box-Muller pairs)
+      const lq::Philox4 x = lq::philox4x32_10(c0, c1, (uint32_t)((nu + 1) / 2 + pp), 0u, k0, k1);
+      const double u = ((double)(x.v[0] >> 5) * 67108864.0 + (double)(x.v[1] >> 6) + 1.0) * (1.0 / 9007199254740992.0);
+      const double v = ((double)(x.v[2] >> 5) * 67108864.0 + (double)(x.v[3] >> 6)) * (1.0 / 9007199254740992.0);
+      const double rr = sqrt(-2.0 * log(u)), th = 6.283185307179586476925286766559 * v;
+      if (2 * pp >= row0 && 2 * pp < row0 + R) g.Xs[2 * pp] = rr * cos(th);
+      if (2 * pp + 1 >= row0 && 2 * pp + 1 < row0 + R) g.Xs[2 * pp + 1] = rr * sin(th);
+    }
+#pragma unroll
+    for (int r = 0; r < R; ++r)
+#pragma unroll
+      for (int j = 0; j < n; ++j) P[r][j] = pb.Pt[(row0 + r) * n + j];
+  } else {
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+#pragma unroll
+      for (int j = 0; j < n; ++j) {
+        const int e = (row0 + r) * n + j;
+        g.Ah[e] = g.cA[e] + ldg_stream(a.dA + (int64_t)e * a.ld + s);
+        P[r][j] = pb.Pt[e];
+      }
+#pragma unroll
+      for (int j = 0; j < m; ++j) {
+        const int e = (row0 + r) * m + j;
+        const double v = g.cB[e] + ldg_stream(a.dB + (int64_t)e * a.ld + s);
+        Bhr[r][j] = v;
+        g.Bh[e] = v;
+      }
+      g.Xs[row0 + r] = ldg_stream(a.x0 + (int64_t)(row0 + r) * a.ld + s);
+    }
   }
   __syncwarp();
   double v_exp;
@@ -624,26 +672,26 @@ __global__ void __launch_bounds__((GroupLayout<n, m, L, NESTED>::kThreads), MINB
   }
 }
 
-template <int n, int m, int L, bool NESTED, int MINB>
-int launch_group_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
+template <int n, int m, int L, bool NESTED, int MINB, bool SEEDED>
+int launch_group_t(lqmpc_ctx* ctx, const EvalArgs& a, const SeedArgs& sd, cudaStream_t stream) {
   using Lay = GroupLayout<n, m, L, NESTED>;
   const lq::Problem<n, m>& pb = *reinterpret_cast<const lq::Problem<n, m>*>(ctx->pb);
   const int64_t blocks = (a.S + Lay::kGroups - 1) / Lay::kGroups;
   if (blocks > 0x7fffffffLL) return lq_set_error(ctx, LQMPC_EINVAL, "batch too large for one launch");
   if (a.S <= 0) return 0;
-  int rc = lq_check_cuda(ctx, cudaFuncSetAttribute(group_eval_kernel<n, m, L, NESTED, MINB>,
+  int rc = lq_check_cuda(ctx, cudaFuncSetAttribute(group_eval_kernel<n, m, L, NESTED, MINB, SEEDED>,
                                                    cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Lay::kSmemBytes),
                          "group_eval_kernel smem attribute");
   if (rc) return rc;
-  group_eval_kernel<n, m, L, NESTED, MINB><<<(unsigned)blocks, Lay::kThreads, Lay::kSmemBytes, stream>>>(pb, a);
+  group_eval_kernel<n, m, L, NESTED, MINB, SEEDED><<<(unsigned)blocks, Lay::kThreads, Lay::kSmemBytes, stream>>>(pb, a, sd);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "group_eval_kernel launch");
 }
 
-template <int n, int m, int L, int MINB>
-int launch_group(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
-  if (a.N_min == a.N_max && a.Vn == nullptr) return launch_group_t<n, m, L, false, MINB>(ctx, a, stream);
-  return launch_group_t<n, m, L, true, MINB>(ctx, a, stream);
+template <int n, int m, int L, int MINB, bool SEEDED = false>
+int launch_group(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream, const SeedArgs& sd = SeedArgs{}) {
+  if (a.N_min == a.N_max && a.Vn == nullptr) return launch_group_t<n, m, L, false, MINB, SEEDED>(ctx, a, sd, stream);
+  return launch_group_t<n, m, L, true, MINB, SEEDED>(ctx, a, sd, stream);
 }
 
 }  // namespace
@@ -662,5 +710,12 @@ int lq_launch_eval_group(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream)
     return launch_group<8, 2, 4, 3>(ctx, a, stream);
   }
   if (ctx->n == 6 && ctx->m == 2) return launch_group<6, 2, 2, 2>(ctx, a, stream);
+  return lq_set_error(ctx, LQMPC_EINVAL, "lane-group K1 is built for 6x2 and 8x2");
+}
+
+int lq_launch_eval_group_seeded(lqmpc_ctx* ctx, const EvalArgs& a, uint64_t seed, int64_t first, double e_A, double e_B) {
+  const SeedArgs sd{seed, first, e_A, e_B};
+  if (ctx->n == 8 && ctx->m == 2) return launch_group<8, 2, 4, 3, true>(ctx, a, ctx->stream, sd);
+  if (ctx->n == 6 && ctx->m == 2) return launch_group<6, 2, 2, 2, true>(ctx, a, ctx->stream, sd);
   return lq_set_error(ctx, LQMPC_EINVAL, "lane-group K1 is built for 6x2 and 8x2");
 }

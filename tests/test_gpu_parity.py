@@ -260,6 +260,33 @@ def test_k1_seeded_entry_point(engine):
     assert engine.eval_seeded(1, 0, 0, 0.01, 0.01, 3, 3, want=("J",))["J"].shape == (1, 0)
 
 
+@pytest.mark.parametrize("n,m", [(8, 2), (6, 2)])
+def test_k1_seeded_entry_point_on_lane_groups(engine, n, m, monkeypatch):
+    """lqmpc_eval_seeded at n = 6, 8: every lane of a group draws its own rows from the (sample, pair)-addressed Philox
+    stream. Same checks as above, plus: the lane-group build and the thread-per-sample build (LQMPC_K1_GROUP=0) see the
+    same samples (their tables agree to 1e-9; the evaluation arithmetic differs, the operands do not)."""
+    import torch
+    from oracle import np_batched as nb, np_sampler as ns
+    monkeypatch.delenv("LQMPC_K1_GROUP", raising=False)
+    A, B, Q, R = nb.synth_problem(n, m, seed=1)
+    engine.set_problem(A, B, Q, R, Q, None, None, 30)
+    S, first = 5_003, (1 << 32) - 2000
+    got = engine.eval_seeded(3, first, S, 0.02, 0.005, 4, 6, want=("J", "rho", "ratio", "flags", "moments"))
+    dA, dB, x0 = ns.seeded_samples(3, first, S, n, m, 0.02, 0.005)
+    ref = nb.eval_batch(A, B, Q, R, Q, nb.expert_matrix(A, B, Q, R, Q, 30), dA, dB, x0, 4, 6)
+    for k in ("J", "rho", "ratio"):
+        assert relerr(got[k].cpu().numpy(), ref[k]) < TOL, k
+    assert not got["flags"].cpu().numpy().any()
+    a = engine.eval_seeded(3, first, 3_000, 0.02, 0.005, 4, 6, want=("J", "rho", "ratio"))
+    b = engine.eval_seeded(3, first + 3_000, S - 3_000, 0.02, 0.005, 4, 6, want=("J", "rho", "ratio"))
+    assert torch.equal(torch.cat([a["table"], b["table"]], dim=1), got["table"])
+    one = engine.eval_seeded(3, first, S, 0.02, 0.005, 6, 6, want=("J", "rho"))       # the one-horizon build
+    assert relerr(one["J"].cpu().numpy(), ref["J"][2:3]) < TOL
+    monkeypatch.setenv("LQMPC_K1_GROUP", "0")
+    thr = engine.eval_seeded(3, first, S, 0.02, 0.005, 4, 6, want=("J", "rho", "ratio"))
+    assert relerr(thr["table"].cpu().numpy(), got["table"].cpu().numpy()) < TOL
+
+
 def test_k1_unstable_flagged(engine):
     """An estimated model far from the plant gives an unstable closed loop: J = +inf, flag bit 0, rho >= 1."""
     A = np.array([[1.2, 0.5], [0.0, 1.1]])
