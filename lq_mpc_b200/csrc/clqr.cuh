@@ -25,6 +25,53 @@ struct WsView {
   LQ_HD double& operator[](int64_t e) const { return p[e * stride]; }
 };
 
+// Stage loops over the strided workspace are chains of dependent steps whose first instruction waits for a global
+// load (ncu, round 2: the first use of a stage's gain held 21 % of the sweep kernels' stall samples at 3 warps per
+// scheduler). The addresses do not depend on the data, so the loads of stage k + PF are issued while stage k is
+// computed: `fetch(k, v)` fills v[0..W) for stage k, `body(k, v)` consumes it; stages run in order 0..N-1. The
+// lookahead is a register ring, hence only for the small dimensions; PF = 0 keeps the plain loop.
+#ifndef LQ_K2_PF_SMALL
+#define LQ_K2_PF_SMALL 1      // n m <= 2 (the shipped 2-state example)
+#endif
+#ifndef LQ_K2_PF_MID
+#define LQ_K2_PF_MID 1        // n m <= 4
+#endif
+// Measured on the sweep's two launches (scripts/k2_probe.py, 1e6 samples, N = 5 / 10 / 25 / 50 summed), (n, m) = (2, 1):
+// depth 1 at 3 CTAs/SM (160 registers, no spills) 9.99 ms ring solves / 3.05 ms closed loops; no lookahead 13.9 / 3.6-4.0;
+// depth 2: 12.0 / 3.45; depth 4: 13.9 / 3.6 at 214 registers, 16.4 / 4.7 held to 168 (the ring spills); 4 or 5 CTAs/SM
+// (128 / 96 registers) lose to their spills at every depth.
+template <int n, int m>
+struct StagePrefetch {
+  static constexpr int depth = (n * m <= 2) ? LQ_K2_PF_SMALL : ((n * m <= 4) ? LQ_K2_PF_MID : 0);
+};
+
+template <int W, int PF, class Fetch, class Body>
+LQ_HD void staged_loop(int N, Fetch fetch, Body body) {
+  if (PF == 0) {
+    for (int k = 0; k < N; ++k) {
+      double v[W];
+      fetch(k, v);
+      body(k, v);
+    }
+    return;
+  }
+  constexpr int D = (PF > 0) ? PF : 1;
+  double ring[D][W];
+  LQ_UNROLL for (int q = 0; q < D; ++q)
+    if (q < N) fetch(q, ring[q]);
+  for (int k0 = 0; k0 < N; k0 += D) {
+    LQ_UNROLL for (int q = 0; q < D; ++q) {
+      const int k = k0 + q;
+      if (k < N) {
+        double v[W];
+        LQ_UNROLL for (int e = 0; e < W; ++e) v[e] = ring[q][e];
+        if (k + D < N) fetch(k + D, ring[q]);
+        body(k, v);
+      }
+    }
+  }
+}
+
 // Shared references of LQ_MPC_Controller.solve (utils_class.py:48-81): x_ref[:, i] is the reference of x_{i+1},
 // u_ref[:, i] of u_i (row-major, leading dimension ld >= N; only the first N columns are read). NULL = zeros, which is
 // what every caller in the reference passes; non-zero references make the law affine and disable the Riccati fast path.
@@ -97,6 +144,10 @@ template <int n, int m>
 struct Plan {
   double Ah[n * n], Bh[n * m];
   double P0[n * n];  // unconstrained horizon-N cost-to-go: V_N = x0' P0 x0 when no bound is active
+  // unconstrained first-stage gain: the certificate's fast path reads it every closed-loop step. Register-resident for
+  // the small dimensions only (the n >= 6 instantiations already spill; they re-read it from the workspace).
+  static constexpr bool kHoldK0 = (n * m <= 8);
+  double K0[kHoldK0 ? m * n : 1];
   double cstar;      // feasibility certificate: x0' P0 x0 <= cstar  =>  the whole unconstrained plan stays inside the box
 };
 
@@ -114,6 +165,9 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
     double K[m * n];
     riccati_gain<n, m>(st, pl.Ah, K);
     LQ_UNROLL for (int e = 0; e < m * n; ++e) ws[L.oKu + (int64_t)k * (m * n) + e] = K[e];
+    if (Plan<n, m>::kHoldK0 && k == 0) {
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) pl.K0[Plan<n, m>::kHoldK0 ? e : 0] = K[e];
+    }
     riccati_update<n, m>(st, pl.Ah, pb.Q, P);
     // S_k: where a constrained sweep may start when every clamped input sits at an earlier stage (clqr_backward)
     {
@@ -147,9 +201,10 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
       double Phi[n * n];
       LQ_UNROLL for (int i = 0; i < n; ++i)
         LQ_UNROLL for (int j = 0; j < n; ++j) Phi[i * n + j] = (i == j) ? 1.0 : 0.0;
-      for (int k = 0; k < N; ++k) {
-        double K[m * n], g[m * n], Acl[n * n], Pn[n * n];
-        LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+      staged_loop<m * n, StagePrefetch<n, m>::depth>(N, [&](int k, double* v) {
+        LQ_UNROLL for (int e = 0; e < m * n; ++e) v[e] = ws[L.oKu + (int64_t)k * (m * n) + e];
+      }, [&](int k, const double* K) {
+        double g[m * n], Acl[n * n], Pn[n * n];
         mm<m, n, n>(K, Phi, g);
         LQ_UNROLL for (int j = 0; j < m; ++j) {             // y = L^-1 g_j' (forward substitution), q = y'y = g_j P0^-1 g_j'
           double y[n], q = 0.0;
@@ -171,7 +226,7 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
           mm<n, n, n>(Acl, Phi, Pn);
           LQ_UNROLL for (int i = 0; i < n * n; ++i) Phi[i] = Pn[i];
         }
-      }
+      });
       if (cs == cs) pl.cstar = cs * (1.0 - 1e-9);
     }
   } else {
@@ -338,9 +393,13 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     // ---- 0. regulation: inside the certificate ellipsoid the unconstrained plan is feasible, hence optimal
     const double V0 = quad<n>(x0, pl.P0, x0);
     if (V0 <= pl.cstar) {
-      double K[m * n];
-      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + e];
-      mv<m, n>(K, x0, u0);
+      if (Plan<n, m>::kHoldK0) {
+        mv<m, n>(pl.K0, x0, u0);
+      } else {
+        double K[m * n];
+        LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[L.oKu + e];
+        mv<m, n>(K, x0, u0);
+      }
       *V = V0;
       return flags;
     }
@@ -350,13 +409,14 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = x0[i];
   const double c0 = quad<n>(x0, pb.Q, x0);
   double cost_u = c0;
-  for (int k = 0; k < N; ++k) {
-    double K[m * n];
-    LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[oK + (int64_t)k * (m * n) + e];
+  staged_loop<m * n + m, StagePrefetch<n, m>::depth>(N, [&](int k, double* v) {
+    LQ_UNROLL for (int e = 0; e < m * n; ++e) v[e] = ws[oK + (int64_t)k * (m * n) + e];
+    LQ_UNROLL for (int j = 0; j < m; ++j) v[m * n + j] = trk ? ws[L.okc + (int64_t)k * m + j] : 0.0;
+  }, [&](int k, const double* K) {
     mv<m, n>(K, x, u);
     const bool was_feas = feas;
     LQ_UNROLL for (int j = 0; j < m; ++j) {
-      if (trk) u[j] += ws[L.okc + (int64_t)k * m + j];
+      if (trk) u[j] += K[m * n + j];
       if (k == 0) u0[j] = u[j];
       if (u[j] < pb.ulo[j] || u[j] > pb.uhi[j]) feas = false;
       const int bit = k * m + j;
@@ -392,7 +452,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       cost_u += (k == N - 1) ? quad<n>(dx, pb.Pt, dx) : quad<n>(dx, pb.Q, dx);
     }
     LQ_UNROLL for (int i = 0; i < n; ++i) x[i] = xn[i];
-  }
+  });
   if (feas) {
     *V = trk ? cost_u : quad<n>(x0, pl.P0, x0);
     return flags;
@@ -423,20 +483,26 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
     bool block_hi = false;
     LQ_UNROLL for (int i = 0; i < n; ++i) { x[i] = x0[i]; ws[L.oxs + i] = x0[i]; }
     cost = c0;
-    for (int k = 0; k < N; ++k) {
-      double K[m * n];
+    // per stage: the gain, its offset (zero beyond klast: unconstrained law) and the current iterate z_k
+    staged_loop<m * n + 2 * m, StagePrefetch<n, m>::depth>(N, [&](int k, double* v) {
+      const bool tl = (k > klast);
+      const int64_t og = tl ? L.oKu : L.oKc;
+      LQ_UNROLL for (int e = 0; e < m * n; ++e) v[e] = ws[og + (int64_t)k * (m * n) + e];
+      LQ_UNROLL for (int j = 0; j < m; ++j) {
+        v[m * n + j] = tl ? 0.0 : ws[L.okc + (int64_t)k * m + j];
+        v[m * n + m + j] = ws[oz + (int64_t)k * m + j];
+      }
+    }, [&](int k, const double* K) {
       const bool tail = (k > klast);                       // unconstrained law (zero offset) beyond klast
-      const int64_t og = tail ? L.oKu : L.oKc;
-      LQ_UNROLL for (int e = 0; e < m * n; ++e) K[e] = ws[og + (int64_t)k * (m * n) + e];
       mv<m, n>(K, x, u);
       LQ_UNROLL for (int j = 0; j < m; ++j) {
-        if (!tail) u[j] += ws[L.okc + (int64_t)k * m + j];
+        if (!tail) u[j] += K[m * n + j];
         const int bit = k * m + j;
         const bool isfx = fixed.test(bit);
         if (isfx) u[j] = athi.test(bit) ? pb.uhi[j] : pb.ulo[j];
         ws[ozs + (int64_t)k * m + j] = u[j];
         if (!isfx) {
-          const double zc = ws[oz + (int64_t)k * m + j];
+          const double zc = K[m * n + m + j];
           if (u[j] > pb.uhi[j]) {
             const double a = (pb.uhi[j] - zc) / (u[j] - zc);
             if (a < alpha) { alpha = a; block = k * m + j; block_hi = true; }
@@ -458,7 +524,7 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
       if (k <= klast || k == N - 1) {
         LQ_UNROLL for (int i = 0; i < n; ++i) ws[L.oxs + (int64_t)(k + 1) * n + i] = xn[i];
       }
-    }
+    });
     if (block >= 0) {
       // partial step to the blocking bound, which joins the working set
       if (alpha < 0.0) alpha = 0.0;

@@ -15,8 +15,14 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   return v;
 }
 
+// CTAs per SM the register allocation of the n m <= 2 instantiation is held to (1 = unconstrained; A/B switch).
+// Measured on cfg-sweep-f (bounds phase of 5e7 evals): unconstrained (162 registers, 3 CTAs/SM) 0.314 s,
+// 4 (128 registers, 96 B of stack) 0.293 s, 5 (96 registers, 200 B) 0.303 s.
+#ifndef LQ_K3_MINB_SMALL
+#define LQ_K3_MINB_SMALL 4
+#endif
 template <int n, int m>
-__global__ void __launch_bounds__(128) bounds_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+__global__ void __launch_bounds__(128, (n * m <= 2) ? LQ_K3_MINB_SMALL : 1) bounds_kernel(const __grid_constant__ lq::Problem<n, m> pb,
                                                      const __grid_constant__ BoundsArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;

@@ -16,6 +16,16 @@ __device__ __forceinline__ double ld_stream(const double* p) {
   return v;
 }
 
+// CTAs per SM the register allocation of the n m <= 2 instantiations is held to (1 = unconstrained). 3 -> 160 registers
+// without spills; measured with the stage lookahead of clqr.cuh (see StagePrefetch).
+#ifndef LQ_K2_MINB_SMALL
+#define LQ_K2_MINB_SMALL 3
+#endif
+template <int n, int m>
+struct K2Occupancy {
+  static constexpr int min_blocks = (n * m <= 2) ? LQ_K2_MINB_SMALL : 1;
+};
+
 template <int n, int m>
 __device__ __forceinline__ void load_plan(const MpcArgs& a, const lq::Problem<n, m>& pb, int64_t s,
                                           lq::Plan<n, m>& pl) {
@@ -26,7 +36,7 @@ __device__ __forceinline__ void load_plan(const MpcArgs& a, const lq::Problem<n,
 }
 
 template <int n, int m, bool POLY>
-__global__ void __launch_bounds__(128) mpc_solve_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+__global__ void __launch_bounds__(128, K2Occupancy<n, m>::min_blocks) mpc_solve_kernel(const __grid_constant__ lq::Problem<n, m> pb,
                                                         const __grid_constant__ MpcArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;
@@ -77,7 +87,7 @@ struct DevTraj {
 };
 
 template <int n, int m, bool POLY>
-__global__ void __launch_bounds__(128) simulate_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+__global__ void __launch_bounds__(128, K2Occupancy<n, m>::min_blocks) simulate_kernel(const __grid_constant__ lq::Problem<n, m> pb,
                                                        const __grid_constant__ MpcArgs a) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int64_t nthreads = (int64_t)gridDim.x * blockDim.x;

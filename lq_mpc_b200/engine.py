@@ -13,7 +13,7 @@ from typing import Optional
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "_lib", "liblqmpc_b200.so")
+LIB_PATH = os.environ.get("LQMPC_LIB") or os.path.join(_PKG, "_lib", "liblqmpc_b200.so")   # LQMPC_LIB: A/B builds (scripts/unit_variants.sh)
 
 FLAG_UNSTABLE = 1
 FLAG_QP_ACTIVE = 2
