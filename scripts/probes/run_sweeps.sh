@@ -1,5 +1,5 @@
 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
-for v in "" k3b4 k3b5; do
+for v in "" $VARIANTS; do
   if [ -n "$v" ]; then export LQMPC_LIB=$PWD/lq_mpc_b200/_lib/variants/$v.so; fi
   python bench.py --workload cfg-sweep-f --no-cpu-baseline > gpurun_out/sweep_$v.json 2> gpurun_out/sweep_$v.err
   python -c "
