@@ -153,7 +153,7 @@ struct Plan {
 
 // Unconstrained Riccati sweep; stores the gains K_k (u_k = K_k x_k) for k = 0..N-1 in the workspace.
 template <int n, int m>
-LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsView& ws) {
+LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsView& ws, bool certificate = true) {
   const ClqrLayout<n, m> L(N);
   double P[n * n];
   LQ_UNROLL for (int i = 0; i < n * n; ++i) P[i] = pb.Pt[i];
@@ -185,8 +185,11 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
   // anyway: it is V_N) instead of an N-stage rollout. Sufficient, not necessary — outside the ellipsoid the rollout
   // decides as before, so nothing is approximated. In the closed loops of the sweeps the state enters the ellipsoid
   // after the first few steps. (1 - 1e-9 margin against rounding in cstar itself.)
+  // `certificate = false` (the ring solves: a handful of states per sample, chosen OUTSIDE the region where the
+  // unconstrained law is feasible) skips the N-stage construction — it costs about 1.7 clipped rollouts — and leaves
+  // cstar = -1: every solve then decides feasibility by its rollout, exactly as before the certificate existed.
   pl.cstar = -1.0;
-  if (pb.has_bounds) {
+  if (pb.has_bounds && certificate) {
     double Lc[n * n], Lci[n];
     LQ_UNROLL for (int i = 0; i < n * n; ++i) Lc[i] = P[i];
     bool okc = chol_inv<n>(Lc, Lci);
@@ -229,7 +232,7 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
       });
       if (cs == cs) pl.cstar = cs * (1.0 - 1e-9);
     }
-  } else {
+  } else if (!pb.has_bounds) {
     pl.cstar = HUGE_VAL;             // no input bounds at all: every plan is feasible
   }
   return flags;

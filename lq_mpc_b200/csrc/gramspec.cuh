@@ -29,8 +29,8 @@ namespace lq {
 
 // Square-root-free factorisation test of a small symmetric matrix: G = L D L' (unit lower L left below the diagonal),
 // reciprocals of the pivots in dinv (MUFU.RCP64H + 2 Newton steps instead of the ~30-instruction FP64 rsqrt of a
-// Cholesky: ncu showed 8 % of the kernel's instructions there). Returns "every pivot is positive"; a non-positive or
-// NaN pivot is replaced by 1 so that nothing downstream overflows (the probe has failed anyway).
+// Cholesky: ncu showed 8 % of the kernel's instructions there). Returns "every pivot is positive" (a positive normal
+// number: a denormal pivot counts as zero); a non-positive or NaN pivot is replaced by 1 so that nothing downstream overflows (the probe has failed anyway).
 template <int m>
 LQ_HD bool ldl_pos(double* G, double* dinv) {
   bool ok = true;
@@ -42,7 +42,7 @@ LQ_HD bool ldl_pos(double* G, double* dinv) {
       w[k] = G[j * m + k] * dv[k];
       d = fma(-G[j * m + k], w[k], d);
     }
-    const bool pos = (d > 0.0) && (d < 1.7e308);
+    const bool pos = is_pos_normal(d);           // integer pipe: the probes are FP64-pipe bound
     ok = ok && pos;
     d = pos ? d : 1.0;
     dv[j] = d;

@@ -46,7 +46,7 @@ __global__ void __launch_bounds__(128, K2Occupancy<n, m>::min_blocks) mpc_solve_
   for (int64_t s = tid; s < a.S; s += nthreads) {
     lq::Plan<n, m> pl;
     load_plan<n, m>(a, pb, s, pl);
-    const int pf = lq::plan_prepare<n, m>(pb, pl, a.N, ws);
+    const int pf = lq::plan_prepare<n, m>(pb, pl, a.N, ws, /*certificate=*/false);
     const int P = a.pts ? a.npts : 1;
     double mv = -HUGE_VAL;
     for (int p = 0; p < P; ++p) {

@@ -41,6 +41,18 @@ LQ_HD uint32_t abs_hi(double v) {
   return (uint32_t)(b >> 32) & 0x7fffffffu;
 #endif
 }
+// "v is a positive NORMAL finite number", decided on the high word (one integer subtract + compare instead of two
+// FP64-pipe DSETPs): sign clear and exponent field in [1, 0x7fe]. NaN, Inf, zero, negatives and denormals are false.
+LQ_HD bool is_pos_normal(double v) {
+#if defined(__CUDA_ARCH__)
+  const uint32_t h = (uint32_t)__double2hiint(v);
+#else
+  uint64_t b;
+  memcpy(&b, &v, sizeof(b));
+  const uint32_t h = (uint32_t)(b >> 32);
+#endif
+  return (h - 0x00100000u) < 0x7fe00000u;
+}
 LQ_HD double from_abs_hi(uint32_t h) {
 #if defined(__CUDA_ARCH__)
   return __hiloint2double((int)h, 0);
