@@ -230,11 +230,11 @@ LQ_HD double spectral_radius_qr(const double* Ain, bool* ok) {
 // max modulus of the roots of x^2 + p x + q, and (re, im >= 0) of the root attaining it
 LQ_HD double quad_rho(double p, double q, double* re, double* im, double* sq_abs_disc) {
   const double disc = fma(p, p, -4.0 * q);
-  const double sd = sqrt(fabs(disc));
+  const double sd = sqrt_fast(fabs(disc));
   *sq_abs_disc = sd;
   if (disc < 0.0) {
     *re = -0.5 * p; *im = 0.5 * sd;
-    return sqrt(fabs(q));
+    return sqrt_fast(fabs(q));
   }
   const double r = -0.5 * (p + dsign(sd, p));   // larger-magnitude root (no cancellation)
   *re = r; *im = 0.0;
@@ -251,12 +251,12 @@ LQ_HD double cubic_largest_real_root(double A, double B, double C) {
   const double D = fma(hq, hq, tp * tp * tp);
   double y;
   if (D > 0.0) {
-    const double sD = sqrt(D);
+    const double sD = sqrt_fast(D);
     const double u = cbrt(hq + dsign(sD, hq));
     y = (u != 0.0) ? u - tp / u : 0.0;
   } else {
     const double t2 = -tp;                                          // >= 0 here
-    const double t = sqrt(t2);
+    const double t = sqrt_fast(t2);
     double arg = (t2 > 0.0) ? hq / (t2 * t) : 0.0;
     arg = dmin(1.0, dmax(-1.0, arg));
     y = 2.0 * t * cos(acos(arg) * third);
@@ -265,8 +265,8 @@ LQ_HD double cubic_largest_real_root(double A, double B, double C) {
   LQ_UNROLL for (int it = 0; it < 2; ++it) {
     const double g = fma(fma(z + A, z, B), z, C);
     const double dg = fma(fma(3.0, z, 2.0 * A), z, B);
-    if (dg > 0.0) {                     // at the largest real root the slope is >= 0; never step on a flat spot
-      const double zn = z - g / dg;
+    if (dg > 1e-290) {                  // at the largest real root the slope is >= 0; never step on a flat spot
+      const double zn = fma(-g, rcp(dg), z);
       z = (zn == zn) ? zn : z;
     }
   }
@@ -284,10 +284,10 @@ LQ_HD bool quartic_rho(double a, double b, double c, double d, double* rho_out) 
   const double B3 = fma(p, p, -4.0 * r);
   double z = cubic_largest_real_root(2.0 * p, B3, -q * q);
   z = dmax(z, 0.0);
-  const double alpha = sqrt(z);
+  const double alpha = sqrt_fast(z);
   double w;                                                           // w = q / alpha, stable for alpha -> 0 too
   if (z > 1e-6) w = q * rcp(alpha);
-  else w = dsign(sqrt(dmax(fma(z, z + 2.0 * p, B3), 0.0)), q);
+  else w = dsign(sqrt_fast(dmax(fma(z, z + 2.0 * p, B3), 0.0)), q);
   const double beta = 0.5 * (p + z - w);
   // first factor in x: x^2 + p1 x + q1
   double p1 = fma(0.5, a, alpha);
@@ -319,7 +319,7 @@ LQ_HD bool quartic_rho(double a, double b, double c, double d, double* rho_out) 
   const double dpq = first ? (p2 - p1) : (p1 - p2), dqq = first ? (q2 - q1) : (q1 - q2);
   const double re = first ? re1 : re2, im = first ? im1 : im2, sd = first ? sd1 : sd2;
   const double gr = fma(dpq, re, dqq), gi = dpq * im;
-  const double fprime = sd * sqrt(fma(gr, gr, gi * gi));
+  const double fprime = sd * sqrt_fast(fma(gr, gr, gi * gi));
   *rho_out = rho;
   const bool small_rem = (fabs(r1) + fabs(r0)) <= 2e-14;
   return small_rem && (fprime * rho >= 4e-5) && (rho == rho);

@@ -30,6 +30,14 @@
 namespace {
 
 constexpr int kT = 128;
+#ifndef LQ_K4_KUNROLL
+#define LQ_K4_KUNROLL 8          // k-steps of a warp tile unrolled together: 1 / 2 / 4 / 8 measured 36.9 / 34.75 / 34.2 / 33.6 ms per 1.25e5 evals at 32 x 8 x 30
+#endif
+constexpr int kKUnroll = LQ_K4_KUNROLL;
+#ifndef LQ_K4_SPLIT1
+#define LQ_K4_SPLIT1 0           // single-tile products in two interleaved accumulator chains: measured SLOWER (34.0 vs 33.6 ms) — with 5 CTAs/SM the pipe, not the chain latency, is the limit
+#endif
+constexpr bool kSplitSkinny = (LQ_K4_SPLIT1 != 0);
 #ifndef LQ_K4_DMMA_DEFAULT
 #define LQ_K4_DMMA_DEFAULT true   // measured: tensor-core MMAs beat the DFMA evaluation of the same tiles
 #endif
@@ -154,8 +162,21 @@ __device__ __forceinline__ void warp_mma(int K, int r0, int c0, FA fa, FB fb, do
   for (int i = 0; i < MT; ++i)
 #pragma unroll
     for (int j = 0; j < NT; ++j) c[i][j][0] = c[i][j][1] = 0.0;
-  if (DM) {
-#pragma unroll 2
+  if (DM && MT * NT == 1 && kSplitSkinny) {
+    // one 8 x 8 output tile: its K / 4 MMAs would form ONE dependent chain (the skinny products P B^, Z, G — the last
+    // two sit on the chain warp's critical path). Two accumulators over alternating k-steps halve the chain.
+    double d0 = 0.0, d1 = 0.0;
+#pragma unroll kKUnroll
+    for (int k0 = 0; k0 < K; k0 += 8) {
+      const double a0 = fa(r0 + g, k0 + tg), b0 = fb(k0 + tg, c0 + g);
+      const double a1 = fa(r0 + g, k0 + 4 + tg), b1 = fb(k0 + 4 + tg, c0 + g);
+      dmma_m8n8k4(c[0][0][0], c[0][0][1], a0, b0);
+      dmma_m8n8k4(d0, d1, a1, b1);
+    }
+    c[0][0][0] += d0;
+    c[0][0][1] += d1;
+  } else if (DM) {
+#pragma unroll kKUnroll
     for (int k0 = 0; k0 < K; k0 += 4) {
       double av[MT], bv[NT];
 #pragma unroll

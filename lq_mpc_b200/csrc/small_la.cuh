@@ -190,6 +190,17 @@ LQ_HD double rsqrt_pos(double d) {
 #endif
 }
 
+// sqrt(x) for x >= 0 through the reciprocal square root above (x * rsqrt(x): <= 2 ulp, no slow path); zero and
+// denormals return 0. For the closed-form eigenvalue path, whose inputs are scaled to O(1) and whose results pass an
+// a-posteriori acceptance test. Host build: plain sqrt.
+LQ_HD double sqrt_fast(double x) {
+#if defined(__CUDA_ARCH__)
+  return is_pos_normal(x) ? x * rsqrt_pos(x) : 0.0;
+#else
+  return sqrt(x);
+#endif
+}
+
 template <int m>
 LQ_HD bool chol_inv(double* G, double* dinv) {
   bool ok = true;
