@@ -447,7 +447,12 @@ class Engine:
         dA, dB = self._opt_dev(dA), self._opt_dev(dB)
         if S is None:
             S = dA.shape[-1] if dA is not None else (x0.shape[-1] if x0 is not None else 1)
-        xs = None if x0_shared is None else self._dev(np.asarray(x0_shared, dtype=np.float64).reshape(n))
+        if x0_shared is None:
+            xs = None
+        elif isinstance(x0_shared, torch.Tensor):               # already staged by the caller (no per-call H2D copy)
+            xs = self._dev(x0_shared).reshape(n)
+        else:
+            xs = self._dev(np.asarray(x0_shared, dtype=np.float64).reshape(n))
         x0_d = self._opt_dev(x0)
         out = {}
         if "J_T" in want:
