@@ -5,6 +5,7 @@
 // One sample per thread, grid-stride over the batch; the per-thread scratch of clqr.cuh (gains, plan, trajectory)
 // lives in a global workspace laid out [element][thread] so that a warp touches 32 consecutive doubles per access.
 #pragma once
+#include <stdlib.h>
 #include "pclqr.cuh"
 #include "engine.h"
 
@@ -120,7 +121,17 @@ int launch_mpc_t(lqmpc_ctx* ctx, MpcArgs a, bool sim) {
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, ctx->device);
   const int threads = 128;
   int64_t blocks = (a.S + threads - 1) / threads;
-  const int64_t cap = (int64_t)sms * 16;   // grid-stride beyond this; bounds the workspace
+  // Grid-stride beyond `cap` CTAs; the per-thread workspace is sized by the LAUNCHED threads. With one wave of resident
+  // CTAs every thread keeps rewriting the same few kB, which the 126 MB L2 partly absorbs (N = 50, 1e6 samples:
+  // ring solves 5.22 -> 4.66 ms, closed loops 1.56 -> 1.46); short horizons have little scratch and prefer the
+  // finer-grained balance of three waves (measured 1 / 2 / 3 waves and the former 16 CTAs per SM, scripts/k2_probe.py).
+  int occ = 0;
+  if (sim) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, simulate_kernel<n, m, POLY>, threads, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, mpc_solve_kernel<n, m, POLY>, threads, 0);
+  if (occ < 1) occ = 1;
+  int waves = (a.N >= 20) ? 1 : 3;
+  if (const char* wv = getenv("LQMPC_K2_WAVES")) { if (atoi(wv) > 0) waves = atoi(wv); }   // A/B switch
+  const int64_t cap = (int64_t)sms * occ * waves;
   if (blocks > cap) blocks = cap;
   const int64_t nthreads = blocks * threads;
   const int64_t per = lq::clqr_ws_doubles<n, m>(a.N);
