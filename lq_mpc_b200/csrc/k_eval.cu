@@ -41,8 +41,8 @@ struct DeviceSink {
 };
 
 // MINB = minimum resident CTAs per SM the register allocator must allow (occupancy vs. spills; see K1Tune below)
-template <int n, int m, int MINB>
-__global__ void __launch_bounds__(128, MINB) eval_kernel(const __grid_constant__ lq::Problem<n, m> pb,
+template <int n, int m, int MINB, int THREADS = 128>
+__global__ void __launch_bounds__(THREADS, MINB) eval_kernel(const __grid_constant__ lq::Problem<n, m> pb,
                                                          const __grid_constant__ EvalArgs a) {
   const int64_t s = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (s >= a.S) return;
@@ -82,6 +82,15 @@ __global__ void prepare_kernel(lq::Problem<n, m>* pb, int N_opc) {
 }
 
 // Register budget per (n, m) and mode: 128-thread CTAs, MINB CTAs/SM -> 65536 / (128 MINB) registers per thread.
+#ifndef LQ_K1_THREADS_SINGLE
+// CTA size / resident CTAs of the one-horizon launch (A/B switches). Registers map to resident warps in steps of four
+// (255 -> 8, 168 -> 12, 128 -> 16 warps per SM), so smaller CTAs open no new occupancy point; at 8 warps per SM CTAs of
+// 128 / 64 / 32 threads measured 3.425 / 3.416 / 3.409 ms per 1.25e7 evals (within run-to-run noise): 128 stays.
+#define LQ_K1_THREADS_SINGLE 128
+#endif
+#ifndef LQ_K1_MINB_SINGLE
+#define LQ_K1_MINB_SINGLE 2
+#endif
 template <int n, int m>
 struct K1Tune {
   // measured on B200 (scripts/k1_probe.py and k1_sustained_probe.py, n=4 m=2, 1.25e7 samples). From a cold power state
@@ -89,7 +98,8 @@ struct K1Tune {
   // kernel runs into the board's power cap and SUSTAINED the spill-free 255-register build wins clearly
   // (3.49 / 3.73 / 3.89 / 3.97 ms: spill traffic and the extra instructions cost power, i.e. clock). With all horizons
   // 1..10 emitted the order flips (18.0 / 16.4 / 15.9 / 15.6 ms sustained): occupancy hides the per-horizon stores.
-  static constexpr int minb_single = 2;                 // N_min == N_max
+  static constexpr int minb_single = LQ_K1_MINB_SINGLE;       // N_min == N_max
+  static constexpr int threads_single = LQ_K1_THREADS_SINGLE;
   static constexpr int minb_nested = (n <= 4) ? 4 : 2;  // several horizons per sample
 };
 
@@ -112,9 +122,12 @@ int launch_eval_t(lqmpc_ctx* ctx, const EvalArgs& a, cudaStream_t stream) {
     return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
   }
 #endif
-  if (a.N_min == a.N_max)
-    eval_kernel<n, m, K1Tune<n, m>::minb_single><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
-  else
+  if (a.N_min == a.N_max) {
+    constexpr int ts = (n <= 4) ? K1Tune<n, m>::threads_single : 128, mb = (n <= 4) ? K1Tune<n, m>::minb_single : 2;
+    const int64_t bs = (a.S + ts - 1) / ts;
+    if (bs > 0x7fffffffLL) return lq_set_error(ctx, LQMPC_EINVAL, "batch too large for one launch");
+    eval_kernel<n, m, mb, ts><<<(unsigned)bs, ts, 0, stream>>>(pb, a);
+  } else
     eval_kernel<n, m, K1Tune<n, m>::minb_nested><<<(unsigned)blocks, threads, 0, stream>>>(pb, a);
   ctx->launches++;
   return lq_check_cuda(ctx, cudaGetLastError(), "eval_kernel launch");
