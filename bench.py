@@ -49,9 +49,9 @@ WORKLOADS = {
 }
 # ncu `sm__pipe_fp64_cycles_active` of the dominant kernel from the committed captures (profiles/README.md): what the
 # pipe actually did, next to the algorithmic fraction
-PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02_k1_eval_4x2_metrics.csv", 0.636),
-                   "cfg-synth-32-8-30": ("profiles/r02d_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.656),
-                   "cfg-sweep-f": ("profiles/r02c_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.741),
+PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02f_k1_eval_4x2_metrics.csv", 0.653),
+                   "cfg-synth-32-8-30": ("profiles/r02f_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.681),
+                   "cfg-sweep-f": ("profiles/r02f_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.762),
                    "probe-8-2-10": ("profiles/r02d_k1_group_eval_8x2_metrics.csv", 0.333)}
 
 
@@ -715,7 +715,7 @@ def measure_sweep(cx, wl, reps=1):
                                           "(k3_flops_per_eval), summed over N = 1..%d" % wl["nmax"],
                      "pipe_active_ncu": PIPE_ACTIVE_NCU["cfg-sweep-f"][1],
                      "pipe_active_ncu_source": PIPE_ACTIVE_NCU["cfg-sweep-f"][0],
-                     "traffic": _json_field("profiles/r02c_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
+                     "traffic": _json_field("profiles/r02f_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
                      "traffic_note": "ncu capture of ONE bounds_kernel launch (N = 50, 1e6 samples): operands + outputs "
                                      "(6 + 31 doubles per sample), no scratch"},
         "gpu_launches": int(launches), "sampler_seconds": t_gen, "clocks": clocks,
