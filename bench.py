@@ -51,7 +51,7 @@ WORKLOADS = {
 # pipe actually did, next to the algorithmic fraction
 PIPE_ACTIVE_NCU = {"cfg-synth-4-2-10": ("profiles/r02f_k1_eval_4x2_metrics.csv", 0.653),
                    "cfg-synth-32-8-30": ("profiles/r02f_k4a_tiled_eval_32x8_metrics.csv (DMMA sub-pipe)", 0.681),
-                   "cfg-sweep-f": ("profiles/r02f_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.762),
+                   "cfg-sweep-f": ("profiles/r02f_sweepN50_k2a_k2b_k3_metrics.csv (bounds_kernel<2,1>, N = 50)", 0.742),
                    "probe-8-2-10": ("profiles/r02d_k1_group_eval_8x2_metrics.csv", 0.333)}
 
 
