@@ -293,13 +293,20 @@ int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, c
   cudaStream_t s_in = ctx->pipe_stream[0], s_out = ctx->pipe_stream[1], s_cmp = ctx->stream;
   rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_cmp), "pre-pipeline sync");
   if (rc) return rc;
-  // three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the two kernels of chunk c (which share one scratch)
-  const int64_t nchunks = (S + chunk - 1) / chunk;
-  for (int64_t c = 0; c < nchunks; ++c) {
+  // three streams: H2D of chunk c+1 and D2H of chunk c-1 overlap the two kernels of chunk c (which share one scratch).
+  // The first chunk's H2D is the one copy nothing can hide, so the chunks RAMP: they start at chunk / 8 and grow by 11/8
+  // — a chunk's H2D (10.5 kB per sample at 32 x 8 over ~54 GB/s) takes 0.72 of the previous chunk's kernel time at
+  // cfg 5, so every later copy stays hidden — until they reach `chunk`. (Fixed chunks of 16 384 left 3.2 ms of the
+  // 36.8 ms step exposed: e2e 3.40e6 vs 3.74e6 evals/s device-resident.)
+  int64_t cur = chunk / 8;
+  if (cur < 512) cur = 512;
+  cur = (cur + 1) & ~(int64_t)1;
+  if (cur > chunk) cur = chunk;
+  int64_t s0 = 0;
+  for (int64_t c = 0; s0 < S; ++c) {
     const int b = (int)(c & 1);
     cudaEvent_t ev_in = ctx->tp_ev[b], ev_cmp = ctx->tp_ev[2 + b], ev_out = ctx->tp_ev[4 + b];
-    const int64_t s0 = c * chunk;
-    const int64_t cs = (s0 + chunk <= S) ? chunk : (S - s0);
+    const int64_t cs = (s0 + cur <= S) ? cur : (S - s0);
     double* d_dA = reinterpret_cast<double*>(ctx->pipe_buf[b]);
     double* d_dB = d_dA + (int64_t)n * n * chunk;
     double* d_x0 = d_dB + (int64_t)n * m * chunk;
@@ -331,6 +338,9 @@ int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_h, c
       LQ_PIPE(cudaMemcpy2DAsync(flags_h + s0, (size_t)S * 4, d_flags, (size_t)cs * 4, (size_t)cs * 4, (size_t)H,
                                 cudaMemcpyDeviceToHost, s_out), "D2H flags");
     LQ_PIPE(cudaEventRecord(ev_out, s_out), "record D2H");
+    s0 += cs;
+    cur = (cur * 11 / 8 + 1) & ~(int64_t)1;
+    if (cur > chunk) cur = chunk;
   }
   rc = lq_check_cuda(ctx, cudaStreamSynchronize(s_out), "pipeline sync (D2H)");
   if (rc) return rc;
