@@ -117,9 +117,13 @@ struct Mask128 {   // (name kept from the 128-bit first version)
   }
 };
 
+#ifndef LQ_K2_STORED_P
+#define LQ_K2_STORED_P 12
+#endif
+constexpr int kStoredCostToGo = LQ_K2_STORED_P;
 template <int n, int m>
 struct ClqrLayout {
-  int N;
+  int N, kp;
   int64_t oKu, oKc, okc, oz, ozs, oxs, oP, total;
   static constexpr int np = n * (n + 1) / 2;      // packed upper triangle of a symmetric n x n matrix
   LQ_HD explicit ClqrLayout(int N_) : N(N_) {
@@ -129,8 +133,12 @@ struct ClqrLayout {
     oz = okc + (int64_t)N * m;
     ozs = oz + (int64_t)N * m;
     oxs = ozs + (int64_t)N * m;
-    oP = oxs + (int64_t)(N + 1) * n;              // unconstrained cost-to-go S_k of every stage (packed), k = 0..N-1
-    total = oP + (int64_t)N * np;
+    // unconstrained cost-to-go S_k (packed) of the FIRST kp stages only: a constrained sweep restarts from S_{klast+1},
+    // and in the sweeps the inputs saturate during the first steps; a working set reaching a later stage takes the full
+    // N-stage sweep instead (exact either way). Storing all N stages was 1.2 of the 4.9 kB written per sample at N = 50.
+    kp = (N < kStoredCostToGo) ? N : kStoredCostToGo;
+    oP = oxs + (int64_t)(N + 1) * n;
+    total = oP + (int64_t)kp * np;
   }
 };
 
@@ -170,7 +178,7 @@ LQ_HD int plan_prepare(const Problem<n, m>& pb, Plan<n, m>& pl, int N, const WsV
     }
     riccati_update<n, m>(st, pl.Ah, pb.Q, P);
     // S_k: where a constrained sweep may start when every clamped input sits at an earlier stage (clqr_backward)
-    {
+    if (k < L.kp) {
       int e = 0;
       LQ_UNROLL for (int i = 0; i < n; ++i)
         LQ_UNROLL for (int j = i; j < n; ++j) { ws[L.oP + (int64_t)k * L.np + e] = P[i * n + j]; ++e; }
@@ -475,7 +483,8 @@ LQ_HD int clqr_solve(const Problem<n, m>& pb, const Plan<n, m>& pl, int N, const
   for (int it = 0; it < maxit && !done; ++it) {
     // regulation: stages beyond the last clamped one keep the unconstrained law — the sweep covers 0..klast only
     const int top = fixed.top_bit();
-    const int klast = trk ? N - 1 : (top < 0 ? -1 : top / m);
+    int klast = trk ? N - 1 : (top < 0 ? -1 : top / m);
+    if (klast + 1 >= L.kp) klast = N - 1;                  // S_{klast+1} is not stored that far out: full sweep
     if (!((n <= 4) ? clqr_backward<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)
                    : clqr_backward_call<n, m>(pb, pl, N, fixed, athi, ws, rf, klast)))
       flags |= FLAG_CHOL_FAIL;
