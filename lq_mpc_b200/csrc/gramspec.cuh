@@ -108,9 +108,8 @@ LQ_HD void gs_congruence2(const double* Ah, double* M3) {
   M3[6] = b * b; M3[7] = 2.0 * b * d; M3[8] = d * d;
 }
 
-template <int m>
-LQ_HD bool gs_stage2(const double* M3, const double* Bh, const double* Qw, const double* Rd, double sigma, bool last,
-                     double* P) {
+template <int m, bool LAST>
+LQ_HD bool gs_stage2(const double* M3, const double* Bh, const double* Qw, const double* Rd, double sigma, double* P) {
   constexpr int n = 2;
   double Y[n * m], L[m * m], Di[m];
   LQ_UNROLL for (int j = 0; j < m; ++j) {
@@ -123,7 +122,7 @@ LQ_HD bool gs_stage2(const double* M3, const double* Bh, const double* Qw, const
       L[i * m + j] = fma(sigma, acc, Rd[i * m + j]);
     }
   const bool ok = ldl_pos<m>(L, Di);
-  if (last) return ok;
+  if (LAST) return ok;                     // the last stage only decides its pivot (compile-time: the loop is peeled)
   LQ_UNROLL for (int i = 0; i < n; ++i)
     LQ_UNROLL for (int j = 1; j < m; ++j) {
       double sacc = Y[i * m + j];
@@ -221,11 +220,14 @@ LQ_HD GramSpectrum gram_spectrum(const double* Ah, const double* Bh, const doubl
     LQ_UNROLL for (int e = 0; e < n * n; ++e) { PH[e] = Q[e]; PC[e] = eye[e]; }
     bool okH = true, okC = true;
     if (n == 2) {                         // as below, with the 3 x 3 congruence map
-      for (int s = 1; s <= N; ++s) {
-        const bool last = (s == N);
-        okH = gs_stage2<m>(M3, Bh, Q, RdH, 1.0, last, PH) && okH;
-        okC = gs_stage2<m>(M3, Bh, eye, RdC, -1.0, last, PC) && okC;
+      for (int s = 1; s < N; ++s) {
+        okH = gs_stage2<m, false>(M3, Bh, Q, RdH, 1.0, PH) && okH;
+        okC = gs_stage2<m, false>(M3, Bh, eye, RdC, -1.0, PC) && okC;
         if (!okH && !okC) break;
+      }
+      if (okH || okC) {                   // stage N (peeled): pivots only
+        okH = gs_stage2<m, true>(M3, Bh, Q, RdH, 1.0, PH) && okH;
+        okC = gs_stage2<m, true>(M3, Bh, eye, RdC, -1.0, PC) && okC;
       }
     } else if (n <= 4) {                  // two independent recursions interleaved: instruction-level parallelism
       for (int s = 1; s <= N; ++s) {
