@@ -347,3 +347,50 @@ def test_k3_sturm_search_vs_lapack():
         check(d, np.concatenate(([0], np.sqrt(d[:-1] * d[1:]) * rng.uniform(0, 0.5, k - 1))))
         e = np.full(k, 0.3); e[0] = 0.0; e[k // 2] = 0.0
         check(np.concatenate((np.ones(k // 2), 5 * np.ones(k - k // 2))), e)
+
+
+def test_k2_math_long_horizon_late_saturation_vs_dense_qp():
+    """Round 2: the unconstrained cost-to-go is kept for the first 12 stages only and the stage loops run one stage ahead
+    of their loads. Long horizons whose inputs saturate LATE (working set beyond stage 12 -> the full N-stage sweep) and
+    early (-> restart from the stored S_k), marginally unstable plants, both vs the dense Cholesky + BVLS oracle; the
+    closed loop (certificate fast path with the register-held stage-0 gain) vs the same oracle stepped on the host."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(2024)
+    late = early = 0
+    for (n, m) in [(2, 1), (2, 2), (3, 1), (4, 2)]:
+        for rep in range(3):
+            N = int(rng.integers(20, 41))
+            A = rng.normal(size=(n, n))
+            A *= rng.uniform(0.95, 1.15) / np.max(np.abs(np.linalg.eigvals(A)))
+            B = rng.normal(size=(n, m))
+            Q = rng.uniform(0.5, 3) * np.eye(n); R = rng.uniform(0.1, 2) * np.eye(m)
+            lo, hi = -rng.uniform(0.02, 0.1, size=m), rng.uniform(0.02, 0.1, size=m)
+            S = 6
+            x0 = rng.normal(size=(n, S)) * rng.uniform(0.5, 3.0)
+            sol = hm.mpc(0, A, B, Q, R, Q, lo, hi, None, None, N, x0_soa=x0)
+            assert not np.any(sol["flags"] & ~2)
+            for s in range(S):
+                ur, Vr, _ = o.mpc_solve(N, A, B, Q, R, Q, lo, hi, x0[:, s], exact_fast=False)
+                assert abs(sol["V"][0, s] - Vr) < TOL * abs(Vr), (n, m, N, s)
+                assert np.max(np.abs(sol["u0"][0, :, s] - ur)) < TOL, (n, m, N, s)
+                H, gq, _ = o.condensed_qp(N, A, B, Q, R, Q, x0[:, s])
+                z = o.box_qp(H, gq, np.tile(lo, N), np.tile(hi, N)).reshape(N, m)
+                sat = np.flatnonzero(np.any((z <= lo + 1e-12) | (z >= hi - 1e-12), axis=1))
+                if sat.size:
+                    late += int(sat.max() >= 12)
+                    early += int(sat.max() < 12)
+    assert late >= 10 and early >= 1, (late, early)      # both restart routes were taken
+    # closed loop: T steps of the exact QP on the true plant (= model here), first steps saturated, later ones certified
+    A = np.array([[1, 0.7], [0.12, 0.4]]); B = np.array([[1], [1.2]])
+    Q = 2 * np.eye(2); R = np.eye(1); lo, hi = np.array([-0.1]), np.array([0.1])
+    x0 = np.array([[0.3], [0.25]])
+    N, T = 25, 30
+    sim = hm.mpc(1, A, B, Q, R, Q, lo, hi, None, None, N, T=T, x0_soa=x0)
+    x = x0[:, 0].copy()
+    J = float(x @ Q @ x)
+    for t in range(T):
+        u, _, _ = o.mpc_solve(N, A, B, Q, R, Q, lo, hi, x, exact_fast=False)
+        assert np.max(np.abs(sim["U"][t, :, 0] - u)) < 1e-9, t
+        x = A @ x + B @ u
+        J += float(x @ Q @ x + u @ R @ u)
+    assert abs(sim["J_T"][0] - J) < TOL * J
