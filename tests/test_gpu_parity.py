@@ -590,6 +590,46 @@ def test_clqr_stress_vs_dense_qp(engine):
     assert n_active > 100 and n_arb <= 10
 
 
+def test_clqr_long_horizon_late_saturation(engine):
+    """Round 2: the cost-to-go is stored for the first 12 stages only, the stage loops load one stage ahead, ring solves
+    skip the feasibility certificate. Long horizons on marginally unstable plants whose inputs saturate beyond stage 12
+    (full N-stage sweep) and before it (restart from the stored S_k): batched K2 vs the dense Cholesky + BVLS oracle, and
+    M_V over shared ring points == the maximum of the per-point solves."""
+    from oracle import np_oracle as o
+    rng = np.random.default_rng(2024)
+    late = early = 0
+    for (n, m) in [(2, 1), (2, 2), (3, 1), (4, 2)]:
+        for rep in range(2):
+            N = int(rng.integers(20, 41))
+            A = rng.normal(size=(n, n))
+            A *= rng.uniform(0.95, 1.15) / np.max(np.abs(np.linalg.eigvals(A)))
+            B = rng.normal(size=(n, m))
+            Q = rng.uniform(0.5, 3) * np.eye(n); R = rng.uniform(0.1, 2) * np.eye(m)
+            lo, hi = -rng.uniform(0.02, 0.1, size=m), rng.uniform(0.02, 0.1, size=m)
+            engine.set_problem(A, B, Q, R, Q, lo, hi, 10)
+            S = 40
+            x0 = rng.normal(size=(n, S)) * rng.uniform(0.5, 3.0)
+            got = engine.mpc_solve_batch(None, None, N, x0=x0, S=S)
+            V, u0, fl = (got[k].cpu().numpy() for k in ("V", "u0", "flags"))
+            assert not np.any(fl & ~2)
+            for s in range(0, S, 8):
+                ur, Vr, _ = o.mpc_solve(N, A, B, Q, R, Q, lo, hi, x0[:, s], exact_fast=False)
+                assert abs(V[0, s] - Vr) < TOL * abs(Vr), (n, m, N, s)
+                assert np.max(np.abs(u0[0, :, s] - ur)) < TOL, (n, m, N, s)
+                H, gq, _ = o.condensed_qp(N, A, B, Q, R, Q, x0[:, s])
+                z = o.box_qp(H, gq, np.tile(lo, N), np.tile(hi, N)).reshape(N, m)
+                sat = np.flatnonzero(np.any((z <= lo + 1e-12) | (z >= hi - 1e-12), axis=1))
+                if sat.size:
+                    late += int(sat.max() >= 12)
+                    early += int(sat.max() < 12)
+            pts = x0[:, :8].T.copy()
+            ring = engine.mpc_solve_batch(None, None, N, pts=pts, S=3, want=("V", "M_V"))
+            Vp, MV = ring["V"].cpu().numpy(), ring["M_V"].cpu().numpy()
+            assert np.max(np.abs(Vp[:, 0] - V[0, :8])) <= 1e-12 * np.max(np.abs(V[0, :8]))
+            assert np.all(MV == Vp.max(axis=0))
+    assert late >= 5 and early >= 1, (late, early)
+
+
 def test_clqr_max_working_set_size(engine):
     """N*m = 256 is the largest working set (256-bit mask): N = 64, 128, 256 (m = 1) and N = 64, 128 with m = 2 are
     solved exactly; N*m = 257 with an active bound must flag QP_MAXITER, return V = NaN and a first input clipped into
