@@ -116,7 +116,8 @@ int lqmpc_eval_batch_tiled(lqmpc_ctx* ctx, int64_t S, const double* dA, const do
                            int N_max, double* J, double* rho, double* ratio, double* V_N, int32_t* flags);
 
 /* Same from HOST buffers (array-of-matrices, ideally pinned; outputs [H][S] on the host): chunks are copied H2D,
- * evaluated and copied back on three streams so that PCIe traffic overlaps the kernels. Synchronises. */
+ * evaluated and copied back on three streams so that PCIe traffic overlaps the kernels. `chunk` (<= 0: 16 384) is the
+ * LARGEST chunk: sizes ramp up from chunk / 8 by 11/8 per chunk so that only a small first copy is exposed. Synchronises. */
 int lqmpc_eval_batch_tiled_host(lqmpc_ctx* ctx, int64_t S, const double* dA_host, const double* dB_host,
                                 const double* x0_host, int N_min, int N_max, double* J_host, double* rho_host,
                                 double* ratio_host, int32_t* flags_host, int64_t chunk);
