@@ -713,6 +713,10 @@ def measure_sweep(cx, wl, reps=1):
                      "achieved": k3_tf, "peak": peak, "unit": "TFLOP/s", "frac": k3_tf / peak if peak else None,
                      "algorithmic_flops": "2 searches x 43 probes x N stages x (4n^3+4n^2m+3nm^2+m^3/3) + DARE "
                                           "(k3_flops_per_eval), summed over N = 1..%d" % wl["nmax"],
+                     "executed_note": "at n = 2 the kernel EXECUTES fewer flops than this count (the congruence "
+                                      "P -> A'PA is one 3x3 map on the unique entries: 9 FMAs per stage instead of 14; the "
+                                      "last stage of a probe only decides its pivot), so `frac` overstates the pipe: "
+                                      "`pipe_active_ncu` is the measured occupancy of the FP64 pipe",
                      "pipe_active_ncu": PIPE_ACTIVE_NCU["cfg-sweep-f"][1],
                      "pipe_active_ncu_source": PIPE_ACTIVE_NCU["cfg-sweep-f"][0],
                      "traffic": _json_field("profiles/r02f_sweepN50_k2a_k2b_k3_traffic.json", "dram_bytes_per_launch"),
